@@ -1,0 +1,95 @@
+"""ctypes binding of ``libcnn_graph_b200.so`` (the C ABI declared in
+``include/cnn_graph_b200.h``).  There is NO fallback: if the library is missing or an
+entry point fails, a ``NativeError`` is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcnn_graph_b200.so')
+
+ABI_VERSION = 1
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_size_t = ctypes.c_size_t
+c_float = ctypes.c_float
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/cnn_graph_b200.h one to one
+_SIGNATURES = {
+    'cg_abi_version': (c_int, []),
+    'cg_last_error': (ctypes.c_char_p, []),
+    'cg_graph_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_i64, c_void_p, c_void_p, c_void_p]),
+    'cg_graph_destroy': (c_int, [c_void_p]),
+    'cg_graph_info': (c_int, [c_void_p, ctypes.POINTER(c_i64)]),
+    'cg_cheb_basis': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    'cg_cheb_filter_fwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    'cg_cheb_filter_bwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    'cg_cheb_filter_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_size_t, c_int, c_void_p]),
+    'cg_cheb_filter_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    'cg_bias_act_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'cg_bias_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p]),
+    'cg_pool_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'cg_pool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'cg_perm_data': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    'cg_lstm_gates_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
+                                  c_void_p]),
+    'cg_lstm_gates_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    'cg_host_metis_one_level': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
+                                        c_void_p, ctypes.POINTER(c_i64)]),
+    'cg_host_perm_level': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the native library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            'native library %s is missing -- build it with `python -m cnn_graph_b200.build` '
+            '(there is no CPU / PyTorch fallback for the hot path)' % LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as exc:
+            raise NativeError('native library does not export %s' % name) from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = handle.cg_abi_version()
+    if got != ABI_VERSION:
+        raise NativeError('ABI mismatch: library reports %d, binding expects %d' % (got, ABI_VERSION))
+    _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    """Turn a non-zero status of the C ABI into a Python exception."""
+    if rc != 0:
+        msg = lib().cg_last_error()
+        raise NativeError('%s failed (status %d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / numpy array, or None."""
+    if t is None:
+        return None
+    if hasattr(t, 'data_ptr'):
+        return t.data_ptr()
+    return t.ctypes.data

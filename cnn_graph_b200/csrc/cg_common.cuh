@@ -1,0 +1,90 @@
+// Shared declarations of the cnn_graph_b200 native library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cnn_graph_b200.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void cg_set_error(const char *fmt, ...);
+
+#define CG_CHECK_CUDA(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            cg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,              \
+                         cudaGetErrorString(_e));                                        \
+            return CG_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define CG_REQUIRE(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            cg_set_error(__VA_ARGS__);                                                   \
+            return CG_ERR_ARG;                                                           \
+        }                                                                                \
+    } while (0)
+
+#define CG_LAUNCH_CHECK() CG_CHECK_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------
+// packed operator
+// ---------------------------------------------------------------------------
+// One orientation of the rescaled Laplacian (L~ or L~^T), resident in HBM.
+//   CSR  : rowptr[M+1], col[nnz], val[nnz]          -- streaming kernels
+//   ELL  : ell[M_pad * width] of {val, col} pairs, column-major (slot-major:
+//          entry j of row m at ell[j * M_pad + m]); padding entries are
+//          {0.0f, 0} so they can be applied unconditionally.  Built only when
+//          it is small enough to live in shared memory.
+struct CgCsr {
+    int *rowptr = nullptr;
+    int *col = nullptr;
+    float *val = nullptr;
+    float2 *ell = nullptr;   // .x = value, .y = __int_as_float(col)
+    int width = 0;           // max row length (ELL width)
+    int m_pad = 0;           // rows padded to a multiple of 32
+};
+
+struct cg_graph {
+    int M = 0;
+    int64_t nnz = 0;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;   // max dynamic shared memory per block
+    CgCsr fwd;               // L~
+    CgCsr adj;               // L~^T
+    bool onchip = false;     // ELL of both orientations fits the SMEM kernels
+};
+
+static inline const CgCsr &cg_side(const cg_graph *g, int transpose) { return transpose ? g->adj : g->fwd; }
+
+// ---------------------------------------------------------------------------
+// internal entry points shared between translation units
+// ---------------------------------------------------------------------------
+// Internal layout of a signal slab: S[m][c], c in [0, C), C = N * F, column
+// c = n * F + f (one vertex row holds all signals' features contiguously).
+// A Chebyshev stack is K such slabs: stack[k][m][c].
+
+// stack[0] must already hold the input slab; fills stack[1..K-1].
+int cg_run_basis(const cg_graph *g, int transpose, float *stack, int64_t C, int K, cudaStream_t s, int flags);
+
+// in[A][B][F] -> out[B][A][F]
+int cg_run_permute_abf(const float *in, float *out, int64_t A, int64_t B, int F, cudaStream_t s);
+
+// y[(n*M+m)][fo] = sum_{k,f} stack[k][m*N+n][f] * W[f*K+k][fo]      (contract)
+int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, int F, int Fout, int K,
+                    bool w_transposed, cudaStream_t s);
+
+// dW[(a*K+k)][b] (or [(b*K+k)][a] when swap) = sum_{m,n} stack[k][m*N+n][a] * T[(n*M+m)][b]
+size_t cg_stack_t_plain_workspace(int N, int M, int Fa, int Fb, int K, int sm_count);
+int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, int M, int Fa, int Fb, int K,
+                         bool swap, float *workspace, int sm_count, cudaStream_t s);
+
+static inline int64_t cg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

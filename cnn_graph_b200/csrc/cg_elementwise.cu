@@ -1,0 +1,379 @@
+// Bandwidth-bound helpers around the filter: layout permutes, bias + activation
+// (lib/models.py:226-247), permuted pooling (lib/models.py:249-266), perm_data
+// (lib/coarsening.py:219-240) and the gconv-LSTM gate math (lib/gconv_lstm.py:185-215).
+// All are single-pass, coalesced along the innermost (feature) axis, 128-bit where
+// the feature count allows.
+#include "cg_common.cuh"
+
+static inline unsigned grid_for(int64_t work, int threads, int64_t cap = 148LL * 32) {
+    int64_t b = cg_ceil_div(work, threads);
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (unsigned)b;
+}
+
+// ---------------------------------------------------------------------------
+// in[A][B][F] -> out[B][A][F]
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_permute_direct(const float *__restrict__ in, float *__restrict__ out, int64_t A, int64_t B, int Fv) {
+    // Fv = F / VEC vectors per chunk
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const int64_t total = A * B * Fv;
+    const V *src = reinterpret_cast<const V *>(in);
+    V *dst = reinterpret_cast<V *>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i % Fv;
+        const int64_t ba = i / Fv;
+        const int64_t a = ba % A, b = ba / A;
+        dst[i] = src[(a * B + b) * Fv + f];
+    }
+}
+
+// small F: 32 x 32 tile of F-float elements through shared memory
+__global__ void __launch_bounds__(256)
+k_permute_tiled(const float *__restrict__ in, float *__restrict__ out, int64_t A, int64_t B, int F) {
+    extern __shared__ float tile[];            // [32][32 * F + 1]
+    const int pitch = 32 * F + 1;
+    const int64_t a0 = (int64_t)blockIdx.y * 32, b0 = (int64_t)blockIdx.x * 32;
+    const int nb = (int)min((int64_t)32, B - b0), na = (int)min((int64_t)32, A - a0);
+    const int run_in = nb * F;                  // contiguous floats per a-row of the tile
+    for (int r = threadIdx.y; r < na; r += blockDim.y)
+        for (int i = threadIdx.x; i < run_in; i += blockDim.x)
+            tile[r * pitch + i] = in[((a0 + r) * B + b0) * F + i];
+    __syncthreads();
+    const int run_out = na * F;
+    for (int r = threadIdx.y; r < nb; r += blockDim.y)
+        for (int i = threadIdx.x; i < run_out; i += blockDim.x) {
+            const int a = i / F, f = i - a * F;
+            out[((b0 + r) * A + a0) * F + i] = tile[a * pitch + r * F + f];
+        }
+}
+
+int cg_run_permute_abf(const float *in, float *out, int64_t A, int64_t B, int F, cudaStream_t s) {
+    if (A == 1 || B == 1) {
+        CG_CHECK_CUDA(cudaMemcpyAsync(out, in, sizeof(float) * (size_t)(A * B * F), cudaMemcpyDeviceToDevice, s));
+        return CG_OK;
+    }
+    if (F >= 8) {
+        const bool v4 = F % 4 == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+        if (v4)
+            k_permute_direct<4><<<grid_for(A * B * (F / 4), 256), 256, 0, s>>>(in, out, A, B, F / 4);
+        else
+            k_permute_direct<1><<<grid_for(A * B * F, 256), 256, 0, s>>>(in, out, A, B, F);
+    } else {
+        dim3 grid((unsigned)cg_ceil_div(B, 32), (unsigned)cg_ceil_div(A, 32));
+        CG_REQUIRE(grid.y <= 65535, "permute: A too large (%lld)", (long long)A);
+        const size_t smem = sizeof(float) * 32 * (32 * F + 1);
+        k_permute_tiled<<<grid, dim3(32, 8), smem, s>>>(in, out, A, B, F);
+    }
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// bias + activation
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    return v;
+}
+__device__ __forceinline__ float act_bwd_from_out(float y, float g, int act) {
+    if (act == 1) return y > 0.f ? g : 0.f;
+    if (act == 2) return g * (1.f - y * y);
+    return g;
+}
+
+// period = number of bias entries (F for kind 1, M*F for kind 2, 0 for none)
+__global__ void __launch_bounds__(256)
+k_bias_act_fwd(const float *__restrict__ x, const float *__restrict__ bias, float *__restrict__ y,
+               int64_t total, int64_t period, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (period > 0) v += bias[i % period];
+        y[i] = act_fwd(v, act);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bias_act_fwd_v4(const float4 *__restrict__ x, const float4 *__restrict__ bias, float4 *__restrict__ y,
+                  int64_t total4, int64_t period4, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        if (period4 > 0) {
+            const float4 b = bias[i % period4];
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        y[i] = make_float4(act_fwd(v.x, act), act_fwd(v.y, act), act_fwd(v.z, act), act_fwd(v.w, act));
+    }
+}
+
+extern "C" int cg_bias_act_fwd(const float *x, const float *bias, float *y, int N, int M, int F, int bias_kind,
+                               int act, void *stream) {
+    CG_REQUIRE(x && y, "cg_bias_act_fwd: NULL tensor");
+    CG_REQUIRE(bias_kind >= 0 && bias_kind <= 2 && act >= 0 && act <= 2, "cg_bias_act_fwd: bad bias_kind/act");
+    CG_REQUIRE(bias_kind == 0 || bias, "cg_bias_act_fwd: bias is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = (int64_t)N * M * F;
+    if (total == 0) return CG_OK;
+    const int64_t period = bias_kind == 0 ? 0 : (bias_kind == 1 ? F : (int64_t)M * F);
+    const bool v4 = F % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)bias)) & 15) == 0;
+    if (v4)
+        k_bias_act_fwd_v4<<<grid_for(total / 4, 256), 256, 0, s>>>((const float4 *)x, (const float4 *)bias, (float4 *)y,
+                                                                   total / 4, period / 4, act);
+    else
+        k_bias_act_fwd<<<grid_for(total, 256), 256, 0, s>>>(x, bias, y, total, period, act);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// gx = gy * act'(y); dbias[c] += sum over rows of gx[r][c], c in [0, period).
+// The tensor is viewed as [R][period]; block = TR x TC threads over a column tile.
+__global__ void __launch_bounds__(256)
+k_bias_act_bwd(const float *__restrict__ y, const float *__restrict__ gy, float *__restrict__ gx,
+               float *__restrict__ dbias, int64_t R, int64_t period, int act, int tc, int64_t rows_per_block) {
+    __shared__ float red[256];
+    const int tx = threadIdx.x % tc, ty = threadIdx.x / tc, tr = 256 / tc;
+    const int64_t c = (int64_t)blockIdx.x * tc + tx;
+    const int64_t r_beg = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(R, r_beg + rows_per_block);
+    float acc = 0.f;
+    if (c < period) {
+        for (int64_t r = r_beg + ty; r < r_end; r += tr) {
+            const int64_t i = r * period + c;
+            const float g = act_bwd_from_out(y[i], gy[i], act);
+            gx[i] = g;
+            acc += g;
+        }
+    }
+    if (dbias == nullptr) return;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0 && c < period) {
+        float t = 0.f;
+        for (int q = 0; q < tr; ++q) t += red[q * tc + tx];
+        atomicAdd(dbias + c, t);
+    }
+}
+
+extern "C" int cg_bias_act_bwd(const float *y, const float *gy, float *gx, float *dbias, int N, int M, int F,
+                               int bias_kind, int act, void *stream) {
+    CG_REQUIRE(y && gy && gx, "cg_bias_act_bwd: NULL tensor");
+    CG_REQUIRE(bias_kind >= 0 && bias_kind <= 2 && act >= 0 && act <= 2, "cg_bias_act_bwd: bad bias_kind/act");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = (int64_t)N * M * F;
+    if (total == 0) return CG_OK;
+    if (bias_kind == 0) dbias = nullptr;
+    // view as [R][period]; without bias reduce nothing and use a wide period for coalescing
+    int64_t period = bias_kind == 2 ? (int64_t)M * F : F;
+    int64_t R = total / period;
+    if (dbias) CG_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)period, s));
+    int tc = 256;
+    while (tc > 1 && tc / 2 >= period) tc /= 2;
+    const int64_t col_blocks = cg_ceil_div(period, tc);
+    int64_t row_blocks = cg_ceil_div(148LL * 16, col_blocks);
+    const int tr = 256 / tc;
+    if (row_blocks > cg_ceil_div(R, tr)) row_blocks = cg_ceil_div(R, tr);
+    if (row_blocks < 1) row_blocks = 1;
+    if (row_blocks > 65535) row_blocks = 65535;
+    const int64_t rows_per_block = cg_ceil_div(R, row_blocks);
+    dim3 grid((unsigned)col_blocks, (unsigned)cg_ceil_div(R, rows_per_block));
+    k_bias_act_bwd<<<grid, 256, 0, s>>>(y, gy, gx, dbias, R, period, act, tc, rows_per_block);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pooling over p consecutive vertices
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pool_fwd(const float *__restrict__ x, float *__restrict__ y, uint8_t *__restrict__ amax, int64_t NJ, int F, int p,
+           int kind) {
+    // one thread per output element (nj, f); x viewed as [NJ][p][F]
+    const int64_t total = NJ * F;
+    const float inv = 1.0f / (float)p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nj = i / F;
+        const int f = (int)(i - nj * F);
+        const float *src = x + nj * p * F + f;
+        if (kind == 1) {
+            float best = src[0];
+            int arg = 0;
+            for (int q = 1; q < p; ++q) {
+                const float v = src[(int64_t)q * F];
+                if (v > best) { best = v; arg = q; }
+            }
+            y[i] = best;
+            if (amax) amax[i] = (uint8_t)arg;
+        } else {
+            float sum = 0.f;
+            for (int q = 0; q < p; ++q) sum += src[(int64_t)q * F];
+            y[i] = sum * inv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pool_bwd(const float *__restrict__ gy, const uint8_t *__restrict__ amax, float *__restrict__ gx, int64_t NJ, int F,
+           int p, int kind) {
+    const int64_t total = NJ * F;
+    const float inv = 1.0f / (float)p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nj = i / F;
+        const int f = (int)(i - nj * F);
+        float *dst = gx + nj * p * F + f;
+        const float g = gy[i];
+        if (kind == 1) {
+            const int arg = amax[i];
+            for (int q = 0; q < p; ++q) dst[(int64_t)q * F] = q == arg ? g : 0.f;
+        } else {
+            const float v = g * inv;
+            for (int q = 0; q < p; ++q) dst[(int64_t)q * F] = v;
+        }
+    }
+}
+
+extern "C" int cg_pool_fwd(const float *x, float *y, uint8_t *amax, int N, int M, int F, int p, int kind,
+                           void *stream) {
+    CG_REQUIRE(x && y, "cg_pool_fwd: NULL tensor");
+    CG_REQUIRE(kind == 1 || kind == 2, "cg_pool_fwd: kind must be 1 (max) or 2 (avg)");
+    CG_REQUIRE(p >= 1 && p <= 256 && M % p == 0, "cg_pool_fwd: p=%d must divide M=%d and be <= 256", p, M);
+    const int64_t NJ = (int64_t)N * (M / p);
+    if (NJ * F == 0) return CG_OK;
+    k_pool_fwd<<<grid_for(NJ * F, 256), 256, 0, (cudaStream_t)stream>>>(x, y, amax, NJ, F, p, kind);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+extern "C" int cg_pool_bwd(const float *gy, const uint8_t *amax, float *gx, int N, int M, int F, int p, int kind,
+                           void *stream) {
+    CG_REQUIRE(gy && gx, "cg_pool_bwd: NULL tensor");
+    CG_REQUIRE(kind == 1 || kind == 2, "cg_pool_bwd: kind must be 1 (max) or 2 (avg)");
+    CG_REQUIRE(kind == 2 || amax, "cg_pool_bwd: max pooling needs the argmax tensor");
+    CG_REQUIRE(p >= 1 && p <= 256 && M % p == 0, "cg_pool_bwd: p=%d must divide M=%d and be <= 256", p, M);
+    const int64_t NJ = (int64_t)N * (M / p);
+    if (NJ * F == 0) return CG_OK;
+    k_pool_bwd<<<grid_for(NJ * F, 256), 256, 0, (cudaStream_t)stream>>>(gy, amax, gx, NJ, F, p, kind);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// perm_data
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_perm_data(const float *__restrict__ x, const int *__restrict__ perm, float *__restrict__ out, int64_t N, int M,
+            int Mnew) {
+    const int64_t total = N * Mnew;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / Mnew;
+        const int j = perm[i - n * Mnew];
+        out[i] = (j >= 0 && j < M) ? x[n * M + j] : 0.f;
+    }
+}
+
+extern "C" int cg_perm_data(const float *x, const int32_t *perm, float *out, int64_t N, int M, int Mnew,
+                            void *stream) {
+    CG_REQUIRE(x && perm && out, "cg_perm_data: NULL tensor");
+    CG_REQUIRE(Mnew >= M && M > 0, "cg_perm_data: need Mnew >= M > 0 (M=%d Mnew=%d)", M, Mnew);
+    if (N == 0) return CG_OK;
+    k_perm_data<<<grid_for(N * Mnew, 256), 256, 0, (cudaStream_t)stream>>>(x, perm, out, N, M, Mnew);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// gconv-LSTM gates
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(256)
+k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ bias, const float *__restrict__ c,
+                 float *__restrict__ new_c, float *__restrict__ new_h, int64_t R, int H, int variant) {
+    const int64_t total = R * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / H;
+        const int h = (int)(i - r * H);
+        const float *p = pre + r * 4 * H;
+        const float az = p[h] + bias[h], ai = p[H + h] + bias[H + h];
+        const float af = p[2 * H + h] + bias[2 * H + h], ao = p[3 * H + h] + bias[3 * H + h];
+        const float z = variant == 0 ? tanf(az) : tanhf(az);
+        const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
+        const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
+        const float cn = fg * c[i] + ig * z;
+        new_c[i] = cn;
+        new_h[i] = o * tanhf(cn);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ bias, const float *__restrict__ c,
+                 const float *__restrict__ new_c, const float *__restrict__ g_h, const float *__restrict__ g_c,
+                 float *__restrict__ g_pre, float *__restrict__ g_cprev, float *__restrict__ d_bias, int64_t R, int H,
+                 int variant, int64_t rows_per_block) {
+    // block covers rows [blockIdx.y * rows_per_block, ...) x columns h = blockIdx.x * 256 + tid
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const int64_t r_beg = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(R, r_beg + rows_per_block);
+    float sz = 0.f, si = 0.f, sf = 0.f, so = 0.f;
+    const float bz = bias[h], bi = bias[H + h], bf = bias[2 * H + h], bo = bias[3 * H + h];
+    for (int64_t r = r_beg; r < r_end; ++r) {
+        const int64_t i = r * H + h;
+        const float *p = pre + r * 4 * H;
+        const float az = p[h] + bz, ai = p[H + h] + bi, af = p[2 * H + h] + bf, ao = p[3 * H + h] + bo;
+        const float z = variant == 0 ? tanf(az) : tanhf(az);
+        const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
+        const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
+        const float tc = tanhf(new_c[i]);
+        const float gh = g_h ? g_h[i] : 0.f;
+        const float dcn = (g_c ? g_c[i] : 0.f) + gh * o * (1.f - tc * tc);
+        const float d_o = gh * tc;
+        const float dz = dcn * ig, di = dcn * z, df = dcn * c[i];
+        const float gz = dz * (variant == 0 ? (1.f + z * z) : (1.f - z * z));
+        const float go = d_o * (variant == 0 ? (1.f - o * o) : o * (1.f - o));
+        const float gi = di * ig * (1.f - ig), gf = df * fg * (1.f - fg);
+        float *q = g_pre + r * 4 * H;
+        q[h] = gz; q[H + h] = gi; q[2 * H + h] = gf; q[3 * H + h] = go;
+        g_cprev[i] = dcn * fg;
+        sz += gz; si += gi; sf += gf; so += go;
+    }
+    if (d_bias) {
+        atomicAdd(d_bias + h, sz);
+        atomicAdd(d_bias + H + h, si);
+        atomicAdd(d_bias + 2 * H + h, sf);
+        atomicAdd(d_bias + 3 * H + h, so);
+    }
+}
+
+extern "C" int cg_lstm_gates_fwd(const float *pre, const float *bias, const float *c, float *new_c, float *new_h,
+                                 int64_t R, int H, int variant, void *stream) {
+    CG_REQUIRE(pre && bias && c && new_c && new_h, "cg_lstm_gates_fwd: NULL tensor");
+    CG_REQUIRE(variant == 0 || variant == 1, "cg_lstm_gates_fwd: variant must be 0 (fork) or 1 (standard)");
+    if (R * H == 0) return CG_OK;
+    k_lstm_gates_fwd<<<grid_for(R * H, 256), 256, 0, (cudaStream_t)stream>>>(pre, bias, c, new_c, new_h, R, H, variant);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+extern "C" int cg_lstm_gates_bwd(const float *pre, const float *bias, const float *c, const float *new_c,
+                                 const float *g_h, const float *g_c, float *g_pre, float *g_cprev, float *d_bias,
+                                 int64_t R, int H, int variant, void *stream) {
+    CG_REQUIRE(pre && bias && c && new_c && g_pre && g_cprev, "cg_lstm_gates_bwd: NULL tensor");
+    CG_REQUIRE(variant == 0 || variant == 1, "cg_lstm_gates_bwd: variant must be 0 (fork) or 1 (standard)");
+    if (R * H == 0) return CG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_bias) CG_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * 4 * (size_t)H, s));
+    const int64_t col_blocks = cg_ceil_div(H, 256);
+    int64_t row_blocks = cg_ceil_div(148LL * 8, col_blocks);
+    if (row_blocks > R) row_blocks = R;
+    if (row_blocks > 65535) row_blocks = 65535;
+    const int64_t rows_per_block = cg_ceil_div(R, row_blocks);
+    dim3 grid((unsigned)col_blocks, (unsigned)cg_ceil_div(R, rows_per_block));
+    k_lstm_gates_bwd<<<grid, 256, 0, s>>>(pre, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant,
+                                          rows_per_block);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

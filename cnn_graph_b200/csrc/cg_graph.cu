@@ -1,0 +1,151 @@
+// Packed rescaled-Laplacian handle: host CSR -> device CSR + ELL, both orientations.
+// Replaces the per-call COO -> tf.SparseTensor -> tf.sparse_reorder staging of the
+// reference (lib/models.py:198-201, lib/filter.py:66-70).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cg_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *cg_last_error(void) { return g_err; }
+extern "C" int cg_abi_version(void) { return CG_ABI_VERSION; }
+
+// ELL budget: the on-chip kernels keep one orientation's ELL plus two signal
+// slabs in shared memory; the operator may take at most this many bytes.
+static const size_t kEllSmemBudget = 160 * 1024;
+
+static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &rowptr,
+                       const std::vector<int> &col, const std::vector<float> &val, bool want_ell) {
+    CG_CHECK_CUDA(cudaMalloc(&dst.rowptr, sizeof(int) * (size_t)(M + 1)));
+    CG_CHECK_CUDA(cudaMalloc(&dst.col, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1)));
+    CG_CHECK_CUDA(cudaMalloc(&dst.val, sizeof(float) * (size_t)std::max<int64_t>(nnz, 1)));
+    CG_CHECK_CUDA(cudaMemcpy(dst.rowptr, rowptr.data(), sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice));
+    if (nnz > 0) {
+        CG_CHECK_CUDA(cudaMemcpy(dst.col, col.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CG_CHECK_CUDA(cudaMemcpy(dst.val, val.data(), sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    int width = 0;
+    for (int m = 0; m < M; ++m) width = std::max(width, rowptr[m + 1] - rowptr[m]);
+    dst.width = width;
+    dst.m_pad = (M + 31) / 32 * 32;
+    if (want_ell && width > 0) {
+        std::vector<float2> ell((size_t)dst.m_pad * width, make_float2(0.f, 0.f));  // {0.0f, col 0}
+        for (int m = 0; m < M; ++m) {
+            int j = 0;
+            for (int e = rowptr[m]; e < rowptr[m + 1]; ++e, ++j) {
+                float2 v;
+                v.x = val[e];
+                int c = col[e];
+                memcpy(&v.y, &c, sizeof(int));
+                ell[(size_t)j * dst.m_pad + m] = v;
+            }
+        }
+        CG_CHECK_CUDA(cudaMalloc(&dst.ell, sizeof(float2) * ell.size()));
+        CG_CHECK_CUDA(cudaMemcpy(dst.ell, ell.data(), sizeof(float2) * ell.size(), cudaMemcpyHostToDevice));
+    }
+    return CG_OK;
+}
+
+static void free_side(CgCsr &s) {
+    cudaFree(s.rowptr);
+    cudaFree(s.col);
+    cudaFree(s.val);
+    cudaFree(s.ell);
+    s = CgCsr();
+}
+
+extern "C" int cg_graph_create(cg_graph_t **out, int M, int64_t nnz, const int32_t *indptr,
+                               const int32_t *indices, const float *values) {
+    CG_REQUIRE(out != nullptr, "cg_graph_create: out is NULL");
+    *out = nullptr;
+    CG_REQUIRE(M > 0, "cg_graph_create: M must be positive (got %d)", M);
+    CG_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "cg_graph_create: nnz out of range");
+    CG_REQUIRE(indptr && (nnz == 0 || (indices && values)), "cg_graph_create: NULL CSR arrays");
+    CG_REQUIRE(indptr[0] == 0 && indptr[M] == nnz, "cg_graph_create: indptr[0] must be 0 and indptr[M] == nnz");
+
+    std::vector<int> rowptr(indptr, indptr + M + 1), col(indices, indices + nnz);
+    std::vector<float> val(values, values + nnz);
+    for (int m = 0; m < M; ++m) {
+        CG_REQUIRE(rowptr[m] <= rowptr[m + 1], "cg_graph_create: indptr not monotone at row %d", m);
+        for (int e = rowptr[m]; e < rowptr[m + 1]; ++e) {
+            CG_REQUIRE(col[e] >= 0 && col[e] < M, "cg_graph_create: column index %d out of range in row %d", col[e], m);
+            CG_REQUIRE(e == rowptr[m] || col[e - 1] < col[e],
+                       "cg_graph_create: row %d is not sorted / has duplicates (sum duplicates and sort first)", m);
+        }
+    }
+    // transpose (stable counting sort keeps rows sorted inside every column)
+    std::vector<int> t_rowptr(M + 1, 0), t_col(nnz);
+    std::vector<float> t_val(nnz);
+    for (int64_t e = 0; e < nnz; ++e) t_rowptr[col[e] + 1]++;
+    for (int m = 0; m < M; ++m) t_rowptr[m + 1] += t_rowptr[m];
+    {
+        std::vector<int> fill(t_rowptr.begin(), t_rowptr.end() - 1);
+        for (int m = 0; m < M; ++m)
+            for (int e = rowptr[m]; e < rowptr[m + 1]; ++e) {
+                int p = fill[col[e]]++;
+                t_col[p] = m;
+                t_val[p] = val[e];
+            }
+    }
+    int w_f = 0, w_t = 0;
+    for (int m = 0; m < M; ++m) {
+        w_f = std::max(w_f, rowptr[m + 1] - rowptr[m]);
+        w_t = std::max(w_t, t_rowptr[m + 1] - t_rowptr[m]);
+    }
+    size_t m_pad = (size_t)(M + 31) / 32 * 32;
+    bool onchip = M <= 65535 && m_pad * (size_t)std::max(w_f, w_t) * sizeof(float2) <= kEllSmemBudget;
+
+    cg_graph *g = new cg_graph();
+    g->M = M;
+    g->nnz = nnz;
+    g->onchip = onchip;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e != cudaSuccess) {
+        delete g;
+        cg_set_error("cg_graph_create: no CUDA device: %s", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g->device);
+    g->sm_count = v > 0 ? v : 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device);
+    g->smem_optin = (size_t)v;
+    int rc = upload_side(g->fwd, M, nnz, rowptr, col, val, onchip);
+    if (rc == CG_OK) rc = upload_side(g->adj, M, nnz, t_rowptr, t_col, t_val, onchip);
+    if (rc != CG_OK) {
+        free_side(g->fwd);
+        free_side(g->adj);
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return CG_OK;
+}
+
+extern "C" int cg_graph_destroy(cg_graph_t *g) {
+    if (!g) return CG_OK;
+    free_side(g->fwd);
+    free_side(g->adj);
+    delete g;
+    return CG_OK;
+}
+
+extern "C" int cg_graph_info(const cg_graph_t *g, int64_t info[5]) {
+    CG_REQUIRE(g && info, "cg_graph_info: NULL argument");
+    info[0] = g->M;
+    info[1] = g->nnz;
+    info[2] = g->fwd.width;
+    info[3] = g->adj.width;
+    info[4] = g->onchip ? 1 : 0;
+    return CG_OK;
+}

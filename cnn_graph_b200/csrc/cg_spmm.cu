@@ -1,0 +1,248 @@
+// K1: Chebyshev recurrence  X_k = 2 L~ X_{k-1} - X_{k-2}  (lib/graph.py:241-258,
+// lib/models.py:205-217, lib/filter.py:80-87) on a slab layout S[m][c].
+//
+// Two kernels:
+//   k_basis_onchip  -- all K steps in ONE launch.  A CTA owns CW columns; the whole
+//                      operator (ELL) and two M x CW signal slabs live in shared
+//                      memory, neighbours are gathered with 128-bit LDS, every
+//                      step's slab is streamed out to HBM with 128-bit stores.
+//                      HBM traffic = read X once + write the K-1 new slabs.
+//   k_spmm_step     -- one step per launch for operators too large for SMEM
+//                      (CSR from HBM/L2, 128-bit gathers along the column axis).
+#include "cg_common.cuh"
+
+// ---------------------------------------------------------------------------
+// streaming step:  out = alpha * L X1 - X0   (X0 may be null -> out = alpha * L X1)
+// ---------------------------------------------------------------------------
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> {
+    using type = float4;
+};
+template <>
+struct VecT<1> {
+    using type = float;
+};
+
+__device__ __forceinline__ void fma_acc(float4 &a, float s, const float4 &x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+    a.z = fmaf(s, x.z, a.z);
+    a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void fma_acc(float &a, float s, const float &x) { a = fmaf(s, x, a); }
+__device__ __forceinline__ float4 axmb(float alpha, const float4 &a, const float4 &b) {
+    return make_float4(fmaf(alpha, a.x, -b.x), fmaf(alpha, a.y, -b.y), fmaf(alpha, a.z, -b.z), fmaf(alpha, a.w, -b.w));
+}
+__device__ __forceinline__ float axmb(float alpha, const float &a, const float &b) { return fmaf(alpha, a, -b); }
+__device__ __forceinline__ float4 scale(float alpha, const float4 &a) {
+    return make_float4(alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w);
+}
+__device__ __forceinline__ float scale(float alpha, const float &a) { return alpha * a; }
+template <typename T>
+__device__ __forceinline__ T zero_v();
+template <>
+__device__ __forceinline__ float4 zero_v<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <>
+__device__ __forceinline__ float zero_v<float>() { return 0.f; }
+
+// block = 256 threads = (256 / lpr) rows x lpr lanes; lane handles VEC columns.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_spmm_step(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
+            const float *__restrict__ X1, const float *__restrict__ X0, float *__restrict__ out, int M,
+            int64_t C, float alpha, int lpr) {
+    using V = typename VecT<VEC>::type;
+    const int lane = threadIdx.x % lpr;
+    const int rows_per_block = 256 / lpr;
+    const int64_t m = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / lpr;
+    const int64_t c = ((int64_t)blockIdx.y * lpr + lane) * VEC;
+    if (m >= M || c >= C) return;
+    const int beg = rowptr[m], end = rowptr[m + 1];
+    V acc = zero_v<V>();
+    int e = beg;
+    for (; e + 3 < end; e += 4) {
+        const int c0 = col[e], c1 = col[e + 1], c2 = col[e + 2], c3 = col[e + 3];
+        const float v0 = val[e], v1 = val[e + 1], v2 = val[e + 2], v3 = val[e + 3];
+        const V x0 = *reinterpret_cast<const V *>(X1 + (int64_t)c0 * C + c);
+        const V x1 = *reinterpret_cast<const V *>(X1 + (int64_t)c1 * C + c);
+        const V x2 = *reinterpret_cast<const V *>(X1 + (int64_t)c2 * C + c);
+        const V x3 = *reinterpret_cast<const V *>(X1 + (int64_t)c3 * C + c);
+        fma_acc(acc, v0, x0);
+        fma_acc(acc, v1, x1);
+        fma_acc(acc, v2, x2);
+        fma_acc(acc, v3, x3);
+    }
+    for (; e < end; ++e) {
+        const V x = *reinterpret_cast<const V *>(X1 + (int64_t)col[e] * C + c);
+        fma_acc(acc, val[e], x);
+    }
+    V r;
+    if (X0 != nullptr) {
+        const V old = *reinterpret_cast<const V *>(X0 + m * C + c);
+        r = axmb(alpha, acc, old);
+    } else {
+        r = scale(alpha, acc);
+    }
+    *reinterpret_cast<V *>(out + m * C + c) = r;
+}
+
+static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, float *out, int64_t C,
+                       float alpha, cudaStream_t s) {
+    const bool vec4 = (C % 4 == 0) && ((((uintptr_t)X1 | (uintptr_t)out | (uintptr_t)X0) & 15) == 0);
+    const int vec = vec4 ? 4 : 1;
+    int64_t lanes_needed = cg_ceil_div(C, vec);
+    int lpr = 32;
+    while (lpr > 1 && lpr / 2 >= lanes_needed) lpr /= 2;
+    const int rows_per_block = 256 / lpr;
+    dim3 grid((unsigned)cg_ceil_div(M, rows_per_block), (unsigned)cg_ceil_div(lanes_needed, lpr));
+    CG_REQUIRE(grid.y <= 65535, "spmm_step: too many columns (C=%lld)", (long long)C);
+    if (vec4)
+        k_spmm_step<4><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
+    else
+        k_spmm_step<1><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// on-chip fused recurrence
+// ---------------------------------------------------------------------------
+// shared memory:  ell[width][m_pad] float2 | len[m_pad] int | S0[M][CW] | S1[M][CW]
+constexpr int kOnchipThreads = 512;
+
+template <int CW>
+__global__ void __launch_bounds__(kOnchipThreads, 1)
+k_basis_onchip(const float2 *__restrict__ ell_g, const int *__restrict__ rowptr, int width, int m_pad, int M,
+               const float *__restrict__ in, float *__restrict__ stack, int64_t C, int K, int write_slab0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LPR = CW / 4;                 // lanes per row
+    constexpr int RPP = kOnchipThreads / LPR;   // rows per pass
+    float2 *ell = reinterpret_cast<float2 *>(smem_raw);
+    int *len = reinterpret_cast<int *>(ell + (size_t)width * m_pad);
+    float *S0 = reinterpret_cast<float *>(len + m_pad);
+    float *S1 = S0 + (size_t)M * CW;
+
+    const int tid = threadIdx.x;
+    const int lane = tid % LPR;
+    const int row0 = tid / LPR;
+    const int64_t cbase = (int64_t)blockIdx.x * CW + lane * 4;
+    const bool cvalid = cbase < C;              // C % 4 == 0 -> the whole float4 is in range
+    const int64_t slab = (int64_t)M * C;
+
+    for (int i = tid; i < width * m_pad; i += kOnchipThreads) ell[i] = ell_g[i];
+    for (int m = tid; m < m_pad; m += kOnchipThreads) len[m] = m < M ? rowptr[m + 1] - rowptr[m] : 0;
+    for (int m = row0; m < M; m += RPP) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cvalid) v = *reinterpret_cast<const float4 *>(in + (int64_t)m * C + cbase);
+        *reinterpret_cast<float4 *>(S0 + m * CW + lane * 4) = v;
+        if (write_slab0 && cvalid) *reinterpret_cast<float4 *>(stack + (int64_t)m * C + cbase) = v;
+    }
+    __syncthreads();
+
+    float *prev = S0, *cur = S1;                // cur holds X_{k-2} and receives X_k
+    for (int k = 1; k < K; ++k) {
+        float *dst = stack + (int64_t)k * slab;
+        for (int m = row0; m < M; m += RPP) {
+            const int n = len[m];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = 0;
+            for (; j + 1 < n; j += 2) {
+                const float2 e0 = ell[j * m_pad + m];
+                const float2 e1 = ell[(j + 1) * m_pad + m];
+                const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
+                const float4 x1 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e1.y) * CW + lane * 4);
+                fma_acc(acc, e0.x, x0);
+                fma_acc(acc, e1.x, x1);
+            }
+            if (j < n) {
+                const float2 e0 = ell[j * m_pad + m];
+                const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
+                fma_acc(acc, e0.x, x0);
+            }
+            float4 *slot = reinterpret_cast<float4 *>(cur + m * CW + lane * 4);
+            float4 r = acc;
+            if (k > 1) r = axmb(2.0f, acc, *slot);
+            *slot = r;
+            if (cvalid) *reinterpret_cast<float4 *>(dst + (int64_t)m * C + cbase) = r;
+        }
+        __syncthreads();
+        float *t = prev;
+        prev = cur;
+        cur = t;
+    }
+}
+
+// widest column group (multiple of 8, power of two, <= 128) whose two slabs fit next to the ELL
+static int onchip_cw(const cg_graph *g, const CgCsr &L, int64_t C) {
+    if (!g->onchip || L.ell == nullptr || C % 4 != 0) return 0;
+    const size_t fixed = (size_t)L.width * L.m_pad * sizeof(float2) + (size_t)L.m_pad * sizeof(int);
+    const size_t limit = g->smem_optin;
+    int best = 0;
+    for (int cw = 8; cw <= 128; cw *= 2) {
+        if (fixed + 2 * (size_t)g->M * cw * sizeof(float) <= limit) best = cw;
+    }
+    // do not pick a group much wider than the problem
+    while (best > 8 && best / 2 >= C) best /= 2;
+    return best;
+}
+
+template <int CW>
+static int launch_onchip(const cg_graph *g, const CgCsr &L, const float *in, float *stack, int64_t C, int K,
+                         int write_slab0, cudaStream_t s) {
+    const size_t smem = (size_t)L.width * L.m_pad * sizeof(float2) + (size_t)L.m_pad * sizeof(int) +
+                        2 * (size_t)g->M * CW * sizeof(float);
+    CG_CHECK_CUDA(cudaFuncSetAttribute(k_basis_onchip<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)cg_ceil_div(C, CW);
+    k_basis_onchip<CW><<<grid, kOnchipThreads, smem, s>>>(L.ell, L.rowptr, L.width, L.m_pad, g->M, in, stack, C, K,
+                                                          write_slab0);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// `in` is slab 0 (may alias stack); fills stack[1..K-1] (and stack[0] when in != stack).
+static int run_basis_from(const cg_graph *g, int transpose, const float *in, float *stack, int64_t C, int K,
+                          cudaStream_t s, int flags) {
+    const CgCsr &L = cg_side(g, transpose);
+    const int M = g->M;
+    const int64_t slab = (int64_t)M * C;
+    const bool aligned = ((((uintptr_t)in) | ((uintptr_t)stack)) & 15) == 0;
+    int cw = (flags & CG_FILTER_FORCE_STREAMING) || !aligned ? 0 : onchip_cw(g, L, C);
+    if (L.width == 0) cw = 0;   // empty operator: streaming path handles it (all zeros)
+    if ((flags & CG_FILTER_FORCE_ONCHIP) && cw == 0 && L.width > 0) {
+        cg_set_error("cheb basis: on-chip kernel requested but operator/columns do not fit (M=%d width=%d C=%lld)",
+                     M, L.width, (long long)C);
+        return CG_ERR_ARG;
+    }
+    if (cw > 0 && K > 1) {
+        const int w0 = in != stack;
+        switch (cw) {
+            case 8: return launch_onchip<8>(g, L, in, stack, C, K, w0, s);
+            case 16: return launch_onchip<16>(g, L, in, stack, C, K, w0, s);
+            case 32: return launch_onchip<32>(g, L, in, stack, C, K, w0, s);
+            case 64: return launch_onchip<64>(g, L, in, stack, C, K, w0, s);
+            default: return launch_onchip<128>(g, L, in, stack, C, K, w0, s);
+        }
+    }
+    if (in != stack)
+        CG_CHECK_CUDA(cudaMemcpyAsync(stack, in, sizeof(float) * (size_t)slab, cudaMemcpyDeviceToDevice, s));
+    for (int k = 1; k < K; ++k) {
+        const float *x1 = stack + (int64_t)(k - 1) * slab;
+        const float *x0 = k > 1 ? stack + (int64_t)(k - 2) * slab : nullptr;
+        int rc = launch_step(L, M, x1, x0, stack + (int64_t)k * slab, C, k > 1 ? 2.0f : 1.0f, s);
+        if (rc != CG_OK) return rc;
+    }
+    return CG_OK;
+}
+
+int cg_run_basis(const cg_graph *g, int transpose, float *stack, int64_t C, int K, cudaStream_t s, int flags) {
+    return run_basis_from(g, transpose, stack, stack, C, K, s, flags);
+}
+
+extern "C" int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float *dev_Xt, int64_t C,
+                             int K, void *stream) {
+    CG_REQUIRE(g && dev_X && dev_Xt, "cg_cheb_basis: NULL argument");
+    CG_REQUIRE(C > 0 && K >= 1, "cg_cheb_basis: C and K must be positive (C=%lld K=%d)", (long long)C, K);
+    return run_basis_from(g, transpose, dev_X, dev_Xt, C, K, (cudaStream_t)stream, CG_FILTER_DEFAULT);
+}

@@ -1,0 +1,348 @@
+"""PyTorch-facing operators of the hot path: thin ``autograd.Function`` wrappers that hand
+raw device pointers and the current CUDA stream to the C ABI (``include/cnn_graph_b200.h``).
+PyTorch is plumbing only (device memory, streams, autograd tape); every kernel is native.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import _native
+from ._native import check, ptr
+
+FILTER_DEFAULT = 0
+FILTER_FORCE_STREAMING = 1
+FILTER_FORCE_ONCHIP = 2
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _native.NativeError('cnn_graph_b200 ops need CUDA tensors (no CPU fallback); got device %s' % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------
+# rescaled Laplacian handle
+# ---------------------------------------------------------------------------------------
+
+def rescale_csr(L, lmax=2):
+    """L~ = L / (lmax/2) - I as a fresh sorted float32 CSR (lib/graph.py:232-238).
+
+    Unlike the reference (lib/models.py:196 aliases the caller's data, lib/filter.py:65 does
+    not copy at all) the caller's matrix is never modified; identical for lmax = 2.
+    """
+    L = scipy.sparse.csr_matrix(L, dtype=np.float32, copy=True)
+    M = L.shape[0]
+    L /= lmax / 2
+    L -= scipy.sparse.identity(M, format='csr', dtype=L.dtype)
+    L = scipy.sparse.csr_matrix(L)
+    L.sum_duplicates()
+    L.sort_indices()
+    return L
+
+
+class GraphHandle:
+    """Packed L~ / L~^T resident on the current CUDA device (``cg_graph_t``)."""
+
+    def __init__(self, L_rescaled):
+        L = scipy.sparse.csr_matrix(L_rescaled, dtype=np.float32)
+        L.sum_duplicates()
+        L.sort_indices()
+        if L.shape[0] != L.shape[1]:
+            raise ValueError('Laplacian must be square, got %r' % (L.shape,))
+        if not torch.cuda.is_available():
+            raise _native.NativeError('cnn_graph_b200 needs a CUDA device (no CPU fallback)')
+        self.M = int(L.shape[0])
+        self.nnz = int(L.nnz)
+        indptr = np.ascontiguousarray(L.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(L.indices, dtype=np.int32)
+        data = np.ascontiguousarray(L.data, dtype=np.float32)
+        self.device = torch.cuda.current_device()
+        h = ctypes.c_void_p()
+        check(_native.lib().cg_graph_create(ctypes.byref(h), self.M, self.nnz, indptr.ctypes.data,
+                                            indices.ctypes.data, data.ctypes.data), 'cg_graph_create')
+        self._h = h
+
+    @classmethod
+    def from_laplacian(cls, L, lmax=2):
+        return cls(rescale_csr(L, lmax))
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise _native.NativeError('graph handle already destroyed')
+        return self._h
+
+    def info(self):
+        out = (ctypes.c_int64 * 5)()
+        check(_native.lib().cg_graph_info(self.handle, out), 'cg_graph_info')
+        return {'M': out[0], 'nnz': out[1], 'width': out[2], 'width_t': out[3], 'onchip': bool(out[4])}
+
+    def close(self):
+        if getattr(self, '_h', None) is not None:
+            _native.lib().cg_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handle_cache = {}
+
+
+def get_handle(L, lmax=2):
+    """Handle for a scipy Laplacian, cached per (object, lmax, device) -- the reference
+    re-stages L on every filter call site (lib/models.py:196-201)."""
+    if isinstance(L, GraphHandle):
+        return L
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    key = (id(L), float(lmax), dev)
+    hit = _handle_cache.get(key)
+    if hit is not None:
+        ref, nnz, h = hit
+        if ref() is L and nnz == L.nnz:
+            return h
+    h = GraphHandle.from_laplacian(L, lmax)
+    try:
+        ref = weakref.ref(L, lambda _r, k=key: _handle_cache.pop(k, None))
+    except TypeError:
+        ref = (lambda obj: (lambda: obj))(L)
+    _handle_cache[key] = (ref, L.nnz, h)
+    return h
+
+
+# ---------------------------------------------------------------------------------------
+# Chebyshev basis (graph.chebyshev)
+# ---------------------------------------------------------------------------------------
+
+def cheb_basis(handle, X, K, transpose=False):
+    """Xt [K, M, C] = T_k(L~) X for X [M, C] on the device (lib/graph.py:241-258)."""
+    _require_cuda(X)
+    X = _f32c(X)
+    M, C = X.shape
+    if M != handle.M:
+        raise ValueError('X has %d rows, graph has %d vertices' % (M, handle.M))
+    Xt = torch.empty((K, M, C), dtype=torch.float32, device=X.device)
+    check(_native.lib().cg_cheb_basis(handle.handle, int(bool(transpose)), ptr(X), ptr(Xt), C, K, _stream()),
+          'cg_cheb_basis')
+    return Xt
+
+
+# ---------------------------------------------------------------------------------------
+# Chebyshev filter
+# ---------------------------------------------------------------------------------------
+
+class ChebFilterFn(torch.autograd.Function):
+    """y = chebyshev5(x; L~, W)  (lib/models.py:192-224).  x [N,M,Fin], W [Fin*K, Fout]."""
+
+    @staticmethod
+    def forward(ctx, x, W, handle, K, grad_x, flags):
+        _require_cuda(x, W)
+        x = _f32c(x)
+        W = _f32c(W)
+        N, M, Fin = x.shape
+        if M != handle.M:
+            raise ValueError('x has %d vertices, graph has %d' % (M, handle.M))
+        if W.shape[0] != Fin * K:
+            raise ValueError('W must be [Fin*K, Fout] = [%d, *], got %r' % (Fin * K, tuple(W.shape)))
+        Fout = W.shape[1]
+        lib = _native.lib()
+        y = torch.empty((N, M, Fout), dtype=torch.float32, device=x.device)
+        nbytes = lib.cg_cheb_filter_fwd_workspace_bytes(handle.handle, N, Fin, Fout, K, flags)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
+        check(lib.cg_cheb_filter_fwd(handle.handle, ptr(x), ptr(W), ptr(y), N, Fin, Fout, K, ptr(ws), nbytes,
+                                     flags, _stream()), 'cg_cheb_filter_fwd')
+        ctx.save_for_backward(x, W)
+        ctx.handle, ctx.K, ctx.grad_x, ctx.flags = handle, K, grad_x, flags
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        handle, K, flags = ctx.handle, ctx.K, ctx.flags
+        gy = _f32c(gy)
+        N, M, Fin = x.shape
+        Fout = W.shape[1]
+        lib = _native.lib()
+        need_dx = bool(ctx.needs_input_grad[0] and ctx.grad_x)
+        dx = torch.empty_like(x) if need_dx else None
+        dW = torch.empty_like(W)
+        nbytes = lib.cg_cheb_filter_bwd_workspace_bytes(handle.handle, N, Fin, Fout, K, int(need_dx), flags)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
+        check(lib.cg_cheb_filter_bwd(handle.handle, ptr(x), ptr(W), ptr(gy), ptr(dx), ptr(dW), N, Fin, Fout, K,
+                                     ptr(ws), nbytes, flags, _stream()), 'cg_cheb_filter_bwd')
+        return dx, dW, None, None, None, None
+
+
+def cheb_filter(x, W, L, K, lmax=2, grad_x=True, flags=FILTER_DEFAULT):
+    """Functional Chebyshev filter; ``L`` is a scipy Laplacian (rescaled here) or a GraphHandle."""
+    return ChebFilterFn.apply(x, W, get_handle(L, lmax), int(K), bool(grad_x), int(flags))
+
+
+# ---------------------------------------------------------------------------------------
+# bias + activation, pooling
+# ---------------------------------------------------------------------------------------
+
+ACT = {'none': 0, 'relu': 1, 'tanh': 2}
+
+
+class BiasActFn(torch.autograd.Function):
+    """act(x + bias) with bias None | [F] | [M, F]  (lib/models.py:226-247)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, act):
+        _require_cuda(x, bias)
+        x = _f32c(x)
+        N, M, F = x.shape
+        kind = 0
+        if bias is not None:
+            bias = _f32c(bias)
+            if bias.numel() == F:
+                kind = 1
+            elif bias.numel() == M * F:
+                kind = 2
+            else:
+                raise ValueError('bias must have F=%d or M*F=%d entries, got %d' % (F, M * F, bias.numel()))
+        y = torch.empty_like(x)
+        check(_native.lib().cg_bias_act_fwd(ptr(x), ptr(bias), ptr(y), N, M, F, kind, act, _stream()),
+              'cg_bias_act_fwd')
+        ctx.save_for_backward(y)
+        ctx.kind, ctx.act = kind, act
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = _f32c(gy)
+        N, M, F = y.shape
+        gx = torch.empty_like(y)
+        db = None
+        if ctx.kind != 0 and ctx.needs_input_grad[1]:
+            db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=y.device)
+        check(_native.lib().cg_bias_act_bwd(ptr(y), ptr(gy), ptr(gx), ptr(db), N, M, F, ctx.kind, ctx.act,
+                                            _stream()), 'cg_bias_act_bwd')
+        return gx, db, None
+
+
+def bias_act(x, bias, act):
+    return BiasActFn.apply(x, bias, ACT[act] if isinstance(act, str) else int(act))
+
+
+class PoolFn(torch.autograd.Function):
+    """mpool1 (kind 1) / apool1 (kind 2) over p consecutive vertices (lib/models.py:249-266)."""
+
+    @staticmethod
+    def forward(ctx, x, p, kind):
+        _require_cuda(x)
+        x = _f32c(x)
+        N, M, F = x.shape
+        if M % p != 0:
+            raise ValueError('pool size %d does not divide M=%d' % (p, M))
+        y = torch.empty((N, M // p, F), dtype=torch.float32, device=x.device)
+        amax = torch.empty((N, M // p, F), dtype=torch.uint8, device=x.device) if kind == 1 else None
+        check(_native.lib().cg_pool_fwd(ptr(x), ptr(y), ptr(amax), N, M, F, p, kind, _stream()), 'cg_pool_fwd')
+        ctx.amax, ctx.p, ctx.kind, ctx.M = amax, p, kind, M
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = _f32c(gy)
+        N, Mp, F = gy.shape
+        gx = torch.empty((N, ctx.M, F), dtype=torch.float32, device=gy.device)
+        check(_native.lib().cg_pool_bwd(ptr(gy), ptr(ctx.amax), ptr(gx), N, ctx.M, F, ctx.p, ctx.kind, _stream()),
+              'cg_pool_bwd')
+        return gx, None, None
+
+
+def pool(x, p, kind):
+    if p <= 1:
+        return x
+    return PoolFn.apply(x, int(p), 1 if kind in (1, 'max') else 2)
+
+
+def pool_argmax(x, p):
+    """Pooled values and first-max indices (uint8) -- used by the bit-exact parity tests."""
+    _require_cuda(x)
+    x = _f32c(x)
+    N, M, F = x.shape
+    y = torch.empty((N, M // p, F), dtype=torch.float32, device=x.device)
+    amax = torch.empty((N, M // p, F), dtype=torch.uint8, device=x.device)
+    check(_native.lib().cg_pool_fwd(ptr(x), ptr(y), ptr(amax), N, M, F, p, 1, _stream()), 'cg_pool_fwd')
+    return y, amax
+
+
+# ---------------------------------------------------------------------------------------
+# perm_data on the device
+# ---------------------------------------------------------------------------------------
+
+def perm_data_device(x, perm):
+    """out[:, i] = x[:, perm[i]] if perm[i] < M else 0  (lib/coarsening.py:219-240), float32."""
+    _require_cuda(x)
+    x = _f32c(x)
+    N, M = x.shape
+    perm_t = torch.as_tensor(np.asarray(perm, dtype=np.int32), device=x.device)
+    out = torch.empty((N, perm_t.numel()), dtype=torch.float32, device=x.device)
+    check(_native.lib().cg_perm_data(ptr(x), ptr(perm_t), ptr(out), N, M, perm_t.numel(), _stream()), 'cg_perm_data')
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# gconv-LSTM gates
+# ---------------------------------------------------------------------------------------
+
+class LstmGatesFn(torch.autograd.Function):
+    """Gate nonlinearities + state update of GConvLSTMCell (lib/gconv_lstm.py:185-215).
+
+    pre [N, M, 4H] (z|i|f|o), bias [4H], c [N, M, H]  ->  new_h, new_c.
+    """
+
+    @staticmethod
+    def forward(ctx, pre, bias, c, variant):
+        _require_cuda(pre, bias, c)
+        pre, bias, c = _f32c(pre), _f32c(bias), _f32c(c)
+        H = c.shape[-1]
+        R = c.numel() // H
+        new_c = torch.empty_like(c)
+        new_h = torch.empty_like(c)
+        check(_native.lib().cg_lstm_gates_fwd(ptr(pre), ptr(bias), ptr(c), ptr(new_c), ptr(new_h), R, H, variant,
+                                              _stream()), 'cg_lstm_gates_fwd')
+        ctx.save_for_backward(pre, bias, c, new_c)
+        ctx.variant = variant
+        return new_h, new_c
+
+    @staticmethod
+    def backward(ctx, g_h, g_c):
+        pre, bias, c, new_c = ctx.saved_tensors
+        H = c.shape[-1]
+        R = c.numel() // H
+        g_h = _f32c(g_h) if g_h is not None else None
+        g_c = _f32c(g_c) if g_c is not None else None
+        g_pre = torch.empty_like(pre)
+        g_cprev = torch.empty_like(c)
+        d_bias = torch.empty_like(bias)
+        check(_native.lib().cg_lstm_gates_bwd(ptr(pre), ptr(bias), ptr(c), ptr(new_c), ptr(g_h), ptr(g_c),
+                                              ptr(g_pre), ptr(g_cprev), ptr(d_bias), R, H, ctx.variant, _stream()),
+              'cg_lstm_gates_bwd')
+        return g_pre, d_bias, g_cprev, None
+
+
+def lstm_gates(pre, bias, c, variant='fork'):
+    v = {'fork': 0, 'standard': 1}[variant] if isinstance(variant, str) else int(variant)
+    return LstmGatesFn.apply(pre, bias, c, v)

@@ -1,0 +1,155 @@
+/*
+ * cnn_graph_b200 -- C ABI of the B200-native Chebyshev graph-convolution hot path.
+ *
+ * The reference (xu-wang11/cnn_graph) has no FFI: its hot path sits behind a
+ * Python name-binding surface (getattr(self, 'chebyshev5'), getattr(filter,
+ * 'cheby_conv'), the RNN-cell protocol).  This header is the boundary a
+ * maintainer of the reference binds with ctypes from those Python methods
+ * (INTEGRATION.md shows the stubs).  Every entry point cites the reference
+ * function it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - all tensors are dense, contiguous, float32 unless stated; "dev" pointers
+ *     are CUDA device pointers owned by the caller, "host" pointers are CPU;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, non-zero on error; cg_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - no function allocates device memory behind the caller's back except
+ *     cg_graph_create (the packed operator, freed by cg_graph_destroy);
+ *     scratch is passed in by the caller, sized by the *_workspace_bytes query;
+ *   - thread-compatible: no global state besides the per-thread error string.
+ *
+ * Tensor layouts (reference layouts, unchanged):
+ *   x   [N, M, Fin]      lib/models.py:193   (N signals, M vertices, Fin features)
+ *   W   [Fin*K, Fout]    lib/models.py:222   row = fin*K + k  (fin-major)
+ *   y   [N, M, Fout]     lib/models.py:224
+ *   Xt  [K, M, C]        lib/graph.py:248    Chebyshev basis of X [M, C]
+ */
+#ifndef CNN_GRAPH_B200_H
+#define CNN_GRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_ABI_VERSION 1
+
+/* ---- status ------------------------------------------------------------ */
+enum {
+    CG_OK = 0,
+    CG_ERR_ARG = 1,      /* bad argument (shape, null pointer, unsupported size)   */
+    CG_ERR_CUDA = 2,     /* CUDA runtime error; message carries cudaGetErrorString */
+    CG_ERR_WORKSPACE = 3 /* workspace too small                                     */
+};
+
+int cg_abi_version(void);
+const char *cg_last_error(void);
+
+/* ---- rescaled Laplacian handle ---------------------------------------- */
+/* Opaque packed operator: L~ and its transpose, CSR + ELL, resident in HBM.
+ * Replaces the per-call COO -> tf.SparseTensor -> tf.sparse_reorder staging of
+ * lib/models.py:198-201 and lib/filter.py:66-70.  The caller passes the
+ * ALREADY RESCALED matrix (graph.rescale_L, lib/graph.py:232-238) as host CSR
+ * with sorted column indices. */
+typedef struct cg_graph cg_graph_t;
+
+int cg_graph_create(cg_graph_t **out, int M, int64_t nnz, const int32_t *host_indptr,
+                    const int32_t *host_indices, const float *host_values);
+int cg_graph_destroy(cg_graph_t *g);
+/* info[0]=M, [1]=nnz, [2]=max row length of L~, [3]=max row length of L~^T,
+ * [4]=1 if the operator fits the shared-memory (on-chip) kernels, else 0     */
+int cg_graph_info(const cg_graph_t *g, int64_t info[5]);
+
+/* ---- Chebyshev basis ---------------------------------------------------- */
+/* graph.chebyshev(L, X, K)  lib/graph.py:241-258:
+ *   Xt[0] = X, Xt[1] = L~ X, Xt[k] = 2 L~ Xt[k-1] - Xt[k-2].
+ * dev_X [M, C], dev_Xt [K, M, C].  transpose != 0 applies L~^T instead.      */
+int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float *dev_Xt,
+                  int64_t C, int K, void *stream);
+
+/* ---- Chebyshev filter (chebyshev5 / chebyshev2 / cheby_conv) ---------- */
+/* Forward: lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95
+ *   y[n,m,fo] = sum_{fin,k} (T_k(L~) x)[n,m,fin] * W[fin*K+k, fo]
+ * Backward (TF autodiff of the above, lib/graph_model.py:296):
+ *   dx[n,m,fin] = sum_{k,fo} (T_k(L~^T) gy)[n,m,fo] * W[fin*K+k, fo]
+ *   dW[fin*K+k, fo] = sum_{n,m} (T_k(L~) x)[n,m,fin] * gy[n,m,fo]
+ * dev_dx may be NULL (first layer / chebyshev2, which has no x-gradient,
+ * lib/models.py:183).  dev_dW is overwritten (not accumulated).
+ * `flags`: CG_FILTER_* bits.                                                 */
+enum {
+    CG_FILTER_DEFAULT = 0,
+    CG_FILTER_FORCE_STREAMING = 1, /* never use the on-chip (SMEM-resident) kernels */
+    CG_FILTER_FORCE_ONCHIP = 2     /* fail with CG_ERR_ARG if the on-chip kernels do not fit */
+};
+size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
+size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
+                                          int need_dx, int flags);
+int cg_cheb_filter_fwd(const cg_graph_t *g, const float *dev_x, const float *dev_W, float *dev_y,
+                       int N, int Fin, int Fout, int K, void *dev_workspace, size_t workspace_bytes,
+                       int flags, void *stream);
+int cg_cheb_filter_bwd(const cg_graph_t *g, const float *dev_x, const float *dev_W, const float *dev_gy,
+                       float *dev_dx, float *dev_dW, int N, int Fin, int Fout, int K,
+                       void *dev_workspace, size_t workspace_bytes, int flags, void *stream);
+
+/* ---- bias + activation (b1relu / b1tanh / b2relu) ---------------------- */
+/* lib/models.py:226-247.  bias_kind: 0 none (fork b1relu), 1 per filter
+ * [F] (upstream b1relu, b1tanh), 2 per vertex and filter [M, F] (b2relu).
+ * act: 0 identity, 1 relu, 2 tanh.
+ * Backward takes the forward OUTPUT y (relu: mask y > 0; tanh: 1 - y^2).
+ * dev_dbias may be NULL; when given it is overwritten.                       */
+int cg_bias_act_fwd(const float *dev_x, const float *dev_bias, float *dev_y, int N, int M, int F,
+                    int bias_kind, int act, void *stream);
+int cg_bias_act_bwd(const float *dev_y, const float *dev_gy, float *dev_gx, float *dev_dbias,
+                    int N, int M, int F, int bias_kind, int act, void *stream);
+
+/* ---- permuted pooling (mpool1 / apool1) -------------------------------- */
+/* lib/models.py:249-266: max / mean over p consecutive (permuted) vertices.
+ * kind: 1 max, 2 avg.  dev_argmax [N, M/p, F] uint8 (max only, may be NULL on
+ * avg): index in 0..p-1 of the FIRST maximal element (TF MaxPoolGrad routing). */
+int cg_pool_fwd(const float *dev_x, float *dev_y, uint8_t *dev_argmax, int N, int M, int F, int p,
+                int kind, void *stream);
+int cg_pool_bwd(const float *dev_gy, const uint8_t *dev_argmax, float *dev_gx, int N, int M, int F,
+                int p, int kind, void *stream);
+
+/* ---- coarsening.perm_data ---------------------------------------------- */
+/* lib/coarsening.py:219-240: out[:, i] = x[:, perm[i]] if perm[i] < M else 0.
+ * dev_x [N, M], dev_perm [Mnew] int32, dev_out [N, Mnew] (float32 on device;
+ * the host API converts to the reference's float64).                         */
+int cg_perm_data(const float *dev_x, const int32_t *dev_perm, float *dev_out, int64_t N, int M,
+                 int Mnew, void *stream);
+
+/* ---- graph-conv LSTM gates --------------------------------------------- */
+/* lib/gconv_lstm.py:185-215 (variant 0, 'fork': z = tan, o = tanh) and
+ * lib/gconvRNN.py:189-213 (variant 1, 'standard': z = tanh, o = sigmoid).
+ * dev_pre [R, 4H] holds the four summed filter outputs, gate order z,i,f,o
+ * (R = N*M rows); dev_bias [4H]; dev_c [R, H].  Writes new c and new h.
+ * Backward: given g_h, g_c (either may be NULL) produces g_pre [R,4H],
+ * g_cprev [R,H]; d_bias [4H] is overwritten when non-NULL.                   */
+int cg_lstm_gates_fwd(const float *dev_pre, const float *dev_bias, const float *dev_c, float *dev_new_c,
+                      float *dev_new_h, int64_t R, int H, int variant, void *stream);
+int cg_lstm_gates_bwd(const float *dev_pre, const float *dev_bias, const float *dev_c,
+                      const float *dev_new_c, const float *dev_g_h, const float *dev_g_c,
+                      float *dev_g_pre, float *dev_g_cprev, float *dev_d_bias, int64_t R, int H,
+                      int variant, void *stream);
+
+/* ---- host-side native loops of the coarsening -------------------------- */
+/* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32
+ * arithmetic in the reference's order, including the reference's row-table
+ * off-by-one.  rr sorted; arrays are host pointers; cluster_id has N = rr[nnz-1]+1
+ * entries.  Returns the number of clusters through *nclusters.               */
+int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int64_t *cc, const float *vv,
+                            const int64_t *rid, int64_t n_rid, const float *weights,
+                            int32_t *cluster_id, int64_t *nclusters);
+/* lib/coarsening.py:179-204 (one level of compute_perm): children of the
+ * vertices listed in `order` (length n_order) under `parent` (length n_parent),
+ * singletons padded with fake ids starting at n_parent.  out has 2*n_order.  */
+int cg_host_perm_level(const int64_t *parent, int64_t n_parent, const int64_t *order, int64_t n_order,
+                       int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNN_GRAPH_B200_H */
