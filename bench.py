@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Benchmark of the Chebyshev graph-conv hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Workload (config.workload): BASELINE config C2 -- MNIST-shaped synthetic data on the 28x28
+8-NN grid graph, 4-level Graclus coarsening (M = 992 after fake-node padding), cgcnn
+GC32-P4-GC64-P4-FC512-FC10 with K = 25 Chebyshev terms (nips2016/mnist.ipynb cells 1,3,14,17).
+One "step" = one full training step of that model on one batch: forward, softmax
+cross-entropy + L2, backward, momentum-SGD update (and, for N > 1 GPUs, the all-reduce of the
+weight gradients).  Every graph-conv kernel is native (cnn_graph_b200/csrc); the two dense
+FC layers, the loss and the optimiser are stock PyTorch.
+
+Prints ONE JSON line (rank 0).  `value`: samples/s with the batch resident in HBM;
+`e2e`: the same step driven from pinned HOST buffers (raw 784-pixel images -> H2D -> device
+perm_data -> train step -> loss read back) every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F, K, P, MFC = [32, 64], [25, 25], [4, 4], [512, 10]
+HYPER = dict(regularization=5e-4, dropout=0.5, learning_rate=0.02, decay_rate=0.95, momentum=0.9)
+
+
+def build_graphs(seed=0):
+    from cnn_graph_b200.lib import coarsening, graph
+    np.random.seed(seed)
+    A = graph.adjacency(*graph.distance_sklearn_metrics(graph.grid(28), k=8, metric='euclidean'))
+    graphs, perm = coarsening.coarsen(A, levels=4, self_connections=False, verbose=False)
+    L = [graph.laplacian(g, normalized=True) for g in graphs]
+    return L, perm
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work of the native kernels in one training step
+# ------------------------------------------------------------------------------------------
+def step_work(L, N):
+    """Per kernel name: list of (algorithmic bytes, algorithmic flops) per filter call."""
+    from cnn_graph_b200 import ops
+    lay = []
+    for i, Fin, Fout in ((0, 1, F[0]), (2, F[0], F[1])):
+        Lr = ops.rescale_csr(L[i], 2)
+        lay.append((Lr.shape[0], Lr.nnz, Fin, Fout))
+
+    def b_stream(M, nnz, C, Kk):      # sum_{k=1}^{K-1} B_step; first step reads one operand fewer
+        b_step = 8 * nnz + 4 * (M + 1) + 12 * M * C
+        return (Kk - 1) * b_step - 4 * M * C
+
+    def spmm_flops(M, nnz, C, Kk):
+        return (Kk - 1) * 2 * nnz * C + (Kk - 2) * 2 * M * C
+
+    (M1, z1, _, _), (M2, z2, _, _) = lay
+    basis = [  # (M, nnz, C) of every basis computation in a step
+        (M1, z1, N * 1), (M2, z2, N * F[0]),            # forward layer 1, layer 2
+        (M2, z2, N * F[1]), (M1, z1, N * 1),            # backward: T_k(L~^T) gy of layer 2; X-stack of layer 1
+    ]
+    g1 = 2.0 * N * M1 * 1 * K[0] * F[0]
+    g2 = 2.0 * N * M2 * F[0] * K[1] * F[1]
+    return {
+        'basis_onchip': [(b_stream(M, z, C, 25), spmm_flops(M, z, C, 25)) for M, z, C in basis],
+        'contract': [(0, g1), (0, g2), (0, g2)],          # y1, y2, dx2
+        'stack_t_plain': [(0, g2), (0, g1)],              # dW2, dW1
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's numpy/scipy path, restated in oracle/
+# ------------------------------------------------------------------------------------------
+def cpu_training_steps(L, batch, steps, warmup, seed=0):
+    from oracle import model_ref
+    rng = np.random.RandomState(seed)
+    Ls = [L[0], L[2]]
+    params = model_ref.init_params(Ls, F, K, P, MFC, seed=seed)
+    velocity = {}
+    x = rng.uniform(0, 1, (batch, L[0].shape[0])).astype(np.float32)
+    labels = rng.randint(0, 10, batch)
+    times = []
+    for it in range(warmup + steps):
+        masks = [(rng.uniform(size=(batch, MFC[0])) < HYPER['dropout']).astype(np.float32) / HYPER['dropout']]
+        t0 = time.perf_counter()
+        loss, grads = model_ref.forward_backward(params, Ls, F, K, P, MFC, x, labels, HYPER['regularization'],
+                                                 'mpool1', masks)
+        model_ref.sgd_momentum_step(params, grads, velocity, HYPER['learning_rate'], HYPER['momentum'])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, float(loss)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    L, _ = build_graphs()
+    batch = args.ref_batch
+    times, _ = cpu_training_steps(L, batch, args.steps, args.warmup)
+    total = float(np.sum(times))
+    value = batch * len(times) / total
+    cores = os.cpu_count()
+    line = {
+        'impl': 'reference', 'metric': 'cheb_graphconv_train_samples_per_sec', 'value': value, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_step': batch,
+                   'note': 'reference CPU path: TensorFlow is not installable, so the reference\'s own numpy/scipy '
+                           'code path (graph.chebyshev-style scipy CSR SpMM + numpy BLAS), restated in oracle/, is timed'},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d steps of batch %d (full train step: fwd+loss+bwd+update)' % (len(times), batch)},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD = ('C2 MNIST-shaped synthetic: 28x28 8-NN grid graph, 4-level coarsening (M=992), '
+            'cgcnn F=[32,64] K=[25,25] p=[4,4] M=[512,10], full training step')
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from cnn_graph_b200 import _native, dist as cgdist, ops
+    from cnn_graph_b200.lib import models
+
+    rank, world, local_rank = cgdist.init_from_env('nccl')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the hot path has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    lib = _native.lib()
+    L, perm = build_graphs()
+    B = args.batch
+    torch.manual_seed(1234 + rank)
+    model = models.cgcnn(L, F=F, K=K, p=P, M=MFC, filter='chebyshev5', brelu='b1relu', pool='mpool1',
+                         batch_size=B, decay_steps=600, **HYPER)
+    if world > 1:
+        # identical initial weights on every rank, then one flat all-reduce of the gradients per step
+        for p_ in model.store.parameters():
+            torch.distributed.broadcast(p_.data, src=0)
+        model.grad_hook = cgdist.GradAllReducer(average=True)
+
+    # synthetic batch: raw 28x28 "images" U[0,1) on the host (pinned) and their permuted copy in HBM
+    gen = torch.Generator().manual_seed(99 + rank)
+    raw_host = torch.rand((B, 784), generator=gen).pin_memory()
+    labels_host = torch.randint(0, 10, (B,), generator=gen).pin_memory()
+    x_dev = ops.perm_data_device(raw_host.to(device), perm)
+    y_dev = labels_host.to(device)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
+
+    def step_resident():
+        return model.train_step(x_dev, y_dev)
+
+    def step_e2e():
+        xr = raw_host.to(device, non_blocking=True)
+        yl = labels_host.to(device, non_blocking=True)
+        loss = model.train_step(ops.perm_data_device(xr, perm), yl)
+        return float(loss)            # device -> host read of the step's result
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        cgdist.barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = lib.cg_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(0.0)          # evict L2 between timed iterations (outside the timed events)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        cgdist.barrier()
+        launches = lib.cg_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return cgdist.max_over_ranks(ms, device), launches, clocks
+
+    W = max(args.warmup, 3)
+    ms_total, launches, clocks = timed(step_resident, args.steps, W, sample_clocks=True)
+    value = world * B * args.steps / (ms_total * 1e-3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 2)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # per-kernel device time of the same step, CUDA events on the launch stream (profiling pass)
+    roof, kernel_ms = None, {}
+    if rank == 0:
+        lib.cg_profile_reset()
+        lib.cg_profile_enable(1)
+        prof_steps = min(args.steps, 5)
+        for _ in range(prof_steps):
+            flush.fill_(0.0)
+            step_resident()
+        torch.cuda.synchronize()
+        lib.cg_profile_enable(0)
+        import ctypes
+        name = ctypes.create_string_buffer(64)
+        tot, cnt = ctypes.c_double(), ctypes.c_int64()
+        n = lib.cg_profile_query(-1, None, 0, None, None)
+        for i in range(n):
+            lib.cg_profile_query(i, name, 64, ctypes.byref(tot), ctypes.byref(cnt))
+            kernel_ms[name.value.decode()] = {'ms_per_step': tot.value / prof_steps, 'launches_per_step': cnt.value / prof_steps}
+        work = step_work(L, B)
+        pk = peaks()
+        cand = {k: v for k, v in kernel_ms.items() if k in work}
+        if cand:
+            top = max(cand, key=lambda k: cand[k]['ms_per_step'])
+            calls = work[top]
+            avg_s = cand[top]['ms_per_step'] * 1e-3 / max(cand[top]['launches_per_step'], 1)
+            if top == 'basis_onchip':
+                per_launch = sum(b for b, _ in calls) / len(calls)
+                achieved = per_launch / avg_s / 1e9
+                roof = {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                        'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source']}
+            else:
+                per_launch = sum(f for _, f in calls) / len(calls)
+                achieved = per_launch / avg_s / 1e12
+                roof = {'bound': 'tensor', 'kernel': top, 'achieved': achieved, 'peak': pk['bf16_tflops'],
+                        'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'], 'traffic': None,
+                        'peak_source': pk['source'],
+                        'note': 'fp32 FFMA contraction measured against the dense bf16 tensor peak'}
+            # SpMM line of the metric, always reported next to the dominant kernel
+            if 'basis_onchip' in cand:
+                bs = work['basis_onchip']
+                t = cand['basis_onchip']['ms_per_step'] * 1e-3
+                roof['spmm'] = {'kernel': 'basis_onchip', 'algorithmic_GBps': sum(b for b, _ in bs) / t / 1e9,
+                                'frac_of_hbm_peak': sum(b for b, _ in bs) / t / 1e9 / pk['hbm_gbs'],
+                                'ms_per_step': cand['basis_onchip']['ms_per_step']}
+            traffic_file = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+            if os.path.exists(traffic_file):
+                roof['traffic'] = json.load(open(traffic_file)).get(top)
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        times, _ = cpu_training_steps(L, args.ref_batch, 3, 1)
+        cpu = {'value': args.ref_batch * len(times) / float(np.sum(times)), 'unit': 'samples/s',
+               'cores': os.cpu_count(), 'kind': 'port',
+               'sample': '3 timed steps of batch %d (1 warm-up), %.1f s of CPU work; oracle/ numpy+scipy port of the '
+                         'reference path (TensorFlow unavailable)' % (args.ref_batch, time.perf_counter() - t0)}
+    line = {
+        'metric': 'cheb_graphconv_train_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': W, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world,
+                   'parallelism': 'dp%d' % world, 'l2': 'flushed between timed iterations (256 MB fill)',
+                   'timing': 'CUDA events per step on the launch stream, summed; max over ranks'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': B * 784 * 4 + B * 8,
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches),
+        'roofline': roof, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernel_ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='samples per GPU per step')
+    ap.add_argument('--ref-batch', type=int, default=100, help='samples per CPU step (reference batch size)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -28,7 +28,7 @@ _SIGNATURES = {
     'cg_graph_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     'cg_graph_destroy': (c_int, [c_void_p]),
     'cg_graph_info': (c_int, [c_void_p, ctypes.POINTER(c_i64)]),
-    'cg_cheb_basis': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    'cg_cheb_basis': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     'cg_cheb_filter_fwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     'cg_cheb_filter_bwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     'cg_cheb_filter_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -45,6 +45,11 @@ _SIGNATURES = {
                                   c_void_p]),
     'cg_lstm_gates_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    'cg_launch_count': (c_i64, []),
+    'cg_profile_enable': (c_int, [c_int]),
+    'cg_profile_reset': (c_int, []),
+    'cg_profile_query': (c_int, [c_int, ctypes.c_char_p, c_int, ctypes.POINTER(ctypes.c_double),
+                                 ctypes.POINTER(c_i64)]),
     'cg_host_metis_one_level': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                         c_void_p, ctypes.POINTER(c_i64)]),
     'cg_host_perm_level': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p]),

@@ -33,6 +33,22 @@ void cg_set_error(const char *fmt, ...);
 
 #define CG_LAUNCH_CHECK() CG_CHECK_CUDA(cudaGetLastError())
 
+// Counts one kernel launch and, when profiling is enabled (cg_profile_enable), brackets it
+// with CUDA events on its stream.  Put one in the scope of every kernel launch.
+class CgProfScope {
+public:
+    CgProfScope(const char *name, cudaStream_t stream);
+    ~CgProfScope();
+    CgProfScope(const CgProfScope &) = delete;
+    CgProfScope &operator=(const CgProfScope &) = delete;
+
+private:
+    const char *name_;
+    cudaStream_t stream_;
+    cudaEvent_t a_, b_;
+    bool active_;
+};
+
 // ---------------------------------------------------------------------------
 // packed operator
 // ---------------------------------------------------------------------------

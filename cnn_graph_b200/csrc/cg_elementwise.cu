@@ -56,6 +56,7 @@ int cg_run_permute_abf(const float *in, float *out, int64_t A, int64_t B, int F,
         CG_CHECK_CUDA(cudaMemcpyAsync(out, in, sizeof(float) * (size_t)(A * B * F), cudaMemcpyDeviceToDevice, s));
         return CG_OK;
     }
+    CgProfScope prof("permute", s);
     if (F >= 8) {
         const bool v4 = F % 4 == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
         if (v4)
@@ -120,6 +121,7 @@ extern "C" int cg_bias_act_fwd(const float *x, const float *bias, float *y, int 
     if (total == 0) return CG_OK;
     const int64_t period = bias_kind == 0 ? 0 : (bias_kind == 1 ? F : (int64_t)M * F);
     const bool v4 = F % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)bias)) & 15) == 0;
+    CgProfScope prof("bias_act_fwd", s);
     if (v4)
         k_bias_act_fwd_v4<<<grid_for(total / 4, 256), 256, 0, s>>>((const float4 *)x, (const float4 *)bias, (float4 *)y,
                                                                    total / 4, period / 4, act);
@@ -180,6 +182,7 @@ extern "C" int cg_bias_act_bwd(const float *y, const float *gy, float *gx, float
     if (row_blocks > 65535) row_blocks = 65535;
     const int64_t rows_per_block = cg_ceil_div(R, row_blocks);
     dim3 grid((unsigned)col_blocks, (unsigned)cg_ceil_div(R, rows_per_block));
+    CgProfScope prof("bias_act_bwd", s);
     k_bias_act_bwd<<<grid, 256, 0, s>>>(y, gy, gx, dbias, R, period, act, tc, rows_per_block);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -242,6 +245,7 @@ extern "C" int cg_pool_fwd(const float *x, float *y, uint8_t *amax, int N, int M
     CG_REQUIRE(p >= 1 && p <= 256 && M % p == 0, "cg_pool_fwd: p=%d must divide M=%d and be <= 256", p, M);
     const int64_t NJ = (int64_t)N * (M / p);
     if (NJ * F == 0) return CG_OK;
+    CgProfScope prof("pool_fwd", (cudaStream_t)stream);
     k_pool_fwd<<<grid_for(NJ * F, 256), 256, 0, (cudaStream_t)stream>>>(x, y, amax, NJ, F, p, kind);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -255,6 +259,7 @@ extern "C" int cg_pool_bwd(const float *gy, const uint8_t *amax, float *gx, int 
     CG_REQUIRE(p >= 1 && p <= 256 && M % p == 0, "cg_pool_bwd: p=%d must divide M=%d and be <= 256", p, M);
     const int64_t NJ = (int64_t)N * (M / p);
     if (NJ * F == 0) return CG_OK;
+    CgProfScope prof("pool_bwd", (cudaStream_t)stream);
     k_pool_bwd<<<grid_for(NJ * F, 256), 256, 0, (cudaStream_t)stream>>>(gy, amax, gx, NJ, F, p, kind);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -279,6 +284,7 @@ extern "C" int cg_perm_data(const float *x, const int32_t *perm, float *out, int
     CG_REQUIRE(x && perm && out, "cg_perm_data: NULL tensor");
     CG_REQUIRE(Mnew >= M && M > 0, "cg_perm_data: need Mnew >= M > 0 (M=%d Mnew=%d)", M, Mnew);
     if (N == 0) return CG_OK;
+    CgProfScope prof("perm_data", (cudaStream_t)stream);
     k_perm_data<<<grid_for(N * Mnew, 256), 256, 0, (cudaStream_t)stream>>>(x, perm, out, N, M, Mnew);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -353,6 +359,7 @@ extern "C" int cg_lstm_gates_fwd(const float *pre, const float *bias, const floa
     CG_REQUIRE(pre && bias && c && new_c && new_h, "cg_lstm_gates_fwd: NULL tensor");
     CG_REQUIRE(variant == 0 || variant == 1, "cg_lstm_gates_fwd: variant must be 0 (fork) or 1 (standard)");
     if (R * H == 0) return CG_OK;
+    CgProfScope prof("lstm_gates_fwd", (cudaStream_t)stream);
     k_lstm_gates_fwd<<<grid_for(R * H, 256), 256, 0, (cudaStream_t)stream>>>(pre, bias, c, new_c, new_h, R, H, variant);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -366,13 +373,15 @@ extern "C" int cg_lstm_gates_bwd(const float *pre, const float *bias, const floa
     if (R * H == 0) return CG_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (d_bias) CG_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * 4 * (size_t)H, s));
-    const int64_t col_blocks = cg_ceil_div(H, 256);
-    int64_t row_blocks = cg_ceil_div(148LL * 8, col_blocks);
+    const int threads = H >= 256 ? 256 : (H + 31) / 32 * 32;
+    const int64_t col_blocks = cg_ceil_div(H, threads);
+    int64_t row_blocks = cg_ceil_div(148LL * 16, col_blocks);
     if (row_blocks > R) row_blocks = R;
     if (row_blocks > 65535) row_blocks = 65535;
     const int64_t rows_per_block = cg_ceil_div(R, row_blocks);
     dim3 grid((unsigned)col_blocks, (unsigned)cg_ceil_div(R, rows_per_block));
-    k_lstm_gates_bwd<<<grid, 256, 0, s>>>(pre, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant,
+    CgProfScope prof("lstm_gates_bwd", s);
+    k_lstm_gates_bwd<<<grid, threads, 0, s>>>(pre, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant,
                                           rows_per_block);
     CG_LAUNCH_CHECK();
     return CG_OK;

@@ -176,6 +176,7 @@ int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, 
     if (R == 0 || J == 0) return CG_OK;
     const int vecA = (F % 4 == 0) && ((((uintptr_t)stack) & 15) == 0);
     const unsigned gx = (unsigned)cg_ceil_div(R, CT_BM);
+    CgProfScope prof("contract", s);
     if (J > 32) {
         dim3 grid(gx, (unsigned)cg_ceil_div(J, 64));
         k_contract<8><<<grid, CT_THREADS, 0, s>>>(stack, W, y, R, N, M, F, J, K, w_transposed ? 1 : 0, vecA);
@@ -338,6 +339,8 @@ int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, i
     const int vecS = (Fa % 4 == 0) && ((((uintptr_t)stack) & 15) == 0);
     const int vecT = (Fb % 4 == 0) && ((((uintptr_t)T) & 15) == 0);
     const bool wide_a = Fb <= 32;
+    {
+    CgProfScope prof("stack_t_plain", s);
     if (wide_a) {
         dim3 grid((unsigned)used, (unsigned)cg_ceil_div((int64_t)K * Fa, 64), (unsigned)cg_ceil_div(Fb, 32));
         CG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stack_t_plain: problem too large");
@@ -350,6 +353,8 @@ int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, i
                                                            vecS, vecT);
     }
     CG_LAUNCH_CHECK();
+    }
+    CgProfScope prof2("reduce_partials", s);
     const int64_t total = (int64_t)K * Fa * Fb;
     int64_t blocks = cg_ceil_div(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;

@@ -98,6 +98,7 @@ static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, 
     const int rows_per_block = 256 / lpr;
     dim3 grid((unsigned)cg_ceil_div(M, rows_per_block), (unsigned)cg_ceil_div(lanes_needed, lpr));
     CG_REQUIRE(grid.y <= 65535, "spmm_step: too many columns (C=%lld)", (long long)C);
+    CgProfScope prof("spmm_step", s);
     if (vec4)
         k_spmm_step<4><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
     else
@@ -195,6 +196,7 @@ static int launch_onchip(const cg_graph *g, const CgCsr &L, const float *in, flo
                         2 * (size_t)g->M * CW * sizeof(float);
     CG_CHECK_CUDA(cudaFuncSetAttribute(k_basis_onchip<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)cg_ceil_div(C, CW);
+    CgProfScope prof("basis_onchip", s);
     k_basis_onchip<CW><<<grid, kOnchipThreads, smem, s>>>(L.ell, L.rowptr, L.width, L.m_pad, g->M, in, stack, C, K,
                                                           write_slab0);
     CG_LAUNCH_CHECK();
@@ -241,8 +243,8 @@ int cg_run_basis(const cg_graph *g, int transpose, float *stack, int64_t C, int 
 }
 
 extern "C" int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float *dev_Xt, int64_t C,
-                             int K, void *stream) {
+                             int K, int flags, void *stream) {
     CG_REQUIRE(g && dev_X && dev_Xt, "cg_cheb_basis: NULL argument");
     CG_REQUIRE(C > 0 && K >= 1, "cg_cheb_basis: C and K must be positive (C=%lld K=%d)", (long long)C, K);
-    return run_basis_from(g, transpose, dev_X, dev_Xt, C, K, (cudaStream_t)stream, CG_FILTER_DEFAULT);
+    return run_basis_from(g, transpose, dev_X, dev_Xt, C, K, (cudaStream_t)stream, flags);
 }

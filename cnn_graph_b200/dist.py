@@ -1,0 +1,82 @@
+"""Data-parallel plumbing: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink/NVSwitch on the B200 box, gloo in CPU tests).
+
+The Chebyshev hot path shards over the batch with no data-path collective: L~ and the
+weights are replicated, every sample (every column of the signal slab) is independent
+through filter, activation and pooling.  The only exchange per step is the
+sum of the weight gradients, done here as ONE all-reduce over a single flat fp32 bucket
+(launch-latency bound at ~8 MB for the MNIST-shaped model, so one bucket, not many).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment; returns
+    (rank, world_size, local_rank).  Single-process runs return (0, 1, 0) untouched."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def shard_bounds(n_items, rank, world):
+    """Contiguous [begin, end) shard of ``n_items`` for ``rank`` (remainder spread over the
+    first ranks) -- the batch partition of the data-parallel path."""
+    base, rem = divmod(int(n_items), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class GradAllReducer:
+    """Averages gradients across ranks with one flat all-reduce per step."""
+
+    def __init__(self, average=True):
+        self.average = average
+        self._flat = None
+
+    def __call__(self, params):
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        total = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != total or self._flat.device != grads[0].device:
+            self._flat = torch.empty(total, dtype=torch.float32, device=grads[0].device)
+        flat = self._flat
+        offset = 0
+        for g in grads:
+            flat[offset:offset + g.numel()].copy_(g.reshape(-1))
+            offset += g.numel()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if self.average:
+            flat.div_(dist.get_world_size())
+        offset = 0
+        for g in grads:
+            g.copy_(flat[offset:offset + g.numel()].view_as(g))
+            offset += g.numel()
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over all ranks (device-side all-reduce)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

@@ -131,7 +131,7 @@ def get_handle(L, lmax=2):
 # Chebyshev basis (graph.chebyshev)
 # ---------------------------------------------------------------------------------------
 
-def cheb_basis(handle, X, K, transpose=False):
+def cheb_basis(handle, X, K, transpose=False, flags=FILTER_DEFAULT):
     """Xt [K, M, C] = T_k(L~) X for X [M, C] on the device (lib/graph.py:241-258)."""
     _require_cuda(X)
     X = _f32c(X)
@@ -139,7 +139,8 @@ def cheb_basis(handle, X, K, transpose=False):
     if M != handle.M:
         raise ValueError('X has %d rows, graph has %d vertices' % (M, handle.M))
     Xt = torch.empty((K, M, C), dtype=torch.float32, device=X.device)
-    check(_native.lib().cg_cheb_basis(handle.handle, int(bool(transpose)), ptr(X), ptr(Xt), C, K, _stream()),
+    check(_native.lib().cg_cheb_basis(handle.handle, int(bool(transpose)), ptr(X), ptr(Xt), C, K, int(flags),
+                                      _stream()),
           'cg_cheb_basis')
     return Xt
 
@@ -192,6 +193,8 @@ class ChebFilterFn(torch.autograd.Function):
 
 def cheb_filter(x, W, L, K, lmax=2, grad_x=True, flags=FILTER_DEFAULT):
     """Functional Chebyshev filter; ``L`` is a scipy Laplacian (rescaled here) or a GraphHandle."""
+    if x.is_meta:     # shape tracing while a model declares its variables (no device work)
+        return x.new_empty((x.shape[0], x.shape[1], W.shape[1]))
     return ChebFilterFn.apply(x, W, get_handle(L, lmax), int(K), bool(grad_x), int(flags))
 
 
@@ -242,6 +245,8 @@ class BiasActFn(torch.autograd.Function):
 
 
 def bias_act(x, bias, act):
+    if x.is_meta:
+        return x.new_empty(x.shape)
     return BiasActFn.apply(x, bias, ACT[act] if isinstance(act, str) else int(act))
 
 
@@ -274,6 +279,8 @@ class PoolFn(torch.autograd.Function):
 def pool(x, p, kind):
     if p <= 1:
         return x
+    if x.is_meta:
+        return x.new_empty((x.shape[0], x.shape[1] // p, x.shape[2]))
     return PoolFn.apply(x, int(p), 1 if kind in (1, 'max') else 2)
 
 
@@ -345,4 +352,6 @@ class LstmGatesFn(torch.autograd.Function):
 
 def lstm_gates(pre, bias, c, variant='fork'):
     v = {'fork': 0, 'standard': 1}[variant] if isinstance(variant, str) else int(variant)
+    if pre.is_meta:
+        return c.new_empty(c.shape), c.new_empty(c.shape)
     return LstmGatesFn.apply(pre, bias, c, v)

@@ -66,9 +66,10 @@ int cg_graph_info(const cg_graph_t *g, int64_t info[5]);
 /* ---- Chebyshev basis ---------------------------------------------------- */
 /* graph.chebyshev(L, X, K)  lib/graph.py:241-258:
  *   Xt[0] = X, Xt[1] = L~ X, Xt[k] = 2 L~ Xt[k-1] - Xt[k-2].
- * dev_X [M, C], dev_Xt [K, M, C].  transpose != 0 applies L~^T instead.      */
+ * dev_X [M, C], dev_Xt [K, M, C].  transpose != 0 applies L~^T instead.
+ * flags: CG_FILTER_* (kernel selection, see below).                           */
 int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float *dev_Xt,
-                  int64_t C, int K, void *stream);
+                  int64_t C, int K, int flags, void *stream);
 
 /* ---- Chebyshev filter (chebyshev5 / chebyshev2 / cheby_conv) ---------- */
 /* Forward: lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95
@@ -134,6 +135,17 @@ int cg_lstm_gates_bwd(const float *dev_pre, const float *dev_bias, const float *
                       const float *dev_new_c, const float *dev_g_h, const float *dev_g_c,
                       float *dev_g_pre, float *dev_g_cprev, float *dev_d_bias, int64_t R, int H,
                       int variant, void *stream);
+
+/* ---- launch accounting / per-kernel timing (measurement support) -------- */
+/* cg_launch_count: kernels launched by this library since load (all threads).
+ * cg_profile_enable(1): bracket every launch with CUDA events on its own stream;
+ * cg_profile_query(i, ...) returns the number of distinct kernel names and, for a
+ * valid i, that kernel's accumulated device time (ms) and launch count (it
+ * synchronises the recorded events first); cg_profile_reset clears the totals. */
+int64_t cg_launch_count(void);
+int cg_profile_enable(int on);
+int cg_profile_reset(void);
+int cg_profile_query(int index, char *name, int name_cap, double *total_ms, int64_t *count);
 
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32

@@ -1,0 +1,363 @@
+"""Parity of the CUDA hot path (through the C ABI) against the oracle on identical seeded
+inputs, against the reference-generated golden fixtures, and -- at full BASELINE sizes --
+through size-independent properties (linearity, adjoint identities).
+
+Tolerances (BASELINE.json north_star): bit-exact for permutations, perm_data and pooling
+indices; fp32 filter outputs and gradients within rtol 1e-4 with atol = 1e-4 * max|ref|.
+"""
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+from conftest import csr_from
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def close(got, ref, rtol=RTOL):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = max(float(np.abs(ref).max()), 1e-30) if ref.size else 1.0
+    err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()) if ref.size else 0.0
+    assert err <= rtol * scale, 'max abs err %.3e > %.1e * %.3e' % (err, rtol, scale)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from cnn_graph_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+@pytest.fixture(scope='module')
+def tf_ref():
+    from oracle import tf_ref as t
+    return t
+
+
+FLAG_SETS = [0, 1]   # default (on-chip when it fits) and forced streaming
+
+
+# --------------------------------------------------------------------------- basis
+@pytest.mark.parametrize('flags', FLAG_SETS)
+def test_basis_matches_reference_fixtures(ops, c2, directed, flags):
+    h2 = ops.GraphHandle(csr_from(c2, 'Lr2'))
+    assert h2.info()['onchip']
+    for K in (1, 2, 7):
+        got = ops.cheb_basis(h2, dev(c2['basis_X']), K, flags=flags)
+        close(got, c2['basis_K%d' % K], 1e-5)
+    h0 = ops.GraphHandle(csr_from(c2, 'Lr0'))
+    close(ops.cheb_basis(h0, dev(c2['basis0_X'][:, :4]), 25, flags=flags), c2['basis0_K25'][:, :, :4], 1e-5)
+    close(ops.cheb_basis(h0, dev(c2['basis0_X']), 25, flags=flags), c2['basis0_K25'], 1e-5)    # C = 5: scalar path
+    hd = ops.GraphHandle(csr_from(directed, 'Lr'))
+    close(ops.cheb_basis(hd, dev(directed['X']), 6, flags=flags), directed['basis_K6'], 1e-5)
+
+
+def test_basis_transpose_and_wide(ops, directed):
+    from oracle import graph_ref
+    Lr = csr_from(directed, 'Lr')
+    h = ops.GraphHandle(Lr)
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((Lr.shape[0], 520)).astype(np.float32)
+    ref = graph_ref.chebyshev(scipy.sparse.csr_matrix(Lr.T), X, 9)
+    for flags in FLAG_SETS:
+        close(ops.cheb_basis(h, dev(X), 9, transpose=True, flags=flags), ref, 1e-5)
+
+
+def test_lib_graph_chebyshev_host_api(c2):
+    from cnn_graph_b200.lib import graph
+    got = graph.chebyshev(csr_from(c2, 'Lr2'), c2['basis_X'], 7)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32
+    close(got, c2['basis_K7'], 1e-5)
+
+
+# --------------------------------------------------------------------------- filter
+SHAPES = [  # (level, N, Fin, Fout, K)
+    (2, 5, 32, 64, 25), (0, 3, 1, 32, 25), (3, 7, 1, 3, 1), (3, 2, 3, 5, 2), (4, 9, 6, 10, 3), (3, 4, 33, 130, 4),
+    (2, 1, 64, 2, 5), (4, 16, 2, 512, 3), (3, 1, 8, 8, 20), (4, 33, 5, 7, 6),
+]
+
+
+@pytest.mark.parametrize('flags', FLAG_SETS)
+@pytest.mark.parametrize('level,N,Fin,Fout,K', SHAPES)
+def test_filter_forward_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K, flags):
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(100 * level + K)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    xt = dev(x).requires_grad_(True)
+    Wt = dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, K, lmax=2, flags=flags)
+    close(y, tf_ref.chebyshev5(x, L, W, K))
+    y.backward(dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
+
+
+def test_filter_directed_lmax(ops, tf_ref, directed):
+    L = csr_from(directed, 'L')
+    M = L.shape[0]
+    rng = np.random.RandomState(7)
+    x = rng.standard_normal((6, M, 4)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((4 * 5, 12))).astype(np.float32)
+    gy = rng.standard_normal((6, M, 12)).astype(np.float32)
+    before = L.data.copy()
+    for flags in FLAG_SETS:
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, 5, lmax=3.5, flags=flags)
+        close(y, tf_ref.chebyshev5(x, L, W, 5, lmax=3.5))
+        y.backward(dev(gy))
+        dx, dW = tf_ref.chebyshev5_backward(x, L, W, 5, gy, lmax=3.5)
+        close(xt.grad, dx)
+        close(Wt.grad, dW)
+    assert np.array_equal(L.data, before)            # caller's Laplacian untouched
+
+
+def test_chebyshev2_has_no_input_gradient(ops, tf_ref, c2):
+    L = csr_from(c2, 'L3')
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal((4, L.shape[0], 1)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((6, 8))).astype(np.float32)
+    gy = rng.standard_normal((4, L.shape[0], 8)).astype(np.float32)
+    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, 6, grad_x=False)
+    close(y, tf_ref.chebyshev2(x, L, W, 6))
+    y.backward(dev(gy))
+    assert xt.grad is None
+    close(Wt.grad, tf_ref.chebyshev5_backward(x, L, W, 6, gy)[1])
+
+
+def test_empty_batch_and_errors(ops, c2):
+    from cnn_graph_b200 import _native
+    L = csr_from(c2, 'L4')
+    W = dev(np.zeros((2 * 3, 4), np.float32))
+    y = ops.cheb_filter(dev(np.zeros((0, L.shape[0], 2), np.float32)), W, L, 3)
+    assert tuple(y.shape) == (0, L.shape[0], 4)
+    with pytest.raises(ValueError):
+        ops.cheb_filter(dev(np.zeros((1, L.shape[0] + 1, 2), np.float32)), W, L, 3)
+    with pytest.raises(ValueError):
+        ops.cheb_filter(dev(np.zeros((1, L.shape[0], 3), np.float32)), W, L, 3)
+    with pytest.raises(_native.NativeError):
+        ops.cheb_filter(torch.zeros((1, L.shape[0], 2)), W.cpu(), L, 3)      # CPU tensors: no fallback
+    with pytest.raises(_native.NativeError):        # unsorted / duplicate column indices are rejected by the C ABI
+        import ctypes
+        h = ctypes.c_void_p()
+        ip = np.array([0, 2], np.int32); ix = np.array([0, 0], np.int32); v = np.ones(2, np.float32)
+        _native.check(_native.lib().cg_graph_create(ctypes.byref(h), 1, 2, ip.ctypes.data, ix.ctypes.data, v.ctypes.data), 'create')
+
+
+# --------------------------------------------------------------------------- full-size properties
+def test_full_size_c2_linearity_and_adjoint(ops, c2):
+    """BASELINE config C2 layer shapes at batch 100: linear in x, bilinear pairing identities
+    <F(x), g> = <x, dx(g)> = <W, dW(x, g)> (no oracle needed at this size)."""
+    torch.manual_seed(0)
+    for level, Fin, Fout, K in ((0, 1, 32, 25), (2, 32, 64, 25)):
+        L = csr_from(c2, 'L%d' % level)
+        M = L.shape[0]
+        N = 100
+        x1 = torch.randn(N, M, Fin, device='cuda')
+        x2 = torch.randn(N, M, Fin, device='cuda')
+        W = (0.1 * torch.randn(Fin * K, Fout, device='cuda')).requires_grad_(True)
+        y1 = ops.cheb_filter(x1, W, L, K)
+        y2 = ops.cheb_filter(x2, W, L, K)
+        y12 = ops.cheb_filter(2.0 * x1 - 0.5 * x2, W, L, K)
+        close(y12, (2.0 * y1 - 0.5 * y2).detach().cpu().numpy())
+        xa = x1.clone().requires_grad_(True)
+        g = torch.randn(N, M, Fout, device='cuda')
+        ya = ops.cheb_filter(xa, W, L, K)
+        ya.backward(g)
+        lhs = float((ya.detach().double() * g.double()).sum())
+        assert abs(lhs - float((xa.detach().double() * xa.grad.double()).sum())) <= 1e-4 * abs(lhs)
+        assert abs(lhs - float((W.detach().double() * W.grad.double()).sum())) <= 1e-4 * abs(lhs)
+        # K = 1 is the per-vertex linear map y = x W
+        W1 = 0.1 * torch.randn(Fin, Fout, device='cuda')
+        close(ops.cheb_filter(x1, W1, L, 1), (x1 @ W1).cpu().numpy())
+
+
+# --------------------------------------------------------------------------- bias/act, pool, perm_data
+@pytest.mark.parametrize('act', ['relu', 'tanh', 'none'])
+@pytest.mark.parametrize('kind,F', [(0, 5), (1, 32), (1, 3), (2, 8), (2, 7)])
+def test_bias_act_vs_torch(ops, act, kind, F):
+    torch.manual_seed(1)
+    N, M = 6, 20
+    x = torch.randn(N, M, F, device='cuda', requires_grad=True)
+    b = None if kind == 0 else torch.randn((1, 1, F) if kind == 1 else (1, M, F), device='cuda', requires_grad=True)
+    g = torch.randn(N, M, F, device='cuda')
+    y = ops.bias_act(x, b, act)
+    fn = {'relu': torch.relu, 'tanh': torch.tanh, 'none': lambda t: t}[act]
+    xr = x.detach().clone().requires_grad_(True)
+    br = None if b is None else b.detach().clone().requires_grad_(True)
+    yr = fn(xr if br is None else xr + br)
+    close(y, yr.detach().cpu().numpy(), 1e-6)
+    y.backward(g)
+    yr.backward(g)
+    close(x.grad, xr.grad.cpu().numpy(), 1e-5)
+    if b is not None:
+        close(b.grad, br.grad.cpu().numpy(), 1e-5)
+
+
+@pytest.mark.parametrize('p', [1, 2, 4, 8])
+@pytest.mark.parametrize('F', [1, 32, 5])
+def test_pool_bit_exact_vs_oracle(ops, tf_ref, p, F):
+    rng = np.random.RandomState(p * 10 + F)
+    x = rng.standard_normal((5, 16 * p, F)).astype(np.float32)
+    x[x < -0.3] = 0.0                        # ties between zeros as after a ReLU with fake vertices
+    g = rng.standard_normal((5, 16, F)).astype(np.float32)
+    xt = dev(x).requires_grad_(True)
+    y = ops.pool(xt, p, 'max')
+    assert np.array_equal(y.detach().cpu().numpy(), tf_ref.mpool1(x, p))            # bit-exact values
+    if p > 1:
+        _, am = ops.pool_argmax(dev(x), p)
+        assert np.array_equal(am.cpu().numpy(), tf_ref.mpool1_argmax(x, p))          # bit-exact first-max indices
+        y.backward(dev(g))
+        assert np.array_equal(xt.grad.cpu().numpy(), tf_ref.mpool1_backward(x, p, g))
+    xa = dev(x).requires_grad_(True)
+    ya = ops.pool(xa, p, 'avg')
+    close(ya, tf_ref.apool1(x, p), 1e-6)
+    if p > 1:
+        ya.backward(dev(g))
+        close(xa.grad, tf_ref.apool1_backward(x, p, g), 1e-6)
+
+
+def test_perm_data_bit_exact(ops, c2, c1):
+    got = ops.perm_data_device(dev(c2['pd_x']), c2['perm'])
+    assert np.array_equal(got.cpu().numpy().astype(np.float64), c2['pd_y'])          # reference fixture
+    got = ops.perm_data_device(dev(c1['Xd'][:4]), c1['perm'])
+    assert np.array_equal(got.cpu().numpy().astype(np.float64), c1['pd_y'])
+    assert ops.perm_data_device(dev(np.zeros((0, 784), np.float32)), c2['perm']).shape == (0, 992)
+
+
+# --------------------------------------------------------------------------- LSTM
+@pytest.mark.parametrize('variant', ['fork', 'standard'])
+def test_lstm_cell_step_vs_oracle(ops, tf_ref, c2, variant):
+    from cnn_graph_b200.lib import gconv_lstm, variables
+    L = csr_from(c2, 'L4')
+    M, N, Fin, H, K = L.shape[0], 3, 2, 8, 3
+    rng = np.random.RandomState(5)
+    x = (0.5 * rng.standard_normal((N, M, Fin))).astype(np.float32)
+    h = (0.3 * rng.standard_normal((N, M, H))).astype(np.float32)
+    c = (0.3 * rng.standard_normal((N, M, H))).astype(np.float32)
+    store = variables.VariableStore(device='cuda', seed=1)
+    cell = gconv_lstm.GConvLSTMCell(num_units=H, laplacian=L, lmax=2, K=K, feat_in=Fin, nNode=M, gate_variant=variant)
+    with variables.use_store(store):
+        new_h, state = cell(dev(x), (dev(c), dev(h)))
+    v = {k.split('/')[-1]: p.detach().cpu().numpy() for k, p in store.vars.items()}
+    Wx = {g: v['W%sxt' % g] for g in 'zifo'}
+    Wh = {g: v['W%sht' % g] for g in 'zifo'}
+    b = {g: v['b%st' % g] for g in 'zifo'}
+    ref_h, ref_c = tf_ref.gconv_lstm_step(x, c, h, L, 2, K, Wx, Wh, b, variant)
+    close(state.c, ref_c)
+    close(new_h, ref_h)
+    assert state.h is new_h and cell.output_size == H and cell.state_size.c == (M, H)
+
+
+@pytest.mark.parametrize('variant', ['fork', 'standard'])
+def test_lstm_gates_gradients_vs_torch(ops, variant):
+    torch.manual_seed(2)
+    R, H = 37, 5
+    pre = (0.5 * torch.randn(1, R, 4 * H, device='cuda')).requires_grad_(True)
+    bias = (0.1 * torch.randn(4 * H, device='cuda')).requires_grad_(True)
+    c = torch.randn(1, R, H, device='cuda', requires_grad=True)
+    gh, gc = torch.randn(1, R, H, device='cuda'), torch.randn(1, R, H, device='cuda')
+    nh, nc = ops.lstm_gates(pre, bias, c, variant)
+    (nh * gh).sum().add((nc * gc).sum()).backward()
+    p2, b2, c2_ = (t.detach().double().clone().requires_grad_(True) for t in (pre, bias, c))
+    a = p2 + b2
+    z, i, f, o = a[..., :H], a[..., H:2 * H], a[..., 2 * H:3 * H], a[..., 3 * H:]
+    zz = torch.tan(z) if variant == 'fork' else torch.tanh(z)
+    oo = torch.tanh(o) if variant == 'fork' else torch.sigmoid(o)
+    rc = torch.sigmoid(f) * c2_ + torch.sigmoid(i) * zz
+    rh = oo * torch.tanh(rc)
+    (rh * gh.double()).sum().add((rc * gc.double()).sum()).backward()
+    close(nc, rc.detach().cpu().numpy(), 1e-5)
+    close(nh, rh.detach().cpu().numpy(), 1e-5)
+    close(pre.grad, p2.grad.cpu().numpy())
+    close(c.grad, c2_.grad.cpu().numpy())
+    close(bias.grad, b2.grad.cpu().numpy())
+
+
+# --------------------------------------------------------------------------- models
+def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
+    """The MNIST-shaped model of BASELINE config C2 (GC32-P4-GC64-P4-FC512-FC10) end to end."""
+    from cnn_graph_b200.lib import models
+    L = [csr_from(c2, 'L%d' % i) for i in range(5)]
+    N = 6
+    model = models.cgcnn(L, F=[32, 64], K=[25, 25], p=[4, 4], M=[512, 10], batch_size=N, dropout=1)
+    rng = np.random.RandomState(9)
+    x = rng.uniform(0, 1, (N, 992)).astype(np.float32)
+    labels = rng.randint(0, 10, N)
+    logits = model.inference(dev(x), 1)
+    v = {k: p.detach().cpu().numpy() for k, p in model.store.vars.items()}
+    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/filter/weights'], 25)
+    r1 = tf_ref.b1relu(a1, v['conv1/bias_relu/bias'])
+    p1 = tf_ref.mpool1(r1, 4)
+    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/filter/weights'], 25)
+    r2 = tf_ref.b1relu(a2, v['conv2/bias_relu/bias'])
+    p2 = tf_ref.mpool1(r2, 4)
+    f1 = tf_ref.fc(p2.reshape(N, -1), v['fc1/weights'], v['fc1/bias'])
+    ref_logits = tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False)
+    close(logits, ref_logits)
+    # backward: seed with d(sum of logits * g) and push it through the oracle chain by hand
+    g = rng.standard_normal(ref_logits.shape).astype(np.float32)
+    (logits * dev(g)).sum().backward()
+    gf1 = (g @ v['logits/weights'].T) * (f1 > 0)
+    gp2 = (gf1 @ v['fc1/weights'].T).reshape(p2.shape)
+    gr2 = tf_ref.mpool1_backward(r2, 4, gp2)
+    ga2 = gr2 * (r2 > 0)
+    gp1, dW2 = tf_ref.chebyshev5_backward(p1, L[2], v['conv2/filter/weights'], 25, ga2)
+    gr1 = tf_ref.mpool1_backward(r1, 4, gp1)
+    ga1 = gr1 * (r1 > 0)
+    _, dW1 = tf_ref.chebyshev5_backward(x[:, :, None], L[0], v['conv1/filter/weights'], 25, ga1)
+    close(model.store.vars['conv2/filter/weights'].grad, dW2)
+    close(model.store.vars['conv1/filter/weights'].grad, dW1)
+    close(model.store.vars['conv2/bias_relu/bias'].grad.reshape(-1), ga2.sum(axis=(0, 1)))
+    close(model.store.vars['conv1/bias_relu/bias'].grad.reshape(-1), ga1.sum(axis=(0, 1)))
+    # one optimisation step runs and changes the weights
+    before = v['conv1/filter/weights'].copy()
+    loss = model.train_step(dev(x), torch.from_numpy(labels).cuda())
+    assert np.isfinite(float(loss))
+    assert not np.array_equal(before, model.get_var('conv1/filter/weights'))
+
+
+def test_graphconv_and_glstm_models_run(ops, tf_ref, c2):
+    from cnn_graph_b200.lib import gconv_lstm, graph_conv
+    L = csr_from(c2, 'L3')
+    M = L.shape[0]
+    rng = np.random.RandomState(4)
+    # fork residual net: conv_init -> 1 residual layer -> convN, plain-ReLU b1relu
+    net = graph_conv.GraphConv([L], F=[8], K=[3], p=[1], M=[2], _nfilter=8, _nres_layer_count=1, C_0=[6], batch_size=3)
+    x = rng.uniform(0, 1, (3, M, 6)).astype(np.float32)
+    out = net.inference(dev(x), 0)
+    v = {k: p.detach().cpu().numpy() for k, p in net.store.vars.items()}
+    a = np.maximum(tf_ref.chebyshev5(x, L, v['conv_init/weights'], 3), 0)
+    b = np.maximum(tf_ref.chebyshev5(a, L, v['residual_layer_0/sublayer0/weights'], 3), 0)
+    c = np.maximum(tf_ref.chebyshev5(b, L, v['residual_layer_0/sublayer1/weights'], 3) + a, 0)
+    close(out, tf_ref.chebyshev5(c, L, v['convN/weights'], 3))
+    y = rng.uniform(0, 1, (3, M, 2)).astype(np.float32)
+    assert np.isfinite(float(net.train_step(dev(x), dev(y))))
+    # gLSTM model: 3 frames of 2 features, injected all-ones dropout masks -> deterministic
+    gm = gconv_lstm.GconvModel(L, 3, 0, 0, filter_num=8, kernel_num=3, feature_num=6, in_feature_num=2,
+                               infer_func='inference_glstm', batch_size=3, gate_variant='standard', output_keep_prob=1.0)
+    out = gm.inference(dev(x), 0)
+    v = {k.split('/')[-1] if 'Cell' in k else k: p.detach().cpu().numpy() for k, p in gm.store.vars.items()}
+    Wx = {g: v['W%sxt' % g] for g in 'zifo'}
+    Wh = {g: v['W%sht' % g] for g in 'zifo'}
+    bb = {g: v['b%st' % g] for g in 'zifo'}
+    h = np.zeros((3, M, 8), np.float32)
+    cc = np.zeros((3, M, 8), np.float32)
+    frames = x.reshape(3, M, 2, 3)
+    for t in range(3):
+        h, cc = tf_ref.gconv_lstm_step(frames[..., t], cc, h, L, 2, 3, Wx, Wh, bb, 'standard')
+    close(out, tf_ref.chebyshev5(h, L, v['conv_init/weights'], 3))
+    assert np.isfinite(float(gm.train_step(dev(x), dev(y))))
