@@ -221,7 +221,7 @@ def run_ours(args):
         xr = raw_host.to(device, non_blocking=True)
         yl = labels_host.to(device, non_blocking=True)
         loss = model.train_step(ops.perm_data_device(xr, perm), yl)
-        return float(loss)            # device -> host read of the step's result
+        return float(loss.detach())   # device -> host read of the step's result
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):

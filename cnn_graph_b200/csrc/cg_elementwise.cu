@@ -281,9 +281,9 @@ k_perm_data(const float *__restrict__ x, const int *__restrict__ perm, float *__
 
 extern "C" int cg_perm_data(const float *x, const int32_t *perm, float *out, int64_t N, int M, int Mnew,
                             void *stream) {
-    CG_REQUIRE(x && perm && out, "cg_perm_data: NULL tensor");
     CG_REQUIRE(Mnew >= M && M > 0, "cg_perm_data: need Mnew >= M > 0 (M=%d Mnew=%d)", M, Mnew);
     if (N == 0) return CG_OK;
+    CG_REQUIRE(x && perm && out, "cg_perm_data: NULL tensor");
     CgProfScope prof("perm_data", (cudaStream_t)stream);
     k_perm_data<<<grid_for(N * Mnew, 256), 256, 0, (cudaStream_t)stream>>>(x, perm, out, N, M, Mnew);
     CG_LAUNCH_CHECK();

@@ -40,8 +40,8 @@ extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const flo
                                   int Fout, int K, void *workspace, size_t workspace_bytes, int flags, void *stream) {
     int rc = check_dims("cg_cheb_filter_fwd", g, N, Fin, Fout, K);
     if (rc != CG_OK) return rc;
-    CG_REQUIRE(x && W && y, "cg_cheb_filter_fwd: NULL tensor");
     if (N == 0) return CG_OK;
+    CG_REQUIRE(x && W && y, "cg_cheb_filter_fwd: NULL tensor");
     cudaStream_t s = (cudaStream_t)stream;
     const int M = g->M;
     if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
@@ -63,13 +63,14 @@ extern "C" int cg_cheb_filter_bwd(const cg_graph_t *g, const float *x, const flo
                                   int flags, void *stream) {
     int rc = check_dims("cg_cheb_filter_bwd", g, N, Fin, Fout, K);
     if (rc != CG_OK) return rc;
-    CG_REQUIRE(x && W && gy && dW, "cg_cheb_filter_bwd: NULL tensor");
+    CG_REQUIRE(dW != nullptr, "cg_cheb_filter_bwd: dW is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     const int M = g->M;
     if (N == 0) {
         CG_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Fin * K * Fout, s));
         return CG_OK;
     }
+    CG_REQUIRE(x && W && gy, "cg_cheb_filter_bwd: NULL tensor");
     const int need_dx = dx != nullptr;
     const size_t need = cg_cheb_filter_bwd_workspace_bytes(g, N, Fin, Fout, K, need_dx, flags);
     if (workspace == nullptr || workspace_bytes < need) {

@@ -199,13 +199,16 @@ class cgcnn(GraphConvOps, GraphModel):
                     x = self.filter(x, self.L[i], self.F[i], self.K[i])
                 with self.variable_scope('bias_relu'):
                     x = self.brelu(x)
+                    self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
                 with self.variable_scope('pooling'):
                     x = self.pool(x, self.p[i])
+                    self.nets['conv{}/pooling'.format(i + 1)] = x
         N, Mv, Fv = (int(d) for d in x.shape)
         x = x.reshape(N, Mv * Fv)
         for i, width in enumerate(self.M[:-1]):
             with self.variable_scope('fc{}'.format(i + 1)):
                 x = self.fc(x, width)
+                self.nets['fc{}'.format(i + 1)] = x
                 if self.is_train and 0 < dropout < 1 and not x.is_meta:
                     x = torch.nn.functional.dropout(x, p=1 - dropout, training=True)
         with self.variable_scope('logits'):

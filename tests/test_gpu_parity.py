@@ -308,7 +308,16 @@ def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
     f1 = tf_ref.fc(p2.reshape(N, -1), v['fc1/weights'], v['fc1/bias'])
     ref_logits = tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False)
     close(logits, ref_logits)
-    # backward: seed with d(sum of logits * g) and push it through the oracle chain by hand
+    # backward: seed with d(sum of logits * g) and push it through the oracle chain by hand.
+    # ReLU masks and max-pool routing are discontinuous in the activations, so the oracle
+    # chain is evaluated AT the product's (already parity-checked) activations: a value that
+    # is +1e-8 on one side and 0 on the other would otherwise flip a whole gradient entry.
+    nets = {k: t.detach().cpu().numpy() for k, t in model.nets.items()}
+    close(nets['conv1/bias_relu'], r1)
+    close(nets['conv2/bias_relu'], r2)
+    close(nets['conv1/pooling'], p1)
+    close(nets['fc1'], f1)
+    r1, r2, p1, f1 = nets['conv1/bias_relu'], nets['conv2/bias_relu'], nets['conv1/pooling'], nets['fc1']
     g = rng.standard_normal(ref_logits.shape).astype(np.float32)
     (logits * dev(g)).sum().backward()
     gf1 = (g @ v['logits/weights'].T) * (f1 > 0)
