@@ -1,0 +1,94 @@
+// Unit-test kernel for the tcgen05 primitives in cg_umma.cuh: one CTA computes
+//   D[128][N] = A * B^T   with bf16 operands, fp32 accumulation in TMEM,
+// for every combination of K-major / MN-major operand storage.  Exposed through
+// cg_debug_umma_gemm so the GPU parity tests can pin descriptor encodings before the fused
+// kernels rely on them.
+#include "cg_common.cuh"
+#include "cg_umma.cuh"
+
+// A_src: a_mn == 0 -> [128][Kd] (k contiguous);  a_mn == 1 -> [Kd][128] (m contiguous)
+// B_src: b_mn == 0 -> [N][Kd];                   b_mn == 1 -> [Kd][N]
+__global__ void __launch_bounds__(128, 1)
+k_umma_test(const float *__restrict__ A_src, const float *__restrict__ B_src, float *__restrict__ D, int N, int Kd,
+            int a_mn, int b_mn) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __nv_bfloat16 *As = reinterpret_cast<__nv_bfloat16 *>(smem);
+    __nv_bfloat16 *Bs = As + 128 * Kd;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // strides (bytes).  K-major: LBO = between K chunks, SBO = between 8-row groups.
+    //                   MN-major: SBO = between 8-element MN chunks, LBO = between 8-row K groups.
+    const uint32_t a_lbo = a_mn ? 128u * (128 / 8) : 128u;          // MN: k-group stride = 16 mn-chunks * 128 B
+    const uint32_t a_sbo = a_mn ? 128u : 128u * (Kd / 8);
+    const uint32_t b_lbo = b_mn ? 128u * (N / 8) : 128u;
+    const uint32_t b_sbo = b_mn ? 128u : 128u * (Kd / 8);
+
+    for (int e = tid; e < 128 * Kd; e += 128) {
+        int r, k;
+        if (a_mn) { k = e / 128; r = e % 128; } else { r = e / Kd; k = e % Kd; }
+        const float v = A_src[e];
+        uint32_t off = a_mn ? (r / 8) * a_sbo + (k / 8) * a_lbo + (k % 8) * 16 + (r % 8) * 2
+                            : (r / 8) * a_sbo + (k / 8) * a_lbo + (r % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(As) + off) = __float2bfloat16_rn(v);
+    }
+    for (int e = tid; e < N * Kd; e += 128) {
+        int r, k;
+        if (b_mn) { k = e / N; r = e % N; } else { r = e / Kd; k = e % Kd; }
+        const float v = B_src[e];
+        uint32_t off = b_mn ? (r / 8) * b_sbo + (k / 8) * b_lbo + (k % 8) * 16 + (r % 8) * 2
+                            : (r / 8) * b_sbo + (k / 8) * b_lbo + (r % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(Bs) + off) = __float2bfloat16_rn(v);
+    }
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::fence_mbar_init();
+    }
+    uint32_t ncols = 32;
+    while ((int)ncols < N) ncols *= 2;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
+    umma::fence_proxy_async();          // operand tiles written with st.shared -> async proxy
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N, a_mn, b_mn);
+        const uint32_t a0 = umma::smem_u32(As), b0 = umma::smem_u32(Bs);
+        for (int k16 = 0; k16 < Kd / 16; ++k16) {
+            const uint64_t ad = umma::make_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
+            const uint64_t bd = umma::make_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
+            umma::mma_bf16(tmem, ad, bd, idesc, k16 > 0);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[row * N + c + i] = v[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+extern "C" int cg_debug_umma_gemm(const float *A, const float *B, float *D, int N, int Kd, int a_mn, int b_mn,
+                                  void *stream) {
+    CG_REQUIRE(A && B && D, "cg_debug_umma_gemm: NULL tensor");
+    CG_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256, "cg_debug_umma_gemm: N must be a multiple of 16 in [16, 256]");
+    CG_REQUIRE(Kd % 16 == 0 && Kd >= 16 && Kd <= 256, "cg_debug_umma_gemm: Kd must be a multiple of 16 in [16, 256]");
+    const size_t smem = sizeof(__nv_bfloat16) * (size_t)(128 + N) * Kd;
+    CG_CHECK_CUDA(cudaFuncSetAttribute(k_umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CgProfScope prof("umma_test", (cudaStream_t)stream);
+    k_umma_test<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, Kd, a_mn, b_mn);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

@@ -147,6 +147,14 @@ int cg_profile_enable(int on);
 int cg_profile_reset(void);
 int cg_profile_query(int index, char *name, int name_cap, double *total_ms, int64_t *count);
 
+/* ---- tcgen05 self-test ---------------------------------------------------- */
+/* One CTA computes D[128][N] = A . B^T with bf16 operands (round-to-nearest from the fp32
+ * inputs) and fp32 accumulation in TMEM, with the operands staged in shared memory in the
+ * K-major (x_mn = 0: A [128][Kd], B [N][Kd]) or MN-major (x_mn = 1: A [Kd][128], B [Kd][N])
+ * canonical layout.  Pins the descriptor encodings the fused kernels rely on.            */
+int cg_debug_umma_gemm(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, int a_mn,
+                       int b_mn, void *stream);
+
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32
  * arithmetic in the reference's order, including the reference's row-table
