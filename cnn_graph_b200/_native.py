@@ -51,6 +51,7 @@ _SIGNATURES = {
     'cg_profile_query': (c_int, [c_int, ctypes.c_char_p, c_int, ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(c_i64)]),
     'cg_debug_umma_gemm': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'cg_debug_umma_gemm_m': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'cg_host_metis_one_level': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                         c_void_p, ctypes.POINTER(c_i64)]),
     'cg_host_perm_level': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p]),

@@ -6,28 +6,32 @@
 #include "cg_common.cuh"
 #include "cg_umma.cuh"
 
+extern "C" int cg_debug_umma_gemm_m(const float *A, const float *B, float *D, int Mr, int N, int Kd, int a_mn,
+                                    int b_mn, void *stream);
+
 // A_src: a_mn == 0 -> [128][Kd] (k contiguous);  a_mn == 1 -> [Kd][128] (m contiguous)
 // B_src: b_mn == 0 -> [N][Kd];                   b_mn == 1 -> [Kd][N]
 __global__ void __launch_bounds__(128, 1)
 k_umma_test(const float *__restrict__ A_src, const float *__restrict__ B_src, float *__restrict__ D, int N, int Kd,
-            int a_mn, int b_mn) {
+            int a_mn_flags, int b_mn, int Mr) {
+    const int a_mn = a_mn_flags & 1;     // bit 1 of a_mn_flags: (M = 64 only) put the accumulator at TMEM lane offset 16
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __nv_bfloat16 *As = reinterpret_cast<__nv_bfloat16 *>(smem);
-    __nv_bfloat16 *Bs = As + 128 * Kd;
+    __nv_bfloat16 *Bs = As + Mr * Kd;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // strides (bytes).  K-major: LBO = between K chunks, SBO = between 8-row groups.
     //                   MN-major: SBO = between 8-element MN chunks, LBO = between 8-row K groups.
-    const uint32_t a_lbo = a_mn ? 128u * (128 / 8) : 128u;          // MN: k-group stride = 16 mn-chunks * 128 B
+    const uint32_t a_lbo = a_mn ? 128u * (Mr / 8) : 128u;          // MN: k-group stride = 16 mn-chunks * 128 B
     const uint32_t a_sbo = a_mn ? 128u : 128u * (Kd / 8);
     const uint32_t b_lbo = b_mn ? 128u * (N / 8) : 128u;
     const uint32_t b_sbo = b_mn ? 128u : 128u * (Kd / 8);
 
-    for (int e = tid; e < 128 * Kd; e += 128) {
+    for (int e = tid; e < Mr * Kd; e += 128) {
         int r, k;
-        if (a_mn) { k = e / 128; r = e % 128; } else { r = e / Kd; k = e % Kd; }
+        if (a_mn) { k = e / Mr; r = e % Mr; } else { r = e / Kd; k = e % Kd; }
         const float v = A_src[e];
         uint32_t off = a_mn ? (r / 8) * a_sbo + (k / 8) * a_lbo + (k % 8) * 16 + (r % 8) * 2
                             : (r / 8) * a_sbo + (k / 8) * a_lbo + (r % 8) * 16 + (k % 8) * 2;
@@ -55,12 +59,12 @@ k_umma_test(const float *__restrict__ A_src, const float *__restrict__ B_src, fl
     const uint32_t tmem = tmem_slot;
 
     if (tid == 0) {
-        const uint32_t idesc = umma::make_idesc_bf16(128, N, a_mn, b_mn);
+        const uint32_t idesc = umma::make_idesc_bf16(Mr, N, a_mn, b_mn);
         const uint32_t a0 = umma::smem_u32(As), b0 = umma::smem_u32(Bs);
         for (int k16 = 0; k16 < Kd / 16; ++k16) {
             const uint64_t ad = umma::make_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
             const uint64_t bd = umma::make_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
-            umma::mma_bf16(tmem, ad, bd, idesc, k16 > 0);
+            umma::mma_bf16(tmem + ((uint32_t)(Mr == 64 ? (a_mn_flags >> 1) * 16 : 0) << 16), ad, bd, idesc, k16 > 0);
         }
         umma::commit(&bar);
     }
@@ -82,13 +86,20 @@ k_umma_test(const float *__restrict__ A_src, const float *__restrict__ B_src, fl
 
 extern "C" int cg_debug_umma_gemm(const float *A, const float *B, float *D, int N, int Kd, int a_mn, int b_mn,
                                   void *stream) {
+    return cg_debug_umma_gemm_m(A, B, D, 128, N, Kd, a_mn, b_mn, stream);
+}
+
+// Same with Mr = 64 or 128 rows of A; D always receives all 128 TMEM lanes x N columns.
+extern "C" int cg_debug_umma_gemm_m(const float *A, const float *B, float *D, int Mr, int N, int Kd, int a_mn,
+                                    int b_mn, void *stream) {
+    CG_REQUIRE(Mr == 64 || Mr == 128, "cg_debug_umma_gemm_m: Mr must be 64 or 128");
     CG_REQUIRE(A && B && D, "cg_debug_umma_gemm: NULL tensor");
     CG_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256, "cg_debug_umma_gemm: N must be a multiple of 16 in [16, 256]");
     CG_REQUIRE(Kd % 16 == 0 && Kd >= 16 && Kd <= 256, "cg_debug_umma_gemm: Kd must be a multiple of 16 in [16, 256]");
     const size_t smem = sizeof(__nv_bfloat16) * (size_t)(128 + N) * Kd;
     CG_CHECK_CUDA(cudaFuncSetAttribute(k_umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CgProfScope prof("umma_test", (cudaStream_t)stream);
-    k_umma_test<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, Kd, a_mn, b_mn);
+    k_umma_test<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, Kd, a_mn, b_mn, Mr);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -154,6 +154,9 @@ int cg_profile_query(int index, char *name, int name_cap, double *total_ms, int6
  * canonical layout.  Pins the descriptor encodings the fused kernels rely on.            */
 int cg_debug_umma_gemm(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, int a_mn,
                        int b_mn, void *stream);
+/* Same with Mr = 64 or 128 rows of A; dev_D [128][N] receives all 128 TMEM lanes. */
+int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, int Mr, int N, int Kd,
+                         int a_mn, int b_mn, void *stream);
 
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32
