@@ -14,19 +14,34 @@ static size_t stack_bytes(const cg_graph *g, int N, int F, int K) {
 }
 
 extern "C" size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
-    (void)Fout;
     (void)flags;
-    if (!g || K <= 1) return 0;
-    return stack_bytes(g, N, Fin, K);
+    if (!g) return 0;
+    return (K > 1 ? stack_bytes(g, N, Fin, K) : 0) + cg_fused_workspace(Fin, Fout, K);
 }
 
 extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
                                                      int need_dx, int flags) {
     (void)flags;
     if (!g) return 0;
-    if (need_dx)
-        return stack_bytes(g, N, Fout, K) + cg_stack_t_plain_workspace(N, g->M, Fout, Fin, K, g->sm_count);
-    return stack_bytes(g, N, Fin, K) + cg_stack_t_plain_workspace(N, g->M, Fin, Fout, K, g->sm_count);
+    // either the Z-stack (width Fout) for dx and dW, or the X-stack (width Fin) for dW next to a fused dx
+    const size_t wide = stack_bytes(g, N, Fout > Fin ? Fout : Fin, K);
+    const size_t part_a = cg_stack_t_plain_workspace(N, g->M, Fout, Fin, K, g->sm_count);
+    const size_t part_b = cg_stack_t_plain_workspace(N, g->M, Fin, Fout, K, g->sm_count);
+    (void)need_dx;
+    return wide + cg_align_up(part_a > part_b ? part_a : part_b, 256) + cg_fused_workspace(Fin, Fout, K);
+}
+
+// fused kernel wanted and possible?  (CG_FILTER_FORCE_FUSED turns "not possible" into an error)
+static int want_fused(const char *who, const cg_graph *g, int N, int Fin, int Fout, int K, int flags, bool *use) {
+    *use = false;
+    if (flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) return CG_OK;
+    *use = cg_fused_supported(g, N, Fin, Fout, K);
+    if (!*use && (flags & CG_FILTER_FORCE_FUSED)) {
+        cg_set_error("%s: fused kernel requested but the shape is not supported (M=%d Fin=%d Fout=%d K=%d)", who, g->M,
+                     Fin, Fout, K);
+        return CG_ERR_ARG;
+    }
+    return CG_OK;
 }
 
 static int check_dims(const char *who, const cg_graph *g, int N, int Fin, int Fout, int K) {
@@ -44,13 +59,20 @@ extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const flo
     CG_REQUIRE(x && W && y, "cg_cheb_filter_fwd: NULL tensor");
     cudaStream_t s = (cudaStream_t)stream;
     const int M = g->M;
-    if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
-        return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, s);
     const size_t need = cg_cheb_filter_fwd_workspace_bytes(g, N, Fin, Fout, K, flags);
     if (workspace == nullptr || workspace_bytes < need) {
         cg_set_error("cg_cheb_filter_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
         return CG_ERR_WORKSPACE;
     }
+    bool fused = false;
+    rc = want_fused("cg_cheb_filter_fwd", g, N, Fin, Fout, K, flags, &fused);
+    if (rc != CG_OK) return rc;
+    if (fused) {
+        void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
+        return cg_run_fused(g, 0, x, W, y, N, Fin, Fout, K, false, wpack, s);
+    }
+    if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
+        return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, s);
     float *stack = reinterpret_cast<float *>(workspace);
     rc = cg_run_permute_abf(x, stack, N, M, Fin, s);                          // [N][M][F] -> [M][N][F]
     if (rc == CG_OK) rc = cg_run_basis(g, 0, stack, (int64_t)N * Fin, K, s, flags);
@@ -78,7 +100,18 @@ extern "C" int cg_cheb_filter_bwd(const cg_graph_t *g, const float *x, const flo
         return CG_ERR_WORKSPACE;
     }
     float *stack = reinterpret_cast<float *>(workspace);
+    bool fused = false;
     if (need_dx) {
+        rc = want_fused("cg_cheb_filter_bwd", g, N, Fout, Fin, K, flags, &fused);
+        if (rc != CG_OK) return rc;
+    }
+    if (fused) {
+        // dx by the fused kernel on L~^T (Z_k never materialised); dW = X_k^T gy from the narrower X-stack
+        void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
+        rc = cg_run_fused(g, 1, gy, W, dx, N, Fout, Fin, K, true, wpack, s);
+        if (rc != CG_OK) return rc;
+    }
+    if (need_dx && !fused) {
         float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fout, K));
         rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
         if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);

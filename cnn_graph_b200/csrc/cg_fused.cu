@@ -1,0 +1,473 @@
+// Fused Chebyshev filter (lib/models.py:192-224, lib/filter.py:45-95) for operators that fit
+// in shared memory: recurrence AND weight contraction in one persistent kernel; the
+// Chebyshev stack never leaves the SM.
+//
+//   per CTA, per group of S samples (rows r = s*M + m, R = S*M):
+//     X_0 = x                           cp.async.bulk of the contiguous [R][Fin] block (TMA engine)
+//     X_k = 2 L~ X_{k-1} - X_{k-2}      fp32, slabs in SMEM, CSR of L~ in SMEM, 128-bit gathers
+//     y  += X_k W_k                     tcgen05.mma, accumulators [R][Fout] in TMEM
+//   The fp32 slab is the master copy; every step also writes X_k as two bf16 planes
+//   (hi = rn(x), mid = rn(x - hi)) in the canonical K-major UMMA layout, and the product is
+//   formed as  hi*Whi + mid*Whi + hi*Wmid  (three bf16 MMAs, fp32 accumulate; the dropped
+//   terms are <= 2^-16 relative), which keeps the filter inside the reference's fp32
+//   tolerance (rtol 1e-4) while running on the tensor cores.
+//   Warp roles: 16 compute warps (gathers, staging, epilogue) + 1 issue warp (bulk copies of
+//   x / W_k, tcgen05.mma issue, commits).  The MMAs of step k run under the gathers of k+1.
+//
+// The same kernel computes dx = sum_k T_k(L~^T) gy W_k^T  (operator side = transpose,
+// W packed transposed, Fin <-> Fout).
+#include <algorithm>
+
+#include "cg_common.cuh"
+#include "cg_umma.cuh"
+
+namespace {
+
+constexpr int FC = 512;        // compute threads
+constexpr int FT = FC + 32;    // + issue warp
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_smem),
+                 "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &mid) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 m01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+    const __nv_bfloat162 m23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t *>(&h01);
+    hi.y = *reinterpret_cast<const uint32_t *>(&h23);
+    mid.x = *reinterpret_cast<const uint32_t *>(&m01);
+    mid.y = *reinterpret_cast<const uint32_t *>(&m23);
+}
+
+struct FusedParams {
+    const int *rowptr;
+    const int *col;
+    const float *val;
+    const float *x;              // [N][M][Fin]
+    const unsigned char *wp;     // packed W: [K][hi|mid][Fin*Fout] bf16, canonical K-major B operand
+    float *y;                    // [N][M][Fout]
+    int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab;
+    uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
+};
+
+// LPR lanes per row (Fin = 4 * LPR), IPT items (row, 4-column chunk) per compute thread
+template <int LPR, int IPT>
+__global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float2 *ent = reinterpret_cast<float2 *>(smem + p.off_ent);
+    unsigned char *stage = smem + p.off_stage;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *xbar = bars;            // [2] x slab of a group landed
+    uint64_t *wbar = bars + 2;        // [2] W_k landed
+    uint64_t *mbar = bars + 4;        // MMAs of the last issued step completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
+    const int R = S * M;
+    const bool is_issuer = warp == FC / 32;
+
+    // ---- one-time setup ------------------------------------------------------------
+    for (int e = tid; e < p.nnz; e += FT) {
+        float2 v;
+        v.x = p.val[e];
+        v.y = __int_as_float(p.col[e] * Fin);      // neighbour's float offset inside its sample's slab
+        ent[e] = v;
+    }
+    {   // pad rows of the A operand are never written by the steps: clear the staging planes once
+        uint4 *z = reinterpret_cast<uint4 *>(stage);
+        const int n16 = (int)(2 * p.plane_bytes / 16);
+        for (int i = tid; i < n16; i += FT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) umma::mbar_init(bars + i, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+
+    // per-item constants (identical for every step and group)
+    int i_start[IPT], i_len[IPT], i_gbase[IPT], i_soff[IPT], i_stoff[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int it = tid + i * FC;
+        const int r = it / LPR, l = it % LPR;
+        i_len[i] = -1;      // item does not exist
+        i_start[i] = 0;
+        i_gbase[i] = 0;
+        i_soff[i] = 0;
+        i_stoff[i] = 0;
+        if (!is_issuer && r < R) {
+            const int s = r / M, m = r - s * M;
+            const int b = p.rowptr[m];
+            i_start[i] = b;
+            i_len[i] = p.rowptr[m + 1] - b;
+            i_gbase[i] = s * M * Fin + 4 * l;
+            i_soff[i] = r * Fin + 4 * l;
+            i_stoff[i] = (l >> 1) * (int)p.lbo_a + (r >> 3) * 128 + (r & 7) * 16 + (l & 1) * 8;
+        }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (p.N + S - 1) / S;
+    const bool prefetch = p.nslab == 3;
+    const uint32_t slab0 = umma::smem_u32(smem + p.off_slab);
+    const uint32_t wbytes = 2 * p.wplane_bytes;
+    const uint32_t w0 = umma::smem_u32(smem + p.off_w);
+    int sP = 0, sQ = 1, sR = 2;           // slab roles: X_0 of this group, second slab, prefetch target
+    uint32_t mpar = 0;                    // parity of the next MMA-complete phase to wait for
+    uint32_t wpar = 0;                    // issuer: parities of the two W barriers (bit b)
+    int gi = 0;                           // groups processed by this CTA
+
+    if (is_issuer && lane == 0 && (int)blockIdx.x < G) {
+        const int Sg = min(S, p.N - (int)blockIdx.x * S);
+        const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
+        mbar_expect_tx(xbar, bytes);
+        bulk_g2s(slab0, p.x + (size_t)blockIdx.x * S * M * Fin, bytes, xbar);
+    }
+
+    for (int g = blockIdx.x; g < G; g += gridDim.x, ++gi) {
+        const int n0 = g * S;
+        const int Sg = min(S, p.N - n0);
+        const int Rg = Sg * M;
+        const int lim = Rg * Fin;         // items with i_soff >= lim belong to absent samples
+        float *slabP = reinterpret_cast<float *>(smem + p.off_slab + (size_t)sP * p.slab_bytes);
+        float *slabQ = reinterpret_cast<float *>(smem + p.off_slab + (size_t)sQ * p.slab_bytes);
+
+        if (is_issuer) {
+            // =========================== issue warp =====================================
+            if (lane == 0) {
+                // weights of steps 0 and 1 (all MMAs of the previous group have completed)
+                mbar_expect_tx(wbar, wbytes);
+                bulk_g2s(w0, p.wp, wbytes, wbar);
+                if (K > 1) {
+                    mbar_expect_tx(wbar + 1, wbytes);
+                    bulk_g2s(w0 + wbytes, p.wp + wbytes, wbytes, wbar + 1);
+                }
+                const int gn = g + gridDim.x;
+                if (prefetch) {
+                    if (gn < G) {       // next group's x into the spare slab
+                        const int Sn = min(S, p.N - gn * S);
+                        const uint32_t bytes = (uint32_t)Sn * M * Fin * 4u;
+                        umma::fence_proxy_async();
+                        mbar_expect_tx(xbar + ((gi + 1) & 1), bytes);
+                        bulk_g2s(slab0 + (uint32_t)sR * p.slab_bytes, p.x + (size_t)gn * S * M * Fin, bytes,
+                                 xbar + ((gi + 1) & 1));
+                    }
+                } else if (gi > 0) {    // no spare slab: load this group's x now
+                    const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
+                    umma::fence_proxy_async();
+                    mbar_expect_tx(xbar + (gi & 1), bytes);
+                    bulk_g2s(slab0 + (uint32_t)sP * p.slab_bytes, p.x + (size_t)n0 * M * Fin, bytes, xbar + (gi & 1));
+                }
+            }
+            const uint32_t idesc = umma::make_idesc_bf16(128, Fout, 0, 0);
+            const uint32_t a0 = umma::smem_u32(stage);
+            const uint32_t lbo_w = (uint32_t)Fout * 16u;
+            const int nk16 = Fin / 16;
+            for (int k = 0; k < K; ++k) {
+                __syncthreads();                                  // staging of step k is complete
+                if (lane == 0) {
+                    umma::mbar_wait(wbar + (k & 1), (wpar >> (k & 1)) & 1u);
+                    wpar ^= 1u << (k & 1);
+                    umma::fence_after_sync();
+                    const uint32_t wb = w0 + (uint32_t)(k & 1) * wbytes;
+                    for (int t = 0; t < p.tiles; ++t) {
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t ap = a0 + (pass == 1 ? p.plane_bytes : 0u) + (uint32_t)t * 2048u;
+                            const uint32_t bp = wb + (pass == 2 ? p.wplane_bytes : 0u);
+                            for (int j = 0; j < nk16; ++j) {
+                                const uint64_t ad = umma::make_desc(ap + (uint32_t)j * 2u * p.lbo_a, p.lbo_a, 128u);
+                                const uint64_t bd = umma::make_desc(bp + (uint32_t)j * 2u * lbo_w, lbo_w, 128u);
+                                umma::mma_bf16(tmem + (uint32_t)(t * Fout), ad, bd, idesc, (k | pass | j) != 0);
+                            }
+                        }
+                    }
+                    umma::commit(mbar);
+                    // W_{k+2} goes where W_k was, once the MMAs of step k have read it; waiting for every
+                    // step also guarantees that nothing is in flight when the group ends
+                    umma::mbar_wait(mbar, mpar);
+                    if (k + 2 < K) {
+                        mbar_expect_tx(wbar + (k & 1), wbytes);
+                        bulk_g2s(wb, p.wp + (size_t)(k + 2) * wbytes, wbytes, wbar + (k & 1));
+                    }
+                }
+                mpar ^= 1;
+                __syncwarp();
+            }
+        } else {
+            // =========================== compute warps ==================================
+            umma::mbar_wait(xbar + (gi & 1), (uint32_t)((gi >> 1) & 1));
+            float4 res[IPT];
+            // ---- step 0: X_0 = x
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                if (i_len[i] >= 0 && i_soff[i] < lim) res[i] = *reinterpret_cast<const float4 *>(slabP + i_soff[i]);
+            for (int k = 0; k < K; ++k) {
+                if (k > 0) {
+                    const float *prev = (k & 1) ? slabP : slabQ;     // X_{k-1}
+                    float *cur = (k & 1) ? slabQ : slabP;            // X_{k-2} -> X_k
+#pragma unroll
+                    for (int i = 0; i < IPT; ++i) {
+                        if (i_len[i] >= 0 && i_soff[i] < lim) {
+                            const float2 *e = ent + i_start[i];
+                            const float *pb = prev + i_gbase[i];
+                            const int n = i_len[i];
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            int j = 0;
+                            for (; j + 1 < n; j += 2) {
+                                const float2 e0 = e[j], e1 = e[j + 1];
+                                const float4 x0 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e0.y));
+                                const float4 x1 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e1.y));
+                                acc.x = fmaf(e0.x, x0.x, acc.x); acc.y = fmaf(e0.x, x0.y, acc.y);
+                                acc.z = fmaf(e0.x, x0.z, acc.z); acc.w = fmaf(e0.x, x0.w, acc.w);
+                                acc.x = fmaf(e1.x, x1.x, acc.x); acc.y = fmaf(e1.x, x1.y, acc.y);
+                                acc.z = fmaf(e1.x, x1.z, acc.z); acc.w = fmaf(e1.x, x1.w, acc.w);
+                            }
+                            if (j < n) {
+                                const float2 e0 = e[j];
+                                const float4 x0 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e0.y));
+                                acc.x = fmaf(e0.x, x0.x, acc.x); acc.y = fmaf(e0.x, x0.y, acc.y);
+                                acc.z = fmaf(e0.x, x0.z, acc.z); acc.w = fmaf(e0.x, x0.w, acc.w);
+                            }
+                            float4 *slot = reinterpret_cast<float4 *>(cur + i_soff[i]);
+                            if (k > 1) {
+                                const float4 o = *slot;
+                                acc = make_float4(fmaf(2.f, acc.x, -o.x), fmaf(2.f, acc.y, -o.y), fmaf(2.f, acc.z, -o.z),
+                                                  fmaf(2.f, acc.w, -o.w));
+                            }
+                            *slot = acc;
+                            res[i] = acc;
+                        }
+                    }
+                    // the staging planes are free once the MMAs of step k-1 have completed
+                    umma::mbar_wait(mbar, mpar);
+                    mpar ^= 1;
+                }
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    if (i_len[i] >= 0 && i_soff[i] < lim) {
+                        uint2 hi, mid;
+                        split4(res[i], hi, mid);
+                        *reinterpret_cast<uint2 *>(stage + i_stoff[i]) = hi;
+                        *reinterpret_cast<uint2 *>(stage + p.plane_bytes + i_stoff[i]) = mid;
+                    }
+                }
+                umma::fence_proxy_async();
+                if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
+                __syncthreads();
+            }
+            // ---- epilogue: TMEM -> registers -> y
+            umma::mbar_wait(mbar, mpar);
+            mpar ^= 1;
+            umma::fence_after_sync();
+            const int q = warp & 3, wq = warp >> 2;
+            const int nc8 = Fout / 8;
+            for (int idx = wq; idx < p.tiles * nc8; idx += 4) {
+                const int t = idx / nc8, c = idx - t * nc8;
+                const int r = t * 128 + 32 * q + lane;
+                float v[8];
+                umma::tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * Fout + c * 8), v);
+                umma::tmem_ld_wait();
+                if (r < Rg) {
+                    float *dst = p.y + ((size_t)n0 * M + r) * Fout + c * 8;
+                    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        // rotate the slabs: the prefetched block becomes X_0
+        if (prefetch) {
+            const int t = sP;
+            sP = sR;
+            sR = sQ;
+            sQ = t;
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// W [Fin*K, Fout] (row = f*K + k)            -> wp[k][hi|mid] with B(n = fout, q = f)
+// transposed: the operand is W^T per k: B(n = fin_ext, q = fout_ext), i.e. for the dx filter
+// (stack feature = fout of W, output = fin of W):  B(n, q) = W[(n*K + k) * Q + q]
+__global__ void __launch_bounds__(256)
+k_pack_w(const float *__restrict__ W, unsigned char *__restrict__ wp, int Q, int Nn, int K, int transposed) {
+    const int total = K * Q * Nn;
+    const uint32_t plane = (uint32_t)Q * Nn * 2u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / (Q * Nn);
+        const int rem = i - k * Q * Nn;
+        const int q = rem / Nn, n = rem - q * Nn;
+        const float w = transposed ? W[((size_t)n * K + k) * Q + q] : W[((size_t)q * K + k) * Nn + n];
+        __nv_bfloat16 hi, mid;
+        umma::split_bf16(w, hi, mid);
+        const uint32_t off = (uint32_t)(q >> 3) * (uint32_t)Nn * 16u + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u +
+                             (uint32_t)(q & 7) * 2u;
+        unsigned char *base = wp + (size_t)k * 2u * plane;
+        *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + plane + off) = mid;
+    }
+}
+
+struct Plan {
+    bool ok = false;
+    int S = 0, tiles = 0, ipt = 0, nslab = 0, tmem_cols = 0;
+    FusedParams fp;
+    size_t smem = 0;
+};
+
+static Plan make_plan(const cg_graph *g, int64_t nnz, int N, int Fin, int Fout, int K) {
+    Plan best;
+    if (Fin % 16 != 0 || Fin > 128 || (Fin & (Fin - 1)) != 0) return best;     // LPR in {4, 8, 16, 32}
+    if (Fout % 16 != 0 || Fout < 16 || Fout > 256) return best;
+    if (N <= 0 || K < 1) return best;
+    const int M = g->M, LPR = Fin / 4;
+    const double avg = M > 0 ? (double)nnz / M : 0.0;
+    double best_cost = 0.0;
+    for (int S = 1; S <= N && S <= 64; ++S) {
+        const int64_t R = (int64_t)S * M;
+        const int tiles = (int)cg_ceil_div(R, 128);
+        if ((int64_t)tiles * Fout > 512) break;
+        const int64_t items = R * LPR;
+        const int need = (int)cg_ceil_div(items, FC);
+        if (need > 8) break;        // res[] + item constants must stay in registers
+        const int ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+        const uint32_t Rp = (uint32_t)tiles * 128u;
+        const uint32_t lbo_a = Rp * 16u + 64u;
+        const uint32_t plane = (uint32_t)(Fin / 8) * lbo_a;
+        const uint32_t wplane = (uint32_t)Fin * Fout * 2u;
+        const uint32_t slab = (uint32_t)cg_align_up((size_t)R * Fin * 4, 128);
+        for (int nslab = 3; nslab >= 2; --nslab) {
+            FusedParams fp;
+            memset(&fp, 0, sizeof(fp));
+            uint32_t off = 0;
+            fp.off_bar = off;
+            off += 128;
+            fp.off_ent = off;
+            off += (uint32_t)cg_align_up((size_t)std::max<int64_t>(nnz, 1) * 8, 128);
+            fp.off_slab = off;
+            off += (uint32_t)nslab * slab;
+            fp.off_stage = off;
+            off += (uint32_t)cg_align_up(2 * (size_t)plane, 128);
+            fp.off_w = off;
+            off += 4 * wplane;
+            if (off > g->smem_optin) continue;
+            const int64_t G = cg_ceil_div(N, S);
+            const int64_t rounds = cg_ceil_div(G, g->sm_count);
+            const double step = (double)need * (avg * 7.0 + 40.0) + 300.0;
+            const double cost = (double)rounds * ((double)K * step + 600.0 + (double)R * Fout / 64.0) -
+                                (nslab == 3 ? 1.0 : 0.0);
+            if (!best.ok || cost < best_cost) {
+                best.ok = true;
+                best_cost = cost;
+                best.S = S;
+                best.tiles = tiles;
+                best.ipt = ipt;
+                best.nslab = nslab;
+                int cols = 32;
+                while (cols < tiles * Fout) cols *= 2;
+                best.tmem_cols = cols;
+                fp.S = S;
+                fp.tiles = tiles;
+                fp.tmem_cols = cols;
+                fp.nslab = nslab;
+                fp.slab_bytes = slab;
+                fp.plane_bytes = plane;
+                fp.lbo_a = lbo_a;
+                fp.wplane_bytes = wplane;
+                best.fp = fp;
+                best.smem = off;
+            }
+            break;      // 3 slabs fit: no need to look at 2
+        }
+    }
+    return best;
+}
+
+template <int LPR>
+static cudaError_t launch_lpr(const Plan &pl, dim3 grid, cudaStream_t s) {
+#define CG_FUSED_CASE(I)                                                                                         \
+    case I: {                                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(k_cheb_fused<LPR, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)pl.smem);                                                      \
+        if (e != cudaSuccess) return e;                                                                          \
+        k_cheb_fused<LPR, I><<<grid, FT, pl.smem, s>>>(pl.fp);                                                   \
+        return cudaGetLastError();                                                                               \
+    }
+    switch (pl.ipt) {
+        CG_FUSED_CASE(2)
+        CG_FUSED_CASE(4)
+        CG_FUSED_CASE(8)
+    }
+#undef CG_FUSED_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool cg_fused_supported(const cg_graph *g, int N, int Fin, int Fout, int K) {
+    return make_plan(g, g->nnz, N, Fin, Fout, K).ok;
+}
+
+size_t cg_fused_workspace(int Fin, int Fout, int K) { return cg_align_up((size_t)K * Fin * Fout * 4, 256); }
+
+int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, int N, int Fin,
+                 int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s) {
+    Plan pl = make_plan(g, g->nnz, N, Fin, Fout, K);
+    CG_REQUIRE(pl.ok, "cg_run_fused: shape not supported by the fused kernel (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
+    CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
+    const CgCsr &L = cg_side(g, transpose);
+    unsigned char *wp = reinterpret_cast<unsigned char *>(workspace);
+    {
+        CgProfScope prof("pack_w", s);
+        const int total = K * Fin * Fout;
+        k_pack_w<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1024), 256, 0, s>>>(W, wp, Fin, Fout, K,
+                                                                                           w_transposed ? 1 : 0);
+        CG_LAUNCH_CHECK();
+    }
+    FusedParams &fp = pl.fp;
+    fp.rowptr = L.rowptr;
+    fp.col = L.col;
+    fp.val = L.val;
+    fp.x = x;
+    fp.wp = wp;
+    fp.y = y;
+    fp.N = N;
+    fp.M = g->M;
+    fp.Fin = Fin;
+    fp.Fout = Fout;
+    fp.K = K;
+    fp.nnz = (int)g->nnz;
+    const int64_t G = cg_ceil_div(N, pl.S);
+    dim3 grid((unsigned)std::min<int64_t>(G, g->sm_count));
+    CgProfScope prof(transpose ? "fused_dx" : "fused_fwd", s);
+    cudaError_t e;
+    switch (Fin / 4) {
+        case 4: e = launch_lpr<4>(pl, grid, s); break;
+        case 8: e = launch_lpr<8>(pl, grid, s); break;
+        case 16: e = launch_lpr<16>(pl, grid, s); break;
+        default: e = launch_lpr<32>(pl, grid, s); break;
+    }
+    if (e != cudaSuccess) {
+        cg_set_error("cg_run_fused: launch failed: %s", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}

@@ -16,6 +16,8 @@ from ._native import check, ptr
 FILTER_DEFAULT = 0
 FILTER_FORCE_STREAMING = 1
 FILTER_FORCE_ONCHIP = 2
+FILTER_NO_FUSED = 4
+FILTER_FORCE_FUSED = 8
 
 
 def _stream():

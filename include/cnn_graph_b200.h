@@ -83,7 +83,9 @@ int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float 
 enum {
     CG_FILTER_DEFAULT = 0,
     CG_FILTER_FORCE_STREAMING = 1, /* never use the on-chip (SMEM-resident) kernels */
-    CG_FILTER_FORCE_ONCHIP = 2     /* fail with CG_ERR_ARG if the on-chip kernels do not fit */
+    CG_FILTER_FORCE_ONCHIP = 2,    /* fail with CG_ERR_ARG if the on-chip kernels do not fit */
+    CG_FILTER_NO_FUSED = 4,        /* never use the fused recurrence+contraction (tcgen05) kernel */
+    CG_FILTER_FORCE_FUSED = 8      /* fail with CG_ERR_ARG if the fused kernel does not support the shape */
 };
 size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
 size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,

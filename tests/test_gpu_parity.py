@@ -43,7 +43,7 @@ def tf_ref():
     return t
 
 
-FLAG_SETS = [0, 1]   # default (on-chip when it fits) and forced streaming
+FLAG_SETS = [0, 1, 4]   # default (fused / on-chip when it fits), forced streaming, on-chip without the fused kernel
 
 
 # --------------------------------------------------------------------------- basis
@@ -103,6 +103,77 @@ def test_filter_forward_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout,
     dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
     close(xt.grad, dx)
     close(Wt.grad, dW)
+
+
+# shapes the fused recurrence+contraction (tcgen05) kernel must accept: (level, N, Fin, Fout, K)
+FUSED_SHAPES = [
+    (2, 5, 32, 64, 25),      # C2 layer 2
+    (2, 301, 32, 64, 5),     # several groups per CTA (x prefetch, slab rotation), odd tail
+    (4, 37, 16, 48, 4),      # several samples per group, ragged last group
+    (3, 10, 64, 32, 3),
+    (4, 5, 128, 16, 2),
+    (3, 3, 32, 256, 1),      # K = 1: no recurrence
+    (1, 3, 16, 64, 4),       # M = 496: four MMA row tiles
+    (3, 150, 16, 16, 7),
+]
+
+
+@pytest.mark.parametrize('level,N,Fin,Fout,K', FUSED_SHAPES)
+def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K):
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(10 * level + K + N)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    y = ops.cheb_filter(dev(x), dev(W), L, K, lmax=2, flags=ops.FILTER_FORCE_FUSED)
+    close(y, tf_ref.chebyshev5(x, L, W, K))
+    # and the unfused CUDA path agrees too (same inputs, independent kernels)
+    y2 = ops.cheb_filter(dev(x), dev(W), L, K, lmax=2, flags=ops.FILTER_NO_FUSED)
+    close(y, y2.cpu().numpy())
+
+
+@pytest.mark.parametrize('level,N,Fin,Fout,K', [(2, 5, 32, 64, 25), (4, 37, 64, 16, 4), (3, 10, 32, 64, 3),
+                                                (3, 9, 16, 16, 1)])
+def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K):
+    """dx through the fused kernel on L~^T (needs Fout % 16 == 0), dW from the X-stack."""
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(20 * level + K + N)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, K, lmax=2, flags=ops.FILTER_FORCE_FUSED)
+    y.backward(dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
+
+
+def test_fused_filter_directed(ops, tf_ref, directed):
+    """Non-symmetric operator: the fused dx must use the true transpose."""
+    L = csr_from(directed, 'L')
+    M = L.shape[0]
+    rng = np.random.RandomState(11)
+    x = rng.standard_normal((6, M, 16)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((16 * 5, 32))).astype(np.float32)
+    gy = rng.standard_normal((6, M, 32)).astype(np.float32)
+    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, 5, lmax=3.5, flags=ops.FILTER_FORCE_FUSED)
+    close(y, tf_ref.chebyshev5(x, L, W, 5, lmax=3.5))
+    y.backward(dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, 5, gy, lmax=3.5)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
+
+
+def test_fused_unsupported_shape_raises(ops, c2):
+    from cnn_graph_b200 import _native
+    L = csr_from(c2, 'L3')
+    x = torch.zeros((2, L.shape[0], 3), device='cuda')
+    W = torch.zeros((3 * 4, 8), device='cuda')
+    with pytest.raises(_native.NativeError):
+        ops.cheb_filter(x, W, L, 4, flags=ops.FILTER_FORCE_FUSED)
 
 
 def test_filter_directed_lmax(ops, tf_ref, directed):
