@@ -62,6 +62,7 @@ struct CgCsr {
     int *rowptr = nullptr;
     int *col = nullptr;
     float *val = nullptr;
+    int *order = nullptr;    // rows sorted by descending length (stable): work dealing of the fused kernels
     float2 *ell = nullptr;   // .x = value, .y = __int_as_float(col)
     int width = 0;           // max row length (ELL width)
     int m_pad = 0;           // rows padded to a multiple of 32
@@ -104,7 +105,7 @@ int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, i
 
 // Fused recurrence + contraction (cg_fused.cu): y[n,m,:] = sum_k (T_k(L) x)[n,m,:] W_k with the operator side
 // chosen by `transpose`; w_transposed selects the dx form (W_k^T).  workspace: cg_fused_workspace bytes.
-bool cg_fused_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
+bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K);
 size_t cg_fused_workspace(int Fin, int Fout, int K);
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, int N, int Fin,
                  int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);

@@ -32,10 +32,11 @@ extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N,
 }
 
 // fused kernel wanted and possible?  (CG_FILTER_FORCE_FUSED turns "not possible" into an error)
-static int want_fused(const char *who, const cg_graph *g, int N, int Fin, int Fout, int K, int flags, bool *use) {
+static int want_fused(const char *who, const cg_graph *g, int transpose, int N, int Fin, int Fout, int K, int flags,
+                      bool *use) {
     *use = false;
     if (flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) return CG_OK;
-    *use = cg_fused_supported(g, N, Fin, Fout, K);
+    *use = cg_fused_supported(g, transpose, N, Fin, Fout, K);
     if (!*use && (flags & CG_FILTER_FORCE_FUSED)) {
         cg_set_error("%s: fused kernel requested but the shape is not supported (M=%d Fin=%d Fout=%d K=%d)", who, g->M,
                      Fin, Fout, K);
@@ -65,7 +66,7 @@ extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const flo
         return CG_ERR_WORKSPACE;
     }
     bool fused = false;
-    rc = want_fused("cg_cheb_filter_fwd", g, N, Fin, Fout, K, flags, &fused);
+    rc = want_fused("cg_cheb_filter_fwd", g, 0, N, Fin, Fout, K, flags, &fused);
     if (rc != CG_OK) return rc;
     if (fused) {
         void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
@@ -102,7 +103,7 @@ extern "C" int cg_cheb_filter_bwd(const cg_graph_t *g, const float *x, const flo
     float *stack = reinterpret_cast<float *>(workspace);
     bool fused = false;
     if (need_dx) {
-        rc = want_fused("cg_cheb_filter_bwd", g, N, Fout, Fin, K, flags, &fused);
+        rc = want_fused("cg_cheb_filter_bwd", g, 1, N, Fout, Fin, K, flags, &fused);
         if (rc != CG_OK) return rc;
     }
     if (fused) {

@@ -16,6 +16,8 @@
 //
 // The same kernel computes dx = sum_k T_k(L~^T) gy W_k^T  (operator side = transpose,
 // W packed transposed, Fin <-> Fout).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "cg_common.cuh"
@@ -49,14 +51,50 @@ __device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &mid) {
     mid.y = *reinterpret_cast<const uint32_t *>(&m23);
 }
 
+// shared-memory accesses with 32-bit addresses (one IADD of addressing, guaranteed predication)
+__device__ __forceinline__ void lds64_if(float2 &v, uint32_t addr, int j, int n) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, %4;\n\t@p ld.shared.v2.f32 {%0, %1}, [%2];\n\t}"
+                 : "+f"(v.x), "+f"(v.y)
+                 : "r"(addr), "r"(j), "r"(n));
+}
+__device__ __forceinline__ void lds128_if(float4 &v, uint32_t addr, int j, int n) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %5, %6;\n\t@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "r"(addr), "r"(j), "r"(n));
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void fma4(float4 &a, float s, const float4 x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+    a.z = fmaf(s, x.z, a.z);
+    a.w = fmaf(s, x.w, a.w);
+}
+
 struct FusedParams {
     const int *rowptr;
     const int *col;
     const float *val;
+    const int *order;            // rows by descending length
     const float *x;              // [N][M][Fin]
     const unsigned char *wp;     // packed W: [K][hi|mid][Fin*Fout] bf16, canonical K-major B operand
     float *y;                    // [N][M][Fout]
-    int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab;
+    long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][8]
+    int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab, nw, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
 };
 
@@ -78,11 +116,17 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
     const bool is_issuer = warp == FC / 32;
 
     // ---- one-time setup ------------------------------------------------------------
-    for (int e = tid; e < p.nnz; e += FT) {
-        float2 v;
-        v.x = p.val[e];
-        v.y = __int_as_float(p.col[e] * Fin);      // neighbour's float offset inside its sample's slab
-        ent[e] = v;
+    // operator as fixed-stride rows {weight, byte offset of the neighbour inside its sample's slab}; the tail of
+    // a row is {0, 0}, so the gather loops need neither row-length predicates nor tail handling
+    for (int i = tid; i < M * p.estride; i += FT) {
+        const int m = i / p.estride, j = i - m * p.estride;
+        const int b = p.rowptr[m], n = p.rowptr[m + 1] - b;
+        float2 v = make_float2(0.f, __int_as_float(0));
+        if (j < n) {
+            v.x = p.val[b + j];
+            v.y = __int_as_float(p.col[b + j] * Fin * 4);
+        }
+        ent[i] = v;
     }
     {   // pad rows of the A operand are never written by the steps: clear the staging planes once
         uint4 *z = reinterpret_cast<uint4 *>(stage);
@@ -95,27 +139,37 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
 
-    // per-item constants (identical for every step and group)
-    int i_start[IPT], i_len[IPT], i_gbase[IPT], i_soff[IPT], i_stoff[IPT];
+    // per-item constants (identical for every step and group).  Rows are dealt to the items in order of
+    // descending length, interleaving the samples of a group: the four rows of a warp-level item and the two
+    // items of a pair have (nearly) equal lengths, and every warp gets the same mix of long and short rows.
+    uint32_t a_ent[IPT], a_g[IPT], a_soff[IPT], a_stoff[IPT];
+    int nlen[IPT];
+    int wl[IPT / 2];
+    const uint32_t ent0 = umma::smem_u32(ent);
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const int it = tid + i * FC;
-        const int r = it / LPR, l = it % LPR;
-        i_len[i] = -1;      // item does not exist
-        i_start[i] = 0;
-        i_gbase[i] = 0;
-        i_soff[i] = 0;
-        i_stoff[i] = 0;
-        if (!is_issuer && r < R) {
-            const int s = r / M, m = r - s * M;
-            const int b = p.rowptr[m];
-            i_start[i] = b;
-            i_len[i] = p.rowptr[m + 1] - b;
-            i_gbase[i] = s * M * Fin + 4 * l;
-            i_soff[i] = r * Fin + 4 * l;
-            i_stoff[i] = (l >> 1) * (int)p.lbo_a + (r >> 3) * 128 + (r & 7) * 16 + (l & 1) * 8;
+        // the two items of a pair are adjacent in the dealing order
+        // (odd pair slots are dealt in reverse thread order: every warp gets the same mix of long and short rows)
+        const int qd = ((i >> 1) & 1) ? (FC / LPR - 1 - tid / LPR) : tid / LPR;
+        const int o = ((i >> 1) * (FC / LPR) + qd) * 2 + (i & 1), l = tid % LPR;
+        nlen[i] = 0;
+        a_ent[i] = ent0;
+        a_g[i] = 0;
+        a_soff[i] = 0xFFFFFFF0u;     // "absent": compares above every group's limit
+        a_stoff[i] = 0;
+        if (!is_issuer && o < R) {
+            const int s = o % S, m = p.order[o / S];
+            const int r = s * M + m;
+            a_ent[i] = ent0 + 8u * (uint32_t)(m * p.estride);
+            nlen[i] = p.rowptr[m + 1] - p.rowptr[m];
+            a_g[i] = 4u * (uint32_t)(s * M * Fin + 4 * l);
+            a_soff[i] = 4u * (uint32_t)(r * Fin + 4 * l);
+            a_stoff[i] = (uint32_t)((l >> 1) * (int)p.lbo_a + (r >> 3) * 128 + (r & 7) * 16 + (l & 1) * 8);
         }
     }
+#pragma unroll
+    for (int pr = 0; pr < IPT / 2; ++pr)
+        wl[pr] = __reduce_max_sync(0xffffffffu, max(nlen[2 * pr], nlen[2 * pr + 1]));
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -144,8 +198,6 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
         const int Sg = min(S, p.N - n0);
         const int Rg = Sg * M;
         const int lim = Rg * Fin;         // items with i_soff >= lim belong to absent samples
-        float *slabP = reinterpret_cast<float *>(smem + p.off_slab + (size_t)sP * p.slab_bytes);
-        float *slabQ = reinterpret_cast<float *>(smem + p.off_slab + (size_t)sQ * p.slab_bytes);
 
         if (is_issuer) {
             // =========================== issue warp =====================================
@@ -153,7 +205,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 // weights of steps 0 and 1 (all MMAs of the previous group have completed)
                 mbar_expect_tx(wbar, wbytes);
                 bulk_g2s(w0, p.wp, wbytes, wbar);
-                if (K > 1) {
+                if (K > 1 && p.nw > 1) {
                     mbar_expect_tx(wbar + 1, wbytes);
                     bulk_g2s(w0 + wbytes, p.wp + wbytes, wbytes, wbar + 1);
                 }
@@ -181,10 +233,14 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
             for (int k = 0; k < K; ++k) {
                 __syncthreads();                                  // staging of step k is complete
                 if (lane == 0) {
-                    umma::mbar_wait(wbar + (k & 1), (wpar >> (k & 1)) & 1u);
-                    wpar ^= 1u << (k & 1);
+                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
+                    if (tr) p.trace[k * 8 + 4] = clock64();
+                    const int b = k & (p.nw - 1);
+                    umma::mbar_wait(wbar + b, (wpar >> b) & 1u);
+                    wpar ^= 1u << b;
                     umma::fence_after_sync();
-                    const uint32_t wb = w0 + (uint32_t)(k & 1) * wbytes;
+                    if (tr) p.trace[k * 8 + 5] = clock64();
+                    const uint32_t wb = w0 + (uint32_t)b * wbytes;
                     for (int t = 0; t < p.tiles; ++t) {
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
@@ -198,12 +254,14 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                         }
                     }
                     umma::commit(mbar);
-                    // W_{k+2} goes where W_k was, once the MMAs of step k have read it; waiting for every
+                    if (tr) p.trace[k * 8 + 6] = clock64();
+                    // W_{k+nw} goes where W_k was, once the MMAs of step k have read it; waiting for every
                     // step also guarantees that nothing is in flight when the group ends
                     umma::mbar_wait(mbar, mpar);
-                    if (k + 2 < K) {
-                        mbar_expect_tx(wbar + (k & 1), wbytes);
-                        bulk_g2s(wb, p.wp + (size_t)(k + 2) * wbytes, wbytes, wbar + (k & 1));
+                    if (tr) p.trace[k * 8 + 7] = clock64();
+                    if (k + p.nw < K) {
+                        mbar_expect_tx(wbar + b, wbytes);
+                        bulk_g2s(wb, p.wp + (size_t)(k + p.nw) * wbytes, wbytes, wbar + b);
                     }
                 }
                 mpar ^= 1;
@@ -212,63 +270,75 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
         } else {
             // =========================== compute warps ==================================
             umma::mbar_wait(xbar + (gi & 1), (uint32_t)((gi >> 1) & 1));
-            float4 res[IPT];
+            const uint32_t limb = 4u * (uint32_t)lim;
+            const uint32_t aP = slab0 + (uint32_t)sP * p.slab_bytes, aQ = slab0 + (uint32_t)sQ * p.slab_bytes;
+            const uint32_t st0 = umma::smem_u32(stage);
+            float4 res[IPT], old[IPT];     // the thread's own X_{k-1} (X_k after the step) and X_{k-2}
             // ---- step 0: X_0 = x
 #pragma unroll
             for (int i = 0; i < IPT; ++i)
-                if (i_len[i] >= 0 && i_soff[i] < lim) res[i] = *reinterpret_cast<const float4 *>(slabP + i_soff[i]);
+                if (a_soff[i] < limb) res[i] = lds128(aP + a_soff[i]);
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && tid == 0;
             for (int k = 0; k < K; ++k) {
+                if (tr) p.trace[k * 8 + 0] = clock64();
                 if (k > 0) {
-                    const float *prev = (k & 1) ? slabP : slabQ;     // X_{k-1}
-                    float *cur = (k & 1) ? slabQ : slabP;            // X_{k-2} -> X_k
+                    const uint32_t prev = (k & 1) ? aP : aQ;     // X_{k-1}
+                    const uint32_t cur = (k & 1) ? aQ : aP;      // X_{k-2} -> X_k
 #pragma unroll
-                    for (int i = 0; i < IPT; ++i) {
-                        if (i_len[i] >= 0 && i_soff[i] < lim) {
-                            const float2 *e = ent + i_start[i];
-                            const float *pb = prev + i_gbase[i];
-                            const int n = i_len[i];
-                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                            int j = 0;
-                            for (; j + 1 < n; j += 2) {
-                                const float2 e0 = e[j], e1 = e[j + 1];
-                                const float4 x0 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e0.y));
-                                const float4 x1 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e1.y));
-                                acc.x = fmaf(e0.x, x0.x, acc.x); acc.y = fmaf(e0.x, x0.y, acc.y);
-                                acc.z = fmaf(e0.x, x0.z, acc.z); acc.w = fmaf(e0.x, x0.w, acc.w);
-                                acc.x = fmaf(e1.x, x1.x, acc.x); acc.y = fmaf(e1.x, x1.y, acc.y);
-                                acc.z = fmaf(e1.x, x1.z, acc.z); acc.w = fmaf(e1.x, x1.w, acc.w);
-                            }
-                            if (j < n) {
-                                const float2 e0 = e[j];
-                                const float4 x0 = *reinterpret_cast<const float4 *>(pb + __float_as_int(e0.y));
-                                acc.x = fmaf(e0.x, x0.x, acc.x); acc.y = fmaf(e0.x, x0.y, acc.y);
-                                acc.z = fmaf(e0.x, x0.z, acc.z); acc.w = fmaf(e0.x, x0.w, acc.w);
-                            }
-                            float4 *slot = reinterpret_cast<float4 *>(cur + i_soff[i]);
-                            if (k > 1) {
-                                const float4 o = *slot;
-                                acc = make_float4(fmaf(2.f, acc.x, -o.x), fmaf(2.f, acc.y, -o.y), fmaf(2.f, acc.z, -o.z),
-                                                  fmaf(2.f, acc.w, -o.w));
-                            }
-                            *slot = acc;
-                            res[i] = acc;
+                    for (int pr = 0; pr < IPT / 2; ++pr) {
+                        const int i0 = 2 * pr, i1 = 2 * pr + 1;
+                        const uint32_t g0 = prev + a_g[i0], g1 = prev + a_g[i1];
+                        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+                        const int trips = wl[pr];
+                        const int jlast = p.estride - 2;
+                        float4 e0 = lds128(a_ent[i0]), e1 = lds128(a_ent[i1]);     // two {weight, offset} entries each
+                        for (int j = 0; j < trips; j += 2) {
+                            const float4 x00 = lds128(g0 + (uint32_t)__float_as_int(e0.y));
+                            const float4 x10 = lds128(g1 + (uint32_t)__float_as_int(e1.y));
+                            const float4 x01 = lds128(g0 + (uint32_t)__float_as_int(e0.w));
+                            const float4 x11 = lds128(g1 + (uint32_t)__float_as_int(e1.w));
+                            const float w00 = e0.x, w01 = e0.z, w10 = e1.x, w11 = e1.z;
+                            const uint32_t jn = 8u * (uint32_t)min(j + 2, jlast);     // next entries (clamped in-row)
+                            e0 = lds128(a_ent[i0] + jn);
+                            e1 = lds128(a_ent[i1] + jn);
+                            fma4(acc0, w00, x00);
+                            fma4(acc1, w10, x10);
+                            fma4(acc0, w01, x01);
+                            fma4(acc1, w11, x11);
                         }
+                        // X_k = 2 L X_{k-1} - X_{k-2}; the thread's own X_{k-2} is still in registers
+                        if (k > 1) {
+                            const float4 o0 = old[i0], o1 = old[i1];
+                            acc0 = make_float4(fmaf(2.f, acc0.x, -o0.x), fmaf(2.f, acc0.y, -o0.y), fmaf(2.f, acc0.z, -o0.z),
+                                               fmaf(2.f, acc0.w, -o0.w));
+                            acc1 = make_float4(fmaf(2.f, acc1.x, -o1.x), fmaf(2.f, acc1.y, -o1.y), fmaf(2.f, acc1.z, -o1.z),
+                                               fmaf(2.f, acc1.w, -o1.w));
+                        }
+                        old[i0] = res[i0];
+                        old[i1] = res[i1];
+                        res[i0] = acc0;
+                        res[i1] = acc1;
+                        if (a_soff[i0] < limb) sts128(cur + a_soff[i0], acc0);
+                        if (a_soff[i1] < limb) sts128(cur + a_soff[i1], acc1);
                     }
                     // the staging planes are free once the MMAs of step k-1 have completed
+                    if (tr) p.trace[k * 8 + 1] = clock64();
                     umma::mbar_wait(mbar, mpar);
                     mpar ^= 1;
                 }
+                if (tr) p.trace[k * 8 + 2] = clock64();
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
-                    if (i_len[i] >= 0 && i_soff[i] < lim) {
+                    if (a_soff[i] < limb) {
                         uint2 hi, mid;
                         split4(res[i], hi, mid);
-                        *reinterpret_cast<uint2 *>(stage + i_stoff[i]) = hi;
-                        *reinterpret_cast<uint2 *>(stage + p.plane_bytes + i_stoff[i]) = mid;
+                        sts64(st0 + a_stoff[i], hi);
+                        sts64(st0 + p.plane_bytes + a_stoff[i], mid);
                     }
                 }
                 umma::fence_proxy_async();
                 if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
+                if (tr) p.trace[k * 8 + 3] = clock64();
                 __syncthreads();
             }
             // ---- epilogue: TMEM -> registers -> y
@@ -333,7 +403,7 @@ struct Plan {
     size_t smem = 0;
 };
 
-static Plan make_plan(const cg_graph *g, int64_t nnz, int N, int Fin, int Fout, int K) {
+static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin, int Fout, int K) {
     Plan best;
     if (Fin % 16 != 0 || Fin > 128 || (Fin & (Fin - 1)) != 0) return best;     // LPR in {4, 8, 16, 32}
     if (Fout % 16 != 0 || Fout < 16 || Fout > 256) return best;
@@ -341,7 +411,12 @@ static Plan make_plan(const cg_graph *g, int64_t nnz, int N, int Fin, int Fout, 
     const int M = g->M, LPR = Fin / 4;
     const double avg = M > 0 ? (double)nnz / M : 0.0;
     double best_cost = 0.0;
-    for (int S = 1; S <= N && S <= 64; ++S) {
+    int s_lo = 1, s_hi = 64;
+    if (const char *env = getenv("CG_FUSED_S")) {       // tuning / debugging aid: pin the samples per group
+        const int v = atoi(env);
+        if (v > 0) s_lo = s_hi = v;
+    }
+    for (int S = s_lo; S <= N && S <= s_hi; ++S) {
         const int64_t R = (int64_t)S * M;
         const int tiles = (int)cg_ceil_div(R, 128);
         if ((int64_t)tiles * Fout > 512) break;
@@ -354,26 +429,28 @@ static Plan make_plan(const cg_graph *g, int64_t nnz, int N, int Fin, int Fout, 
         const uint32_t plane = (uint32_t)(Fin / 8) * lbo_a;
         const uint32_t wplane = (uint32_t)Fin * Fout * 2u;
         const uint32_t slab = (uint32_t)cg_align_up((size_t)R * Fin * 4, 128);
-        for (int nslab = 3; nslab >= 2; --nslab) {
+        const int estride = std::max(2, (width + 1) & ~1);      // even: 16-byte aligned entry pairs
+        for (int cfg = 0; cfg < 3; ++cfg) {
+            const int nslab = cfg == 0 ? 3 : 2, nw = cfg == 2 ? 1 : 2;
             FusedParams fp;
             memset(&fp, 0, sizeof(fp));
             uint32_t off = 0;
             fp.off_bar = off;
             off += 128;
             fp.off_ent = off;
-            off += (uint32_t)cg_align_up((size_t)std::max<int64_t>(nnz, 1) * 8, 128);
+            off += (uint32_t)cg_align_up((size_t)M * estride * 8, 128);
             fp.off_slab = off;
             off += (uint32_t)nslab * slab;
             fp.off_stage = off;
             off += (uint32_t)cg_align_up(2 * (size_t)plane, 128);
             fp.off_w = off;
-            off += 4 * wplane;
+            off += (uint32_t)nw * 2u * wplane;
             if (off > g->smem_optin) continue;
             const int64_t G = cg_ceil_div(N, S);
             const int64_t rounds = cg_ceil_div(G, g->sm_count);
-            const double step = (double)need * (avg * 7.0 + 40.0) + 300.0;
+            const double step = (double)need * (avg * 7.0 + 40.0) * (need > 4 ? 1.25 : 1.0) + 300.0;   // > 4: spills
             const double cost = (double)rounds * ((double)K * step + 600.0 + (double)R * Fout / 64.0) -
-                                (nslab == 3 ? 1.0 : 0.0);
+                                (nslab == 3 ? 1.0 : 0.0) - (nw == 2 ? 0.5 : 0.0);
             if (!best.ok || cost < best_cost) {
                 best.ok = true;
                 best_cost = cost;
@@ -388,6 +465,8 @@ static Plan make_plan(const cg_graph *g, int64_t nnz, int N, int Fin, int Fout, 
                 fp.tiles = tiles;
                 fp.tmem_cols = cols;
                 fp.nslab = nslab;
+                fp.nw = nw;
+                fp.estride = estride;
                 fp.slab_bytes = slab;
                 fp.plane_bytes = plane;
                 fp.lbo_a = lbo_a;
@@ -422,15 +501,22 @@ static cudaError_t launch_lpr(const Plan &pl, dim3 grid, cudaStream_t s) {
 
 }  // namespace
 
-bool cg_fused_supported(const cg_graph *g, int N, int Fin, int Fout, int K) {
-    return make_plan(g, g->nnz, N, Fin, Fout, K).ok;
+static long long *g_fused_trace = nullptr;
+// debug aid (not in the public header): clock64 stamps of CTA 0's second group, [K][8] int64 on the device
+extern "C" int cg_debug_fused_trace(long long *dev_buf) {
+    g_fused_trace = dev_buf;
+    return CG_OK;
+}
+
+bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K) {
+    return make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K).ok;
 }
 
 size_t cg_fused_workspace(int Fin, int Fout, int K) { return cg_align_up((size_t)K * Fin * Fout * 4, 256); }
 
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, int N, int Fin,
                  int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s) {
-    Plan pl = make_plan(g, g->nnz, N, Fin, Fout, K);
+    Plan pl = make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K);
     CG_REQUIRE(pl.ok, "cg_run_fused: shape not supported by the fused kernel (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
     CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
     const CgCsr &L = cg_side(g, transpose);
@@ -446,6 +532,7 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.rowptr = L.rowptr;
     fp.col = L.col;
     fp.val = L.val;
+    fp.order = L.order;
     fp.x = x;
     fp.wp = wp;
     fp.y = y;
@@ -455,6 +542,7 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.Fout = Fout;
     fp.K = K;
     fp.nnz = (int)g->nnz;
+    fp.trace = g_fused_trace;
     const int64_t G = cg_ceil_div(N, pl.S);
     dim3 grid((unsigned)std::min<int64_t>(G, g->sm_count));
     CgProfScope prof(transpose ? "fused_dx" : "fused_fwd", s);

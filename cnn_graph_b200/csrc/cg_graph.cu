@@ -34,6 +34,15 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
         CG_CHECK_CUDA(cudaMemcpy(dst.col, col.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
         CG_CHECK_CUDA(cudaMemcpy(dst.val, val.data(), sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice));
     }
+    {
+        std::vector<int> order(M);
+        for (int m = 0; m < M; ++m) order[m] = m;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b];
+        });
+        CG_CHECK_CUDA(cudaMalloc(&dst.order, sizeof(int) * (size_t)M));
+        CG_CHECK_CUDA(cudaMemcpy(dst.order, order.data(), sizeof(int) * (size_t)M, cudaMemcpyHostToDevice));
+    }
     int width = 0;
     for (int m = 0; m < M; ++m) width = std::max(width, rowptr[m + 1] - rowptr[m]);
     dst.width = width;
@@ -60,6 +69,7 @@ static void free_side(CgCsr &s) {
     cudaFree(s.rowptr);
     cudaFree(s.col);
     cudaFree(s.val);
+    cudaFree(s.order);
     cudaFree(s.ell);
     s = CgCsr();
 }
