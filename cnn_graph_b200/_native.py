@@ -35,6 +35,11 @@ _SIGNATURES = {
                                    c_void_p, c_size_t, c_int, c_void_p]),
     'cg_cheb_filter_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    'cg_cheb_filter_stack_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    'cg_cheb_filter_fwd_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_size_t, c_int, c_void_p]),
+    'cg_cheb_filter_bwd_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     'cg_bias_act_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'cg_bias_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p]),

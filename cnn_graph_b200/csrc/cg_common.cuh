@@ -103,12 +103,23 @@ size_t cg_stack_t_plain_workspace(int N, int M, int Fa, int Fb, int K, int sm_co
 int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, int M, int Fa, int Fb, int K,
                          bool swap, float *workspace, int sm_count, cudaStream_t s);
 
+// dW[...] = sum over `splits` partial results part[split][k*Fa + a][b] (deterministic, no atomics)
+int cg_reduce_partials(const float *part, float *dW, int splits, int Fa, int Fb, int K, bool swap, cudaStream_t s);
+
+// Tensor-core form of stack_t_plain (cg_dw_umma.cu): same contract, bf16x3 split with fp32 accumulation in TMEM.
+bool cg_dw_umma_supported(int N, int M, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+size_t cg_dw_umma_workspace(int N, int M, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+//   sample_major: stack rows are r = n*M + m (the layout of T itself) instead of r = m*N + n.
+int cg_run_dw_umma(const float *stack, const float *T, float *dW, int N, int M, int Fa, int Fb, int K, bool swap,
+                   bool sample_major, float *workspace, int sm_count, size_t smem_limit, cudaStream_t s);
+
 // Fused recurrence + contraction (cg_fused.cu): y[n,m,:] = sum_k (T_k(L) x)[n,m,:] W_k with the operator side
 // chosen by `transpose`; w_transposed selects the dx form (W_k^T).  workspace: cg_fused_workspace bytes.
 bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K);
 size_t cg_fused_workspace(int Fin, int Fout, int K);
-int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, int N, int Fin,
-                 int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);
+//   stack_out (optional): the basis X_k, [K][N][M][Fin] (sample-major), for a later weight gradient.
+int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
+                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);
 
 static inline int64_t cg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

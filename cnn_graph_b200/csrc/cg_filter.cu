@@ -19,14 +19,29 @@ extern "C" size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N,
     return (K > 1 ? stack_bytes(g, N, Fin, K) : 0) + cg_fused_workspace(Fin, Fout, K);
 }
 
+// stack^T x plain: tensor-core kernel when the shape allows it, FFMA kernel otherwise
+static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
+    const size_t a = cg_stack_t_plain_workspace(N, g->M, Fa, Fb, K, g->sm_count);
+    const size_t b = cg_dw_umma_workspace(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
+    return a > b ? a : b;
+}
+
+static int run_dw(const cg_graph *g, const float *stack, const float *T, float *dW, int N, int Fa, int Fb, int K,
+                  bool swap, float *part, int flags, cudaStream_t s) {
+    const bool tc = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) &&
+                    cg_dw_umma_supported(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
+    if (tc) return cg_run_dw_umma(stack, T, dW, N, g->M, Fa, Fb, K, swap, false, part, g->sm_count, g->smem_optin, s);
+    return cg_run_stack_t_plain(stack, T, dW, N, g->M, Fa, Fb, K, swap, part, g->sm_count, s);
+}
+
 extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
                                                      int need_dx, int flags) {
     (void)flags;
     if (!g) return 0;
     // either the Z-stack (width Fout) for dx and dW, or the X-stack (width Fin) for dW next to a fused dx
     const size_t wide = stack_bytes(g, N, Fout > Fin ? Fout : Fin, K);
-    const size_t part_a = cg_stack_t_plain_workspace(N, g->M, Fout, Fin, K, g->sm_count);
-    const size_t part_b = cg_stack_t_plain_workspace(N, g->M, Fin, Fout, K, g->sm_count);
+    const size_t part_a = dw_workspace(g, N, Fout, Fin, K);
+    const size_t part_b = dw_workspace(g, N, Fin, Fout, K);
     (void)need_dx;
     return wide + cg_align_up(part_a > part_b ? part_a : part_b, 256) + cg_fused_workspace(Fin, Fout, K);
 }
@@ -52,11 +67,32 @@ static int check_dims(const char *who, const cg_graph *g, int N, int Fin, int Fo
     return CG_OK;
 }
 
+// The forward pass can leave the basis X_k behind for the weight gradient ([K][N][M][Fin], sample-major) when
+// both the fused kernel and the tensor-core dW kernel take the shape.
+static bool can_save_stack(const cg_graph *g, int N, int Fin, int Fout, int K, int flags) {
+    if (flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) return false;
+    return N > 0 && cg_fused_supported(g, 0, N, Fin, Fout, K) &&
+           cg_dw_umma_supported(N, g->M, Fin, Fout, K, g->sm_count, g->smem_optin);
+}
+
+extern "C" size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
+    if (!g || Fin <= 0 || Fout <= 0 || K < 1) return 0;
+    return can_save_stack(g, N, Fin, Fout, K, flags) ? sizeof(float) * (size_t)K * N * g->M * Fin : 0;
+}
+
 extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const float *W, float *y, int N, int Fin,
                                   int Fout, int K, void *workspace, size_t workspace_bytes, int flags, void *stream) {
+    return cg_cheb_filter_fwd_ex(g, x, W, y, nullptr, N, Fin, Fout, K, workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const float *W, float *y, float *stack_out,
+                                     int N, int Fin, int Fout, int K, void *workspace, size_t workspace_bytes,
+                                     int flags, void *stream) {
     int rc = check_dims("cg_cheb_filter_fwd", g, N, Fin, Fout, K);
     if (rc != CG_OK) return rc;
     if (N == 0) return CG_OK;
+    CG_REQUIRE(stack_out == nullptr || can_save_stack(g, N, Fin, Fout, K, flags),
+               "cg_cheb_filter_fwd_ex: this shape cannot save the basis (cg_cheb_filter_stack_bytes returned 0)");
     CG_REQUIRE(x && W && y, "cg_cheb_filter_fwd: NULL tensor");
     cudaStream_t s = (cudaStream_t)stream;
     const int M = g->M;
@@ -70,7 +106,7 @@ extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const flo
     if (rc != CG_OK) return rc;
     if (fused) {
         void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
-        return cg_run_fused(g, 0, x, W, y, N, Fin, Fout, K, false, wpack, s);
+        return cg_run_fused(g, 0, x, W, y, stack_out, N, Fin, Fout, K, false, wpack, s);
     }
     if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
         return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, s);
@@ -84,6 +120,13 @@ extern "C" int cg_cheb_filter_fwd(const cg_graph_t *g, const float *x, const flo
 extern "C" int cg_cheb_filter_bwd(const cg_graph_t *g, const float *x, const float *W, const float *gy, float *dx,
                                   float *dW, int N, int Fin, int Fout, int K, void *workspace, size_t workspace_bytes,
                                   int flags, void *stream) {
+    return cg_cheb_filter_bwd_ex(g, x, W, gy, nullptr, dx, dW, N, Fin, Fout, K, workspace, workspace_bytes, flags,
+                                 stream);
+}
+
+extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const float *W, const float *gy,
+                                     const float *saved_stack, float *dx, float *dW, int N, int Fin, int Fout, int K,
+                                     void *workspace, size_t workspace_bytes, int flags, void *stream) {
     int rc = check_dims("cg_cheb_filter_bwd", g, N, Fin, Fout, K);
     if (rc != CG_OK) return rc;
     CG_REQUIRE(dW != nullptr, "cg_cheb_filter_bwd: dW is NULL");
@@ -101,28 +144,41 @@ extern "C" int cg_cheb_filter_bwd(const cg_graph_t *g, const float *x, const flo
         return CG_ERR_WORKSPACE;
     }
     float *stack = reinterpret_cast<float *>(workspace);
-    bool fused = false;
+    bool have_dW = false;
+    if (saved_stack != nullptr) {
+        // dW[fin*K+k, fo] = sum_{n,m} X_k[n,m,fin] gy[n,m,fo] straight from the basis the forward pass left behind
+        CG_REQUIRE(can_save_stack(g, N, Fin, Fout, K, flags), "cg_cheb_filter_bwd_ex: saved stack given for a shape that cannot save one");
+        float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K));
+        rc = cg_run_dw_umma(saved_stack, gy, dW, N, M, Fin, Fout, K, false, true, part, g->sm_count, g->smem_optin, s);
+        if (rc != CG_OK) return rc;
+        have_dW = true;
+    }
     if (need_dx) {
+        bool fused = false;
         rc = want_fused("cg_cheb_filter_bwd", g, 1, N, Fout, Fin, K, flags, &fused);
         if (rc != CG_OK) return rc;
+        if (fused) {
+            // dx by the fused kernel on L~^T (Z_k never materialised)
+            void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
+            rc = cg_run_fused(g, 1, gy, W, dx, nullptr, N, Fout, Fin, K, true, wpack, s);
+            if (rc != CG_OK) return rc;
+        } else {
+            // Z_k = T_k(L~^T) gy materialised: dx = Z W^T, and dW = x^T Z_k if still missing
+            float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fout, K));
+            rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
+            if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);
+            if (rc == CG_OK) rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, s);
+            if (rc == CG_OK && !have_dW) rc = run_dw(g, stack, x, dW, N, Fout, Fin, K, true, part, flags, s);
+            if (rc != CG_OK) return rc;
+            have_dW = true;
+        }
     }
-    if (fused) {
-        // dx by the fused kernel on L~^T (Z_k never materialised); dW = X_k^T gy from the narrower X-stack
-        void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
-        rc = cg_run_fused(g, 1, gy, W, dx, N, Fout, Fin, K, true, wpack, s);
-        if (rc != CG_OK) return rc;
-    }
-    if (need_dx && !fused) {
-        float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fout, K));
-        rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
-        if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);
-        if (rc == CG_OK) rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, s);
-        if (rc == CG_OK) rc = cg_run_stack_t_plain(stack, x, dW, N, M, Fout, Fin, K, true, part, g->sm_count, s);
-    } else {
+    if (!have_dW) {
+        // dW = X_k^T gy with the (narrower) X-stack recomputed
         float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K));
         rc = cg_run_permute_abf(x, stack, N, M, Fin, s);
         if (rc == CG_OK) rc = cg_run_basis(g, 0, stack, (int64_t)N * Fin, K, s, flags);
-        if (rc == CG_OK) rc = cg_run_stack_t_plain(stack, gy, dW, N, M, Fin, Fout, K, false, part, g->sm_count, s);
+        if (rc == CG_OK) rc = run_dw(g, stack, gy, dW, N, Fin, Fout, K, false, part, flags, s);
     }
     return rc;
 }

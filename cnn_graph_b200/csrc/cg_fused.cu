@@ -93,6 +93,7 @@ struct FusedParams {
     const float *x;              // [N][M][Fin]
     const unsigned char *wp;     // packed W: [K][hi|mid][Fin*Fout] bf16, canonical K-major B operand
     float *y;                    // [N][M][Fout]
+    float *stack_out;            // optional: X_k for the weight gradient, [K][N][M][Fin] (sample-major)
     long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][8]
     int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab, nw, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
             const uint32_t idesc = umma::make_idesc_bf16(128, Fout, 0, 0);
             const uint32_t a0 = umma::smem_u32(stage);
             const uint32_t lbo_w = (uint32_t)Fout * 16u;
+            const uint32_t d_hi = umma::desc_hi(128u);      // SBO = 128 for both operands
             const int nk16 = Fin / 16;
             for (int k = 0; k < K; ++k) {
                 __syncthreads();                                  // staging of step k is complete
@@ -241,15 +243,21 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                     umma::fence_after_sync();
                     if (tr) p.trace[k * 8 + 5] = clock64();
                     const uint32_t wb = w0 + (uint32_t)b * wbytes;
+                    // descriptors advance by plain adds on the low word (units of 16 bytes)
+                    const uint32_t a_lo = umma::desc_lo(a0, p.lbo_a), b_lo = umma::desc_lo(wb, lbo_w);
+                    const uint32_t a_mid = p.plane_bytes >> 4, b_mid = p.wplane_bytes >> 4;
+                    const uint32_t a_k = (2u * p.lbo_a) >> 4, b_k = (2u * lbo_w) >> 4;
                     for (int t = 0; t < p.tiles; ++t) {
+                        const uint32_t at = a_lo + (uint32_t)t * 128u;          // 2048 bytes per 128-row tile
+                        const uint32_t acc = tmem + (uint32_t)(t * Fout);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t ap = a0 + (pass == 1 ? p.plane_bytes : 0u) + (uint32_t)t * 2048u;
-                            const uint32_t bp = wb + (pass == 2 ? p.wplane_bytes : 0u);
+                            uint32_t al = at + (pass == 1 ? a_mid : 0u), bl = b_lo + (pass == 2 ? b_mid : 0u);
                             for (int j = 0; j < nk16; ++j) {
-                                const uint64_t ad = umma::make_desc(ap + (uint32_t)j * 2u * p.lbo_a, p.lbo_a, 128u);
-                                const uint64_t bd = umma::make_desc(bp + (uint32_t)j * 2u * lbo_w, lbo_w, 128u);
-                                umma::mma_bf16(tmem + (uint32_t)(t * Fout), ad, bd, idesc, (k | pass | j) != 0);
+                                umma::mma_bf16(acc, umma::desc_join(al, d_hi), umma::desc_join(bl, d_hi), idesc,
+                                               (k | pass | j) != 0);
+                                al += a_k;
+                                bl += b_k;
                             }
                         }
                     }
@@ -327,6 +335,12 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                     mpar ^= 1;
                 }
                 if (tr) p.trace[k * 8 + 2] = clock64();
+                if (p.stack_out != nullptr) {       // side output for the backward pass (coalesced 128-bit stores)
+                    char *dst = reinterpret_cast<char *>(p.stack_out + ((size_t)k * p.N + n0) * M * Fin);
+#pragma unroll
+                    for (int i = 0; i < IPT; ++i)
+                        if (a_soff[i] < limb) *reinterpret_cast<float4 *>(dst + a_soff[i]) = res[i];
+                }
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     if (a_soff[i] < limb) {
@@ -448,7 +462,7 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
             if (off > g->smem_optin) continue;
             const int64_t G = cg_ceil_div(N, S);
             const int64_t rounds = cg_ceil_div(G, g->sm_count);
-            const double step = (double)need * (avg * 7.0 + 40.0) * (need > 4 ? 1.25 : 1.0) + 300.0;   // > 4: spills
+            const double step = (double)need * (avg * 7.0 + 40.0) * (need > 4 ? 1.6 : 1.0) + 300.0;   // > 4: register spills
             const double cost = (double)rounds * ((double)K * step + 600.0 + (double)R * Fout / 64.0) -
                                 (nslab == 3 ? 1.0 : 0.0) - (nw == 2 ? 0.5 : 0.0);
             if (!best.ok || cost < best_cost) {
@@ -514,8 +528,8 @@ bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fo
 
 size_t cg_fused_workspace(int Fin, int Fout, int K) { return cg_align_up((size_t)K * Fin * Fout * 4, 256); }
 
-int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, int N, int Fin,
-                 int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s) {
+int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
+                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s) {
     Plan pl = make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K);
     CG_REQUIRE(pl.ok, "cg_run_fused: shape not supported by the fused kernel (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
     CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
@@ -536,6 +550,7 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.x = x;
     fp.wp = wp;
     fp.y = y;
+    fp.stack_out = stack_out;
     fp.N = N;
     fp.M = g->M;
     fp.Fin = Fin;

@@ -313,6 +313,16 @@ k_reduce_partials(const float *__restrict__ part, float *__restrict__ dW, int sp
     }
 }
 
+int cg_reduce_partials(const float *part, float *dW, int splits, int Fa, int Fb, int K, bool swap, cudaStream_t s) {
+    CgProfScope prof("reduce_partials", s);
+    const int64_t total = (int64_t)K * Fa * Fb;
+    int64_t blocks = cg_ceil_div(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_reduce_partials<<<(unsigned)blocks, 256, 0, s>>>(part, dW, splits, Fa, Fb, K, swap ? 1 : 0);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
 static int sp_splits(int N, int M, int Fa, int Fb, int K, int sm_count) {
     const int64_t R = (int64_t)N * M;
     const bool wide_a = Fb <= 32;
@@ -354,11 +364,5 @@ int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, i
     }
     CG_LAUNCH_CHECK();
     }
-    CgProfScope prof2("reduce_partials", s);
-    const int64_t total = (int64_t)K * Fa * Fb;
-    int64_t blocks = cg_ceil_div(total, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_reduce_partials<<<(unsigned)blocks, 256, 0, s>>>(workspace, dW, used, Fa, Fb, K, swap ? 1 : 0);
-    CG_LAUNCH_CHECK();
-    return CG_OK;
+    return cg_reduce_partials(workspace, dW, used, Fa, Fb, K, swap, s);
 }

@@ -103,3 +103,98 @@ extern "C" int cg_debug_umma_gemm_m(const float *A, const float *B, float *D, in
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// tcgen05.mma issue/throughput micro-benchmark (debug aid, not in the public header).
+// One CTA, operands zero-filled in shared memory; `reps` rounds of `per` MMAs (M = 128, N, K = 16 each)
+// on `nacc` accumulators, then one commit.  mode 0: K-major SWIZZLE_NONE (core matrices of a K chunk
+// contiguous, LBO = 2048*..), 1: MN-major SWIZZLE_NONE, 2: K-major SWIZZLE_128B (rows of 64 bf16),
+// 3: K-major SWIZZLE_NONE with the K chunks of an 8-row group adjacent (LBO = 128).
+// out[0] = clocks from first issue to completion, out[1] = clocks spent issuing.
+__global__ void __launch_bounds__(128, 1)
+k_umma_bench(int mode, int N, int per, int reps, long long *out, int bg, int same_acc) {
+    __shared__ volatile int stop_flag;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (64 * 1024) / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::fence_mbar_init();
+        stop_flag = 0;
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t a0 = umma::smem_u32(smem), b0 = a0 + 32 * 1024;
+        const int a_mn = mode == 1, b_mn = mode == 1;
+        const uint32_t idesc = umma::make_idesc_bf16(128, N, a_mn, b_mn);
+        uint64_t ad, bd;
+        if (mode == 0) {            // K-major, chunk-major: LBO = 128 rows * 16 B, SBO = 128
+            ad = umma::make_desc(a0, 2048u, 128u);
+            bd = umma::make_desc(b0, (uint32_t)N * 16u, 128u);
+        } else if (mode == 1) {     // MN-major: LBO = 128 (k groups), SBO = 256
+            ad = umma::make_desc(a0, 128u, 256u);
+            bd = umma::make_desc(b0, 128u, 256u);
+        } else if (mode == 2) {     // K-major SWIZZLE_128B: SBO = 1024, layout type 2 (bits 61..63)
+            ad = umma::make_desc(a0, 16u, 1024u) | ((uint64_t)2 << 61);
+            bd = umma::make_desc(b0, 16u, 1024u) | ((uint64_t)2 << 61);
+        } else {                    // K-major, K chunks adjacent: LBO = 128, SBO = 256
+            ad = umma::make_desc(a0, 128u, 256u);
+            bd = umma::make_desc(b0, 128u, 256u);
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            uint32_t acc = tmem;
+            for (int i = 0; i < per; ++i) {
+                // distinct operand tiles per MMA (4 KB apart for A, N*32 bytes for B) when mode >= 4 is not set
+                const uint64_t ao = (uint64_t)(((uint32_t)(i & 3) * 4096u) >> 4), bo = (uint64_t)(((uint32_t)(i & 3) * (uint32_t)N * 32u) >> 4);
+                umma::mma_bf16(acc, ad + (same_acc >= 2 ? 0 : ao), bd + (same_acc >= 2 ? 0 : bo), idesc, true);
+                if (!same_acc) {
+                    acc += (uint32_t)N;
+                    if (acc + (uint32_t)N > tmem + 512u) acc = tmem;
+                }
+            }
+        }
+        umma::commit(&bar);
+        const long long t1 = clock64();
+        umma::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t2 - t0;
+        out[1] = t1 - t0;
+        stop_flag = 1;
+    } else if (bg && warp >= 1) {
+        // background shared-memory traffic: conflict-free 128-bit loads (and stores when bg == 2)
+        float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *base = reinterpret_cast<float4 *>(smem + 48 * 1024);
+        int it = 0;
+        while (!stop_flag) {
+#pragma unroll 8
+            for (int u = 0; u < 8; ++u) {
+                const float4 v = base[((it + u) * 96 + (tid - 32)) & 1023];
+                accv.x += v.x; accv.y += v.y; accv.z += v.z; accv.w += v.w;
+                if (bg == 2) base[((it + u) * 96 + (tid - 32) + 512) & 1023] = accv;
+            }
+            it += 8;
+        }
+        if (accv.x == 123.456f) out[1] = 0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+extern "C" int cg_debug_umma_bench(int mode, int N, int per, int reps, long long *dev_out, int bg, int same_acc,
+                                   void *stream) {
+    CG_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256, "cg_debug_umma_bench: bad N");
+    const size_t smem = 64 * 1024;
+    CG_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_bench<<<1, 128, smem, (cudaStream_t)stream>>>(mode, N, per, reps, dev_out, bg, same_acc);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

@@ -151,6 +151,20 @@ def cheb_basis(handle, X, K, transpose=False, flags=FILTER_DEFAULT):
 # Chebyshev filter
 # ---------------------------------------------------------------------------------------
 
+_STACK_SAVE_LIMIT = 8 << 30      # bytes: larger bases are recomputed in the backward pass instead of saved
+_save_stack = True
+
+
+def save_stack_enabled():
+    return _save_stack
+
+
+def set_save_stack(flag):
+    """Let the forward pass keep the Chebyshev basis for the backward pass (default) or always recompute it."""
+    global _save_stack
+    _save_stack = bool(flag)
+
+
 class ChebFilterFn(torch.autograd.Function):
     """y = chebyshev5(x; L~, W)  (lib/models.py:192-224).  x [N,M,Fin], W [Fin*K, Fout]."""
 
@@ -169,8 +183,15 @@ class ChebFilterFn(torch.autograd.Function):
         y = torch.empty((N, M, Fout), dtype=torch.float32, device=x.device)
         nbytes = lib.cg_cheb_filter_fwd_workspace_bytes(handle.handle, N, Fin, Fout, K, flags)
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
-        check(lib.cg_cheb_filter_fwd(handle.handle, ptr(x), ptr(W), ptr(y), N, Fin, Fout, K, ptr(ws), nbytes,
-                                     flags, _stream()), 'cg_cheb_filter_fwd')
+        # when a gradient will be asked for, let the forward leave the basis X_k behind (shapes that allow it)
+        stack = None
+        if any(ctx.needs_input_grad[:2]) and save_stack_enabled():
+            sbytes = lib.cg_cheb_filter_stack_bytes(handle.handle, N, Fin, Fout, K, flags)
+            if 0 < sbytes <= _STACK_SAVE_LIMIT:
+                stack = torch.empty((K, N, M, Fin), dtype=torch.float32, device=x.device)
+        check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, Fin, Fout, K, ptr(ws),
+                                        nbytes, flags, _stream()), 'cg_cheb_filter_fwd_ex')
+        ctx.stack = stack
         ctx.save_for_backward(x, W)
         ctx.handle, ctx.K, ctx.grad_x, ctx.flags = handle, K, grad_x, flags
         return y
@@ -188,8 +209,9 @@ class ChebFilterFn(torch.autograd.Function):
         dW = torch.empty_like(W)
         nbytes = lib.cg_cheb_filter_bwd_workspace_bytes(handle.handle, N, Fin, Fout, K, int(need_dx), flags)
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
-        check(lib.cg_cheb_filter_bwd(handle.handle, ptr(x), ptr(W), ptr(gy), ptr(dx), ptr(dW), N, Fin, Fout, K,
-                                     ptr(ws), nbytes, flags, _stream()), 'cg_cheb_filter_bwd')
+        check(lib.cg_cheb_filter_bwd_ex(handle.handle, ptr(x), ptr(W), ptr(gy), ptr(ctx.stack), ptr(dx), ptr(dW), N,
+                                        Fin, Fout, K, ptr(ws), nbytes, flags, _stream()), 'cg_cheb_filter_bwd_ex')
+        ctx.stack = None
         return dx, dW, None, None, None, None
 
 

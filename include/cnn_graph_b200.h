@@ -97,6 +97,20 @@ int cg_cheb_filter_bwd(const cg_graph_t *g, const float *dev_x, const float *dev
                        float *dev_dx, float *dev_dW, int N, int Fin, int Fout, int K,
                        void *dev_workspace, size_t workspace_bytes, int flags, void *stream);
 
+/* Training variants.  The forward pass can leave the Chebyshev basis X_k = T_k(L~) x behind
+ * (dev_stack_out, [K, N, M, Fin] float32, sample-major) so that the backward pass forms
+ * dW = X_k^T gy without repeating the recurrence -- the B200 answer to TF keeping the whole
+ * concat/transposed stack alive for autodiff (lib/models.py:207-220).
+ * cg_cheb_filter_stack_bytes returns the size of that buffer, or 0 when the shape cannot use it
+ * (then pass NULL).  dev_saved_stack in the backward may be NULL (the basis is recomputed). */
+size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
+int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *dev_x, const float *dev_W, float *dev_y,
+                          float *dev_stack_out, int N, int Fin, int Fout, int K, void *dev_workspace,
+                          size_t workspace_bytes, int flags, void *stream);
+int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *dev_x, const float *dev_W, const float *dev_gy,
+                          const float *dev_saved_stack, float *dev_dx, float *dev_dW, int N, int Fin, int Fout,
+                          int K, void *dev_workspace, size_t workspace_bytes, int flags, void *stream);
+
 /* ---- bias + activation (b1relu / b1tanh / b2relu) ---------------------- */
 /* lib/models.py:226-247.  bias_kind: 0 none (fork b1relu), 1 per filter
  * [F] (upstream b1relu, b1tanh), 2 per vertex and filter [M, F] (b2relu).

@@ -133,7 +133,7 @@ def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K)
 
 
 @pytest.mark.parametrize('level,N,Fin,Fout,K', [(2, 5, 32, 64, 25), (4, 37, 64, 16, 4), (3, 10, 32, 64, 3),
-                                                (3, 9, 16, 16, 1)])
+                                                (3, 9, 16, 16, 1), (3, 5, 64, 64, 25), (4, 130, 16, 32, 3)])
 def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K):
     """dx through the fused kernel on L~^T (needs Fout % 16 == 0), dW from the X-stack."""
     L = csr_from(c2, 'L%d' % level)
@@ -441,3 +441,39 @@ def test_graphconv_and_glstm_models_run(ops, tf_ref, c2):
         h, cc = tf_ref.gconv_lstm_step(frames[..., t], cc, h, L, 2, 3, Wx, Wh, bb, 'standard')
     close(out, tf_ref.chebyshev5(h, L, v['conv_init/weights'], 3))
     assert np.isfinite(float(gm.train_step(dev(x), dev(y))))
+
+
+def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
+    """The forward pass leaves the basis behind (sample-major) and the backward pass uses it for dW:
+    same gradients as the recomputing path and as the oracle."""
+    L = csr_from(c2, 'L2')
+    M = L.shape[0]
+    rng = np.random.RandomState(5)
+    N, Fin, Fout, K = 37, 32, 64, 9
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    grads = []
+    for save in (True, False):
+        ops.set_save_stack(save)
+        try:
+            xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+            y = ops.cheb_filter(xt, Wt, L, K)
+            assert (y.grad_fn.stack is not None) == save
+            y.backward(dev(gy))
+            grads.append((xt.grad.cpu().numpy(), Wt.grad.cpu().numpy()))
+        finally:
+            ops.set_save_stack(True)
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    for gx, gw in grads:
+        close(gx, dx)
+        close(gw, dW)
+    # the saved basis itself is the reference's graph.chebyshev of every sample
+    from oracle import graph_ref
+    h = ops.get_handle(L)
+    xt = dev(x).requires_grad_(True)
+    y = ops.cheb_filter(xt, dev(W), L, K)
+    stack = y.grad_fn.stack.cpu().numpy()                       # [K, N, M, Fin]
+    Lr = ops.rescale_csr(L)
+    ref = graph_ref.chebyshev(Lr, np.ascontiguousarray(x.transpose(1, 0, 2).reshape(M, N * Fin)), K)
+    close(stack.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 1e-5)
