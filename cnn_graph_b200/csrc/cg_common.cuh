@@ -115,11 +115,18 @@ int cg_run_dw_umma(const float *stack, const float *T, float *dW, int N, int M, 
 
 // Fused recurrence + contraction (cg_fused.cu): y[n,m,:] = sum_k (T_k(L) x)[n,m,:] W_k with the operator side
 // chosen by `transpose`; w_transposed selects the dx form (W_k^T).  workspace: cg_fused_workspace bytes.
+// W [..] -> per-k bf16 hi|mid B operands (K-major canonical, n = output feature, q = reduction feature)
+int cg_pack_w(const float *W, unsigned char *wp, int Q, int Nn, int K, bool transposed, cudaStream_t s);
 bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K);
 size_t cg_fused_workspace(int Fin, int Fout, int K);
 //   stack_out (optional): the basis X_k, [K][N][M][Fin] (sample-major), for a later weight gradient.
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
                  int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);
+
+// Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).
+bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
+int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,
+                    void *workspace, cudaStream_t s);
 
 static inline int64_t cg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -155,11 +155,19 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
     }
     if (need_dx) {
         bool fused = false;
-        rc = want_fused("cg_cheb_filter_bwd", g, 1, N, Fout, Fin, K, flags, &fused);
-        if (rc != CG_OK) return rc;
-        if (fused) {
+        const bool allow = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING));
+        const bool clenshaw = allow && !(flags & CG_FILTER_NO_CLENSHAW) && cg_clenshaw_supported(g, N, Fin, Fout, K);
+        if (!clenshaw) {
+            rc = want_fused("cg_cheb_filter_bwd", g, 1, N, Fout, Fin, K, flags, &fused);
+            if (rc != CG_OK) return rc;
+        }
+        void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
+        if (clenshaw) {
+            // adjoint recurrence at the width of dx, G_k = gy W_k^T from tensor memory
+            rc = cg_run_clenshaw(g, gy, W, dx, N, Fin, Fout, K, wpack, s);
+            if (rc != CG_OK) return rc;
+        } else if (fused) {
             // dx by the fused kernel on L~^T (Z_k never materialised)
-            void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
             rc = cg_run_fused(g, 1, gy, W, dx, nullptr, N, Fout, Fin, K, true, wpack, s);
             if (rc != CG_OK) return rc;
         } else {

@@ -22,68 +22,12 @@
 
 #include "cg_common.cuh"
 #include "cg_umma.cuh"
+#include "cg_fused_common.cuh"
 
 namespace {
 
 constexpr int FC = 512;        // compute threads
 constexpr int FT = FC + 32;    // + issue warp
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-// 1-D bulk copy global -> shared (TMA engine), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     dst_smem),
-                 "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &mid) {
-    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-    const __nv_bfloat162 m01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-    const __nv_bfloat162 m23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-    hi.x = *reinterpret_cast<const uint32_t *>(&h01);
-    hi.y = *reinterpret_cast<const uint32_t *>(&h23);
-    mid.x = *reinterpret_cast<const uint32_t *>(&m01);
-    mid.y = *reinterpret_cast<const uint32_t *>(&m23);
-}
-
-// shared-memory accesses with 32-bit addresses (one IADD of addressing, guaranteed predication)
-__device__ __forceinline__ void lds64_if(float2 &v, uint32_t addr, int j, int n) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, %4;\n\t@p ld.shared.v2.f32 {%0, %1}, [%2];\n\t}"
-                 : "+f"(v.x), "+f"(v.y)
-                 : "r"(addr), "r"(j), "r"(n));
-}
-__device__ __forceinline__ void lds128_if(float4 &v, uint32_t addr, int j, int n) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %5, %6;\n\t@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-                 : "r"(addr), "r"(j), "r"(n));
-}
-__device__ __forceinline__ float2 lds64(uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts64(uint32_t addr, const uint2 v) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ void fma4(float4 &a, float s, const float4 x) {
-    a.x = fmaf(s, x.x, a.x);
-    a.y = fmaf(s, x.y, a.y);
-    a.z = fmaf(s, x.z, a.z);
-    a.w = fmaf(s, x.w, a.w);
-}
 
 struct FusedParams {
     const int *rowptr;
@@ -522,6 +466,14 @@ extern "C" int cg_debug_fused_trace(long long *dev_buf) {
     return CG_OK;
 }
 
+int cg_pack_w(const float *W, unsigned char *wp, int Q, int Nn, int K, bool transposed, cudaStream_t s) {
+    CgProfScope prof("pack_w", s);
+    const int total = K * Q * Nn;
+    k_pack_w<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1024), 256, 0, s>>>(W, wp, Q, Nn, K, transposed ? 1 : 0);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
 bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K) {
     return make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K).ok;
 }
@@ -535,13 +487,8 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
     const CgCsr &L = cg_side(g, transpose);
     unsigned char *wp = reinterpret_cast<unsigned char *>(workspace);
-    {
-        CgProfScope prof("pack_w", s);
-        const int total = K * Fin * Fout;
-        k_pack_w<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1024), 256, 0, s>>>(W, wp, Fin, Fout, K,
-                                                                                           w_transposed ? 1 : 0);
-        CG_LAUNCH_CHECK();
-    }
+    int rc = cg_pack_w(W, wp, Fin, Fout, K, w_transposed, s);
+    if (rc != CG_OK) return rc;
     FusedParams &fp = pl.fp;
     fp.rowptr = L.rowptr;
     fp.col = L.col;

@@ -1,0 +1,56 @@
+// Device helpers shared by the fused recurrence kernels (cg_fused.cu, cg_clenshaw.cu): mbarrier / bulk-copy
+// wrappers, shared-memory accesses with 32-bit addresses, the bf16 hi/mid split.
+#pragma once
+#include "cg_umma.cuh"
+
+namespace {
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_smem),
+                 "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &mid) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 m01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+    const __nv_bfloat162 m23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t *>(&h01);
+    hi.y = *reinterpret_cast<const uint32_t *>(&h23);
+    mid.x = *reinterpret_cast<const uint32_t *>(&m01);
+    mid.y = *reinterpret_cast<const uint32_t *>(&m23);
+}
+
+// shared-memory accesses with 32-bit addresses (one IADD of addressing)
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void fma4(float4 &a, float s, const float4 x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+    a.z = fmaf(s, x.z, a.z);
+    a.w = fmaf(s, x.w, a.w);
+}
+
+
+}  // namespace

@@ -198,3 +198,82 @@ extern "C" int cg_debug_umma_bench(int mode, int N, int per, int reps, long long
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// A operand in tensor memory (the Clenshaw dx kernel keeps gy there): D[128][N] = A * B^T with
+// A [128][Kd] written by tcgen05.st (two bf16 per 32-bit column), B [N][Kd] K-major in shared memory.
+__global__ void __launch_bounds__(128, 1)
+k_umma_test_ts(const float *__restrict__ A_src, const float *__restrict__ B_src, float *__restrict__ D, int N, int Kd) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t b_lbo = 128u, b_sbo = 128u * (Kd / 8);
+    for (int e = tid; e < N * Kd; e += 128) {
+        const int r = e / Kd, k = e % Kd;
+        const uint32_t off = (r / 8) * b_sbo + (k / 8) * b_lbo + (r % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(smem + off) = __float2bfloat16_rn(B_src[e]);
+    }
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_col = 256;                       // A lives at columns [256, 256 + Kd/2)
+    {
+        const int row = warp * 32 + lane;
+        for (int c = 0; c < Kd / 2; c += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(A_src[row * Kd + 2 * (c + i)], A_src[row * Kd + 2 * (c + i) + 1]);
+                r[i] = *reinterpret_cast<const uint32_t *>(&v);
+            }
+            umma::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + a_col + (uint32_t)c, r);
+        }
+        umma::tmem_st_wait();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N, 0, 0);
+        const uint32_t b0 = umma::smem_u32(smem);
+        for (int k16 = 0; k16 < Kd / 16; ++k16) {
+            const uint64_t bd = umma::make_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
+            umma::mma_bf16_ts(tmem, tmem + a_col + (uint32_t)k16 * 8u, bd, idesc, k16 > 0);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[row * N + c + i] = v[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+extern "C" int cg_debug_umma_gemm_ts(const float *A, const float *B, float *D, int N, int Kd, void *stream) {
+    CG_REQUIRE(A && B && D, "cg_debug_umma_gemm_ts: NULL tensor");
+    CG_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256, "cg_debug_umma_gemm_ts: N must be a multiple of 16 in [16, 256]");
+    CG_REQUIRE(Kd % 16 == 0 && Kd >= 16 && Kd <= 256, "cg_debug_umma_gemm_ts: Kd must be a multiple of 16 in [16, 256]");
+    const size_t smem = sizeof(__nv_bfloat16) * (size_t)N * Kd;
+    CG_CHECK_CUDA(cudaFuncSetAttribute(k_umma_test_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CgProfScope prof("umma_test_ts", (cudaStream_t)stream);
+    k_umma_test_ts<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, Kd);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

@@ -18,6 +18,7 @@ FILTER_FORCE_STREAMING = 1
 FILTER_FORCE_ONCHIP = 2
 FILTER_NO_FUSED = 4
 FILTER_FORCE_FUSED = 8
+FILTER_NO_CLENSHAW = 16
 
 
 def _stream():

@@ -85,7 +85,8 @@ enum {
     CG_FILTER_FORCE_STREAMING = 1, /* never use the on-chip (SMEM-resident) kernels */
     CG_FILTER_FORCE_ONCHIP = 2,    /* fail with CG_ERR_ARG if the on-chip kernels do not fit */
     CG_FILTER_NO_FUSED = 4,        /* never use the fused recurrence+contraction (tcgen05) kernel */
-    CG_FILTER_FORCE_FUSED = 8      /* fail with CG_ERR_ARG if the fused kernel does not support the shape */
+    CG_FILTER_FORCE_FUSED = 8,     /* fail with CG_ERR_ARG if the fused kernel does not support the shape */
+    CG_FILTER_NO_CLENSHAW = 16     /* input gradient by the forward-form fused kernel on L~^T, not the adjoint recurrence */
 };
 size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
 size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
@@ -173,6 +174,9 @@ int cg_debug_umma_gemm(const float *dev_A, const float *dev_B, float *dev_D, int
 /* Same with Mr = 64 or 128 rows of A; dev_D [128][N] receives all 128 TMEM lanes. */
 int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, int Mr, int N, int Kd,
                          int a_mn, int b_mn, void *stream);
+
+/* A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A operand): dev_A [128][Kd], dev_B [N][Kd]. */
+int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, void *stream);
 
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32

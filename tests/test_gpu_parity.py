@@ -134,8 +134,9 @@ def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K)
 
 @pytest.mark.parametrize('level,N,Fin,Fout,K', [(2, 5, 32, 64, 25), (4, 37, 64, 16, 4), (3, 10, 32, 64, 3),
                                                 (3, 9, 16, 16, 1), (3, 5, 64, 64, 25), (4, 130, 16, 32, 3)])
-def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K):
-    """dx through the fused kernel on L~^T (needs Fout % 16 == 0), dW from the X-stack."""
+@pytest.mark.parametrize('dx_kernel', ['clenshaw', 'forward_form'])
+def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K, dx_kernel):
+    """dx through the adjoint (Clenshaw) kernel or the forward-form fused kernel on L~^T; dW from the basis."""
     L = csr_from(c2, 'L%d' % level)
     M = L.shape[0]
     rng = np.random.RandomState(20 * level + K + N)
@@ -143,7 +144,8 @@ def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K
     W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
     gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
     xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
-    y = ops.cheb_filter(xt, Wt, L, K, lmax=2, flags=ops.FILTER_FORCE_FUSED)
+    flags = ops.FILTER_FORCE_FUSED | (ops.FILTER_NO_CLENSHAW if dx_kernel == 'forward_form' else 0)
+    y = ops.cheb_filter(xt, Wt, L, K, lmax=2, flags=flags)
     y.backward(dev(gy))
     dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
     close(xt.grad, dx)
@@ -158,13 +160,14 @@ def test_fused_filter_directed(ops, tf_ref, directed):
     x = rng.standard_normal((6, M, 16)).astype(np.float32)
     W = (0.1 * rng.standard_normal((16 * 5, 32))).astype(np.float32)
     gy = rng.standard_normal((6, M, 32)).astype(np.float32)
-    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
-    y = ops.cheb_filter(xt, Wt, L, 5, lmax=3.5, flags=ops.FILTER_FORCE_FUSED)
-    close(y, tf_ref.chebyshev5(x, L, W, 5, lmax=3.5))
-    y.backward(dev(gy))
-    dx, dW = tf_ref.chebyshev5_backward(x, L, W, 5, gy, lmax=3.5)
-    close(xt.grad, dx)
-    close(Wt.grad, dW)
+    for flags in (ops.FILTER_FORCE_FUSED, ops.FILTER_FORCE_FUSED | ops.FILTER_NO_CLENSHAW):
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, 5, lmax=3.5, flags=flags)
+        close(y, tf_ref.chebyshev5(x, L, W, 5, lmax=3.5))
+        y.backward(dev(gy))
+        dx, dW = tf_ref.chebyshev5_backward(x, L, W, 5, gy, lmax=3.5)
+        close(xt.grad, dx)
+        close(Wt.grad, dW)
 
 
 def test_fused_unsupported_shape_raises(ops, c2):
