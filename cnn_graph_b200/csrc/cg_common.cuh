@@ -91,17 +91,22 @@ static inline const CgCsr &cg_side(const cg_graph *g, int transpose) { return tr
 // stack[0] must already hold the input slab; fills stack[1..K-1].
 int cg_run_basis(const cg_graph *g, int transpose, float *stack, int64_t C, int K, cudaStream_t s, int flags);
 
+// Sample-major variant of the on-chip basis: x [N][M][F] -> stack [K][N][M][F] directly (rows r = n*M + m).
+bool cg_basis_samples_supported(const cg_graph *g, int transpose, int N, int F);
+int cg_run_basis_samples(const cg_graph *g, int transpose, const float *x, float *stack, int N, int F, int K,
+                         cudaStream_t s);
+
 // in[A][B][F] -> out[B][A][F]
 int cg_run_permute_abf(const float *in, float *out, int64_t A, int64_t B, int F, cudaStream_t s);
 
 // y[(n*M+m)][fo] = sum_{k,f} stack[k][m*N+n][f] * W[f*K+k][fo]      (contract)
 int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, int F, int Fout, int K,
-                    bool w_transposed, cudaStream_t s);
+                    bool w_transposed, bool sample_major, cudaStream_t s);
 
 // dW[(a*K+k)][b] (or [(b*K+k)][a] when swap) = sum_{m,n} stack[k][m*N+n][a] * T[(n*M+m)][b]
 size_t cg_stack_t_plain_workspace(int N, int M, int Fa, int Fb, int K, int sm_count);
 int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, int M, int Fa, int Fb, int K,
-                         bool swap, float *workspace, int sm_count, cudaStream_t s);
+                         bool swap, bool sample_major, float *workspace, int sm_count, cudaStream_t s);
 
 // dW[...] = sum over `splits` partial results part[split][k*Fa + a][b] (deterministic, no atomics)
 int cg_reduce_partials(const float *part, float *dW, int splits, int Fa, int Fb, int K, bool swap, cudaStream_t s);

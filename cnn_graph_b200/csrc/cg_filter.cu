@@ -27,11 +27,19 @@ static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
 }
 
 static int run_dw(const cg_graph *g, const float *stack, const float *T, float *dW, int N, int Fa, int Fb, int K,
-                  bool swap, float *part, int flags, cudaStream_t s) {
+                  bool swap, bool sample_major, float *part, int flags, cudaStream_t s) {
     const bool tc = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) &&
-                    cg_dw_umma_supported(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
-    if (tc) return cg_run_dw_umma(stack, T, dW, N, g->M, Fa, Fb, K, swap, false, part, g->sm_count, g->smem_optin, s);
-    return cg_run_stack_t_plain(stack, T, dW, N, g->M, Fa, Fb, K, swap, part, g->sm_count, s);
+                    cg_dw_umma_supported(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin) &&
+                    ((((uintptr_t)stack | (uintptr_t)T | (uintptr_t)part) & 15) == 0);
+    if (tc)
+        return cg_run_dw_umma(stack, T, dW, N, g->M, Fa, Fb, K, swap, sample_major, part, g->sm_count, g->smem_optin, s);
+    return cg_run_stack_t_plain(stack, T, dW, N, g->M, Fa, Fb, K, swap, sample_major, part, g->sm_count, s);
+}
+
+// basis straight from / to the sample-major layout (no permute) when the on-chip kernel takes the operator
+static bool samples_ok(const cg_graph *g, int transpose, int N, int F, int flags, const void *a, const void *b) {
+    if (flags & CG_FILTER_FORCE_STREAMING) return false;
+    return ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) && cg_basis_samples_supported(g, transpose, N, F);
 }
 
 extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
@@ -70,9 +78,9 @@ static int check_dims(const char *who, const cg_graph *g, int N, int Fin, int Fo
 // The forward pass can leave the basis X_k behind for the weight gradient ([K][N][M][Fin], sample-major) when
 // both the fused kernel and the tensor-core dW kernel take the shape.
 static bool can_save_stack(const cg_graph *g, int N, int Fin, int Fout, int K, int flags) {
-    if (flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) return false;
-    return N > 0 && cg_fused_supported(g, 0, N, Fin, Fout, K) &&
-           cg_dw_umma_supported(N, g->M, Fin, Fout, K, g->sm_count, g->smem_optin);
+    if (N <= 0 || K < 2 || (flags & CG_FILTER_FORCE_STREAMING)) return false;
+    if (!(flags & CG_FILTER_NO_FUSED) && cg_fused_supported(g, 0, N, Fin, Fout, K)) return true;
+    return cg_basis_samples_supported(g, 0, N, Fin);
 }
 
 extern "C" size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
@@ -109,11 +117,18 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
         return cg_run_fused(g, 0, x, W, y, stack_out, N, Fin, Fout, K, false, wpack, s);
     }
     if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
-        return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, s);
+        return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, false, s);
     float *stack = reinterpret_cast<float *>(workspace);
+    if (samples_ok(g, 0, N, Fin, flags, x, stack_out ? stack_out : stack)) {
+        float *st = stack_out ? stack_out : stack;                            // [K][N][M][F], rows in y's order
+        rc = cg_run_basis_samples(g, 0, x, st, N, Fin, K, s);
+        if (rc == CG_OK) rc = cg_run_contract(st, W, y, N, M, Fin, Fout, K, false, true, s);
+        return rc;
+    }
+    CG_REQUIRE(stack_out == nullptr, "cg_cheb_filter_fwd_ex: this call cannot save the basis (unaligned tensors)");
     rc = cg_run_permute_abf(x, stack, N, M, Fin, s);                          // [N][M][F] -> [M][N][F]
     if (rc == CG_OK) rc = cg_run_basis(g, 0, stack, (int64_t)N * Fin, K, s, flags);
-    if (rc == CG_OK) rc = cg_run_contract(stack, W, y, N, M, Fin, Fout, K, false, s);
+    if (rc == CG_OK) rc = cg_run_contract(stack, W, y, N, M, Fin, Fout, K, false, false, s);
     return rc;
 }
 
@@ -149,7 +164,7 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
         // dW[fin*K+k, fo] = sum_{n,m} X_k[n,m,fin] gy[n,m,fo] straight from the basis the forward pass left behind
         CG_REQUIRE(can_save_stack(g, N, Fin, Fout, K, flags), "cg_cheb_filter_bwd_ex: saved stack given for a shape that cannot save one");
         float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K));
-        rc = cg_run_dw_umma(saved_stack, gy, dW, N, M, Fin, Fout, K, false, true, part, g->sm_count, g->smem_optin, s);
+        rc = run_dw(g, saved_stack, gy, dW, N, Fin, Fout, K, false, true, part, flags, s);
         if (rc != CG_OK) return rc;
         have_dW = true;
     }
@@ -173,10 +188,15 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
         } else {
             // Z_k = T_k(L~^T) gy materialised: dx = Z W^T, and dW = x^T Z_k if still missing
             float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fout, K));
-            rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
-            if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);
-            if (rc == CG_OK) rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, s);
-            if (rc == CG_OK && !have_dW) rc = run_dw(g, stack, x, dW, N, Fout, Fin, K, true, part, flags, s);
+            const bool sm = samples_ok(g, 1, N, Fout, flags, gy, stack);
+            if (sm) {
+                rc = cg_run_basis_samples(g, 1, gy, stack, N, Fout, K, s);
+            } else {
+                rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
+                if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);
+            }
+            if (rc == CG_OK) rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, sm, s);
+            if (rc == CG_OK && !have_dW) rc = run_dw(g, stack, x, dW, N, Fout, Fin, K, true, sm, part, flags, s);
             if (rc != CG_OK) return rc;
             have_dW = true;
         }
@@ -184,9 +204,14 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
     if (!have_dW) {
         // dW = X_k^T gy with the (narrower) X-stack recomputed
         float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K));
-        rc = cg_run_permute_abf(x, stack, N, M, Fin, s);
-        if (rc == CG_OK) rc = cg_run_basis(g, 0, stack, (int64_t)N * Fin, K, s, flags);
-        if (rc == CG_OK) rc = run_dw(g, stack, gy, dW, N, Fin, Fout, K, false, part, flags, s);
+        const bool sm = samples_ok(g, 0, N, Fin, flags, x, stack);
+        if (sm) {
+            rc = cg_run_basis_samples(g, 0, x, stack, N, Fin, K, s);
+        } else {
+            rc = cg_run_permute_abf(x, stack, N, M, Fin, s);
+            if (rc == CG_OK) rc = cg_run_basis(g, 0, stack, (int64_t)N * Fin, K, s, flags);
+        }
+        if (rc == CG_OK) rc = run_dw(g, stack, gy, dW, N, Fin, Fout, K, false, sm, part, flags, s);
     }
     return rc;
 }

@@ -30,7 +30,7 @@ __device__ __forceinline__ float w_elem(const float *__restrict__ W, int k, int 
 template <int TN>   // columns per thread (4 or 8); BN = 8 * TN
 __global__ void __launch_bounds__(CT_THREADS)
 k_contract(const float *__restrict__ stack, const float *__restrict__ W, float *__restrict__ y, int64_t R, int N,
-           int M, int F, int J, int K, int w_transposed, int vecA) {
+           int M, int F, int J, int K, int w_transposed, int vecA, int sample_major) {
     constexpr int BN = 8 * TN;
     constexpr int NJ = TN / 4;
     __shared__ __align__(16) float As[CT_BM * CT_AP];
@@ -154,7 +154,7 @@ k_contract(const float *__restrict__ stack, const float *__restrict__ W, float *
         const int64_t r = r0 + rg + 16 * i;
         if (r >= R) continue;
         const int64_t n = r % N, m = r / N;
-        float *dst = y + (n * M + m) * (int64_t)J;
+        float *dst = y + (sample_major ? r : n * M + m) * (int64_t)J;      // stack rows already in y's order?
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
             const int j = j0 + cg * 4 + 32 * jj;
@@ -171,7 +171,7 @@ k_contract(const float *__restrict__ stack, const float *__restrict__ W, float *
 }
 
 int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, int F, int J, int K,
-                    bool w_transposed, cudaStream_t s) {
+                    bool w_transposed, bool sample_major, cudaStream_t s) {
     const int64_t R = (int64_t)N * M;
     if (R == 0 || J == 0) return CG_OK;
     const int vecA = (F % 4 == 0) && ((((uintptr_t)stack) & 15) == 0);
@@ -179,10 +179,12 @@ int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, 
     CgProfScope prof("contract", s);
     if (J > 32) {
         dim3 grid(gx, (unsigned)cg_ceil_div(J, 64));
-        k_contract<8><<<grid, CT_THREADS, 0, s>>>(stack, W, y, R, N, M, F, J, K, w_transposed ? 1 : 0, vecA);
+        k_contract<8><<<grid, CT_THREADS, 0, s>>>(stack, W, y, R, N, M, F, J, K, w_transposed ? 1 : 0, vecA,
+                                                  sample_major ? 1 : 0);
     } else {
         dim3 grid(gx, 1);
-        k_contract<4><<<grid, CT_THREADS, 0, s>>>(stack, W, y, R, N, M, F, J, K, w_transposed ? 1 : 0, vecA);
+        k_contract<4><<<grid, CT_THREADS, 0, s>>>(stack, W, y, R, N, M, F, J, K, w_transposed ? 1 : 0, vecA,
+                                                  sample_major ? 1 : 0);
     }
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -197,7 +199,7 @@ constexpr int SP_RC = 32;       // rows per stage
 template <int TA, int TB>       // output tile TA (q) x TB (b); micro tile 4 x 4; (TA/4)*(TB/4) == 128
 __global__ void __launch_bounds__(SP_THREADS)
 k_stack_t_plain(const float *__restrict__ stack, const float *__restrict__ T, float *__restrict__ part, int64_t R,
-                int N, int M, int Fa, int Fb, int K, int64_t rows_per_split, int vecS, int vecT) {
+                int N, int M, int Fa, int Fb, int K, int64_t rows_per_split, int vecS, int vecT, int sample_major) {
     static_assert((TA / 4) * (TB / 4) == SP_THREADS, "tile/thread mismatch");
     __shared__ __align__(16) float Ss[SP_RC * TA];
     __shared__ __align__(16) float Ts[SP_RC * TB];
@@ -251,7 +253,7 @@ k_stack_t_plain(const float *__restrict__ stack, const float *__restrict__ T, fl
                 const int64_t r = rb + row;
                 if (r < r_end && b0 + bb < Fb) {
                     const int64_t n = r % N, m = r / N;
-                    v = *reinterpret_cast<const float4 *>(T + (n * M + m) * (int64_t)Fb + b0 + bb);
+                    v = *reinterpret_cast<const float4 *>(T + (sample_major ? r : n * M + m) * (int64_t)Fb + b0 + bb);
                 }
                 *reinterpret_cast<float4 *>(Ts + row * TB + bb) = v;
             }
@@ -262,7 +264,7 @@ k_stack_t_plain(const float *__restrict__ stack, const float *__restrict__ T, fl
                 const int64_t r = rb + row;
                 if (r < r_end && b0 + bb < Fb) {
                     const int64_t n = r % N, m = r / N;
-                    v = T[(n * M + m) * (int64_t)Fb + b0 + bb];
+                    v = T[(sample_major ? r : n * M + m) * (int64_t)Fb + b0 + bb];
                 }
                 Ts[row * TB + bb] = v;
             }
@@ -340,7 +342,7 @@ size_t cg_stack_t_plain_workspace(int N, int M, int Fa, int Fb, int K, int sm_co
 }
 
 int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, int M, int Fa, int Fb, int K,
-                         bool swap, float *workspace, int sm_count, cudaStream_t s) {
+                         bool swap, bool sample_major, float *workspace, int sm_count, cudaStream_t s) {
     const int64_t R = (int64_t)N * M;
     const int splits = sp_splits(N, M, Fa, Fb, K, sm_count);
     int64_t rows_per_split = cg_ceil_div(R, splits);
@@ -355,12 +357,12 @@ int cg_run_stack_t_plain(const float *stack, const float *T, float *dW, int N, i
         dim3 grid((unsigned)used, (unsigned)cg_ceil_div((int64_t)K * Fa, 64), (unsigned)cg_ceil_div(Fb, 32));
         CG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stack_t_plain: problem too large");
         k_stack_t_plain<64, 32><<<grid, SP_THREADS, 0, s>>>(stack, T, workspace, R, N, M, Fa, Fb, K, rows_per_split,
-                                                           vecS, vecT);
+                                                           vecS, vecT, sample_major ? 1 : 0);
     } else {
         dim3 grid((unsigned)used, (unsigned)cg_ceil_div((int64_t)K * Fa, 32), (unsigned)cg_ceil_div(Fb, 64));
         CG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stack_t_plain: problem too large");
         k_stack_t_plain<32, 64><<<grid, SP_THREADS, 0, s>>>(stack, T, workspace, R, N, M, Fa, Fb, K, rows_per_split,
-                                                           vecS, vecT);
+                                                           vecS, vecT, sample_major ? 1 : 0);
     }
     CG_LAUNCH_CHECK();
     }

@@ -113,10 +113,13 @@ static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, 
 // shared memory:  ell[width][m_pad] float2 | len[m_pad] int | S0[M][CW] | S1[M][CW]
 constexpr int kOnchipThreads = 512;
 
-template <int CW>
+// Column c of the slab is signal n = c / F, feature f = c % F.  Two global layouts:
+//   SM == 0  "vertex-major"  element (m, c) at m * C + c                  (slab layout S[m][c], lib/graph.py:241)
+//   SM == 1  "sample-major"  element (m, c) at (n * M + m) * F + f        (the layout of x [N][M][F] itself)
+template <int CW, int SM>
 __global__ void __launch_bounds__(kOnchipThreads, 1)
 k_basis_onchip(const float2 *__restrict__ ell_g, const int *__restrict__ rowptr, int width, int m_pad, int M,
-               const float *__restrict__ in, float *__restrict__ stack, int64_t C, int K, int write_slab0) {
+               const float *__restrict__ in, float *__restrict__ stack, int64_t C, int K, int write_slab0, int F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LPR = CW / 4;                 // lanes per row
     constexpr int RPP = kOnchipThreads / LPR;   // rows per pass
@@ -132,13 +135,47 @@ k_basis_onchip(const float2 *__restrict__ ell_g, const int *__restrict__ rowptr,
     const bool cvalid = cbase < C;              // C % 4 == 0 -> the whole float4 is in range
     const int64_t slab = (int64_t)M * C;
 
+    // global element offsets of the thread's four columns at m = 0, and the stride between vertices
+    int64_t o[4];
+    int64_t rs;
+    bool vec;                                   // the four columns are contiguous and 16-byte aligned
+    if (SM) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t c = cbase + i, n = c / F, f = c - n * F;
+            o[i] = n * (int64_t)M * F + f;
+        }
+        rs = F;
+        vec = (F % 4) == 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = cbase + i;
+        rs = C;
+        vec = true;
+    }
+    auto gload = [&](const float *base, int m) {
+        if (vec) return *reinterpret_cast<const float4 *>(base + o[0] + (int64_t)m * rs);
+        return make_float4(base[o[0] + (int64_t)m * rs], base[o[1] + (int64_t)m * rs], base[o[2] + (int64_t)m * rs],
+                           base[o[3] + (int64_t)m * rs]);
+    };
+    auto gstore = [&](float *base, int m, const float4 v) {
+        if (vec) {
+            *reinterpret_cast<float4 *>(base + o[0] + (int64_t)m * rs) = v;
+        } else {
+            base[o[0] + (int64_t)m * rs] = v.x;
+            base[o[1] + (int64_t)m * rs] = v.y;
+            base[o[2] + (int64_t)m * rs] = v.z;
+            base[o[3] + (int64_t)m * rs] = v.w;
+        }
+    };
+
     for (int i = tid; i < width * m_pad; i += kOnchipThreads) ell[i] = ell_g[i];
     for (int m = tid; m < m_pad; m += kOnchipThreads) len[m] = m < M ? rowptr[m + 1] - rowptr[m] : 0;
     for (int m = row0; m < M; m += RPP) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cvalid) v = *reinterpret_cast<const float4 *>(in + (int64_t)m * C + cbase);
+        if (cvalid) v = gload(in, m);
         *reinterpret_cast<float4 *>(S0 + m * CW + lane * 4) = v;
-        if (write_slab0 && cvalid) *reinterpret_cast<float4 *>(stack + (int64_t)m * C + cbase) = v;
+        if (write_slab0 && cvalid) gstore(stack, m, v);
     }
     __syncthreads();
 
@@ -166,7 +203,7 @@ k_basis_onchip(const float2 *__restrict__ ell_g, const int *__restrict__ rowptr,
             float4 r = acc;
             if (k > 1) r = axmb(2.0f, acc, *slot);
             *slot = r;
-            if (cvalid) *reinterpret_cast<float4 *>(dst + (int64_t)m * C + cbase) = r;
+            if (cvalid) gstore(dst, m, r);
         }
         __syncthreads();
         float *t = prev;
@@ -189,18 +226,52 @@ static int onchip_cw(const cg_graph *g, const CgCsr &L, int64_t C) {
     return best;
 }
 
-template <int CW>
+template <int CW, int SM>
 static int launch_onchip(const cg_graph *g, const CgCsr &L, const float *in, float *stack, int64_t C, int K,
-                         int write_slab0, cudaStream_t s) {
+                         int write_slab0, int F, cudaStream_t s) {
     const size_t smem = (size_t)L.width * L.m_pad * sizeof(float2) + (size_t)L.m_pad * sizeof(int) +
                         2 * (size_t)g->M * CW * sizeof(float);
-    CG_CHECK_CUDA(cudaFuncSetAttribute(k_basis_onchip<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CG_CHECK_CUDA(cudaFuncSetAttribute(k_basis_onchip<CW, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)cg_ceil_div(C, CW);
     CgProfScope prof("basis_onchip", s);
-    k_basis_onchip<CW><<<grid, kOnchipThreads, smem, s>>>(L.ell, L.rowptr, L.width, L.m_pad, g->M, in, stack, C, K,
-                                                          write_slab0);
+    k_basis_onchip<CW, SM><<<grid, kOnchipThreads, smem, s>>>(L.ell, L.rowptr, L.width, L.m_pad, g->M, in, stack, C, K,
+                                                              write_slab0, F);
     CG_LAUNCH_CHECK();
     return CG_OK;
+}
+
+template <int SM>
+static int dispatch_onchip(int cw, const cg_graph *g, const CgCsr &L, const float *in, float *stack, int64_t C, int K,
+                           int w0, int F, cudaStream_t s) {
+    switch (cw) {
+        case 8: return launch_onchip<8, SM>(g, L, in, stack, C, K, w0, F, s);
+        case 16: return launch_onchip<16, SM>(g, L, in, stack, C, K, w0, F, s);
+        case 32: return launch_onchip<32, SM>(g, L, in, stack, C, K, w0, F, s);
+        case 64: return launch_onchip<64, SM>(g, L, in, stack, C, K, w0, F, s);
+        default: return launch_onchip<128, SM>(g, L, in, stack, C, K, w0, F, s);
+    }
+}
+
+// Sample-major basis straight from x [N][M][F] into stack [K][N][M][F] (no permute): possible whenever the
+// operator fits the on-chip kernel.
+bool cg_basis_samples_supported(const cg_graph *g, int transpose, int N, int F) {
+    const CgCsr &L = cg_side(g, transpose);
+    return N > 0 && L.width > 0 && onchip_cw(g, L, (int64_t)N * F) > 0;
+}
+
+int cg_run_basis_samples(const cg_graph *g, int transpose, const float *x, float *stack, int N, int F, int K,
+                         cudaStream_t s) {
+    const CgCsr &L = cg_side(g, transpose);
+    const int64_t C = (int64_t)N * F;
+    const int cw = L.width > 0 ? onchip_cw(g, L, C) : 0;
+    CG_REQUIRE(cw > 0, "cg_run_basis_samples: operator / columns do not fit the on-chip kernel");
+    CG_REQUIRE(((((uintptr_t)x) | ((uintptr_t)stack)) & 15) == 0, "cg_run_basis_samples: unaligned tensor");
+    if (K <= 1) {
+        if (x != stack)
+            CG_CHECK_CUDA(cudaMemcpyAsync(stack, x, sizeof(float) * (size_t)C * g->M, cudaMemcpyDeviceToDevice, s));
+        return CG_OK;
+    }
+    return dispatch_onchip<1>(cw, g, L, x, stack, C, K, x != stack, F, s);
 }
 
 // `in` is slab 0 (may alias stack); fills stack[1..K-1] (and stack[0] when in != stack).
@@ -218,14 +289,7 @@ static int run_basis_from(const cg_graph *g, int transpose, const float *in, flo
         return CG_ERR_ARG;
     }
     if (cw > 0 && K > 1) {
-        const int w0 = in != stack;
-        switch (cw) {
-            case 8: return launch_onchip<8>(g, L, in, stack, C, K, w0, s);
-            case 16: return launch_onchip<16>(g, L, in, stack, C, K, w0, s);
-            case 32: return launch_onchip<32>(g, L, in, stack, C, K, w0, s);
-            case 64: return launch_onchip<64>(g, L, in, stack, C, K, w0, s);
-            default: return launch_onchip<128>(g, L, in, stack, C, K, w0, s);
-        }
+        return dispatch_onchip<0>(cw, g, L, in, stack, C, K, in != stack, 1, s);
     }
     if (in != stack)
         CG_CHECK_CUDA(cudaMemcpyAsync(stack, in, sizeof(float) * (size_t)slab, cudaMemcpyDeviceToDevice, s));
