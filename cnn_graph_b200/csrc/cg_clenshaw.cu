@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw(const ClenshawParams p)
                 }
             };
             __syncthreads();                         // sync A: gy of this group is in tensor memory
-            if (lane == 0)
+            if (lane == 0 && umma::elect_lane0())
                 for (int k = K - 1; k >= 0 && k > K - 1 - NS; --k) issue(k);
             __syncwarp();
             for (int j = 0; j <= K; ++j) {
                 __syncthreads();                     // sync j: G_{K-1-j} has left its slot
                 const int kn = K - 1 - j - NS;
-                if (lane == 0 && kn >= 0) issue(kn);
+                if (kn >= 0 && lane == 0 && umma::elect_lane0()) issue(kn);
                 __syncwarp();
             }
             // the compute warps waited for every slot once per use as well

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
             __syncthreads();                              // operands of chunk c are staged
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && c >= 8 && c < 24 && lane == 0;
             if (tr) p.trace[(c - 8) * 8 + 5] = clock64();
-            if (lane == 0) {
+            if (umma::elect_one()) {
                 umma::fence_after_sync();
                 const uint32_t sb = st0 + (uint32_t)(c % p.nstage) * p.stage_bytes;
                 const uint32_t a_lo = umma::desc_lo(sb, 128u), b_lo = umma::desc_lo(sb + p.stage_b_off, 128u);
@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
                         uint32_t al = a_lo + (uint32_t)t * t_step + (pass == 1 ? a_mid : 0u);
                         uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
                         for (int j = 0; j < KD / 16; ++j) {
+                            if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && c == 30 && t * 3 + pass < 16)
+                                p.trace[64 + t * 3 + pass] = clock64();
                             umma::mma_bf16(acc, umma::desc_join(al, d_hi), umma::desc_join(bl, d_hi), idesc,
                                            (c | pass | j) != 0);
                             al += 16u;                      // two k groups of 128 bytes

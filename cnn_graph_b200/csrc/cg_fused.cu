@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
             const int nk16 = Fin / 16;
             for (int k = 0; k < K; ++k) {
                 __syncthreads();                                  // staging of step k is complete
-                if (lane == 0) {
+                if (lane == 0 && umma::elect_lane0()) {
                     const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
                     if (tr) p.trace[k * 8 + 4] = clock64();
                     const int b = k & (p.nw - 1);

@@ -19,6 +19,33 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// true in exactly one lane of a converged warp; the compiler treats the guarded region as single-threaded
+// (tcgen05 operands go to uniform registers without a per-instruction waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// the same inside an `if (lane == 0)` region (member mask = lane 0 only): always true, but it marks the region
+// as single-threaded for the compiler while per-lane pipeline state (barrier parities) stays in lane 0
+__device__ __forceinline__ bool elect_lane0() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0x00000001;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;

@@ -87,3 +87,5 @@ if os.environ.get('CG_TRACE_DW'):
     print(' c ' + ' '.join('%9s' % n for n in names))
     for c in range(16):
         print('%2d ' % c + ' '.join('%9d' % (v - t0 if v else -1) for v in t[c]))
+    tt = buf.cpu().numpy()[64:80]
+    print('per-MMA issue clocks (chunk 30):', [int(v - tt[0]) for v in tt if v])
