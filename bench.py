@@ -90,6 +90,8 @@ def step_work(L, N):
         # layer 1 (Fin = 1): unfused recurrence (forward, and again for dW) and FFMA contraction
         'basis_onchip': {'bound': 'hbm', 'launches': [(b_stream(M1, z1, N, K[0]), spmm_flops(M1, z1, N, K[0]))] * 2},
         'contract': {'bound': 'tensor', 'launches': [(0, g1)]},
+        # layer 1 contraction on the tensor cores: reads the basis (K N M fp32) once, writes y (N M 32 fp32)
+        'contract_umma': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * (K[0] * 1 + F[0]), g1)]},
     }
 
 
@@ -263,14 +265,18 @@ def run_ours(args):
 
     # per-kernel device time of the same step, CUDA events on the launch stream (profiling pass)
     roof, kernel_ms = None, {}
+    # every rank runs the profiling steps (the gradient all-reduce inside the step is a collective); only
+    # rank 0 records
+    prof_steps = min(args.steps, 5)
     if rank == 0:
         lib.cg_profile_reset()
         lib.cg_profile_enable(1)
-        prof_steps = min(args.steps, 5)
-        for _ in range(prof_steps):
-            flush.fill_(0.0)
-            step_resident()
-        torch.cuda.synchronize()
+    for _ in range(prof_steps):
+        flush.fill_(0.0)
+        step_resident()
+    torch.cuda.synchronize()
+    cgdist.barrier()
+    if rank == 0:
         lib.cg_profile_enable(0)
         import ctypes
         name = ctypes.create_string_buffer(64)

@@ -128,6 +128,11 @@ size_t cg_fused_workspace(int Fin, int Fout, int K);
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
                  int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);
 
+// Tensor-core contraction of a sample-major basis that lives in HBM (cg_contract_umma.cu).
+bool cg_contract_umma_supported(int N, int M, int Fa, int J, int K, size_t smem_limit);
+int cg_run_contract_umma(const float *stack, const float *W, float *y, int N, int M, int Fa, int J, int K, int sm_count,
+                         size_t smem_limit, cudaStream_t s);
+
 // Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,

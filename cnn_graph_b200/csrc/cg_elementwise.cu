@@ -266,6 +266,195 @@ extern "C" int cg_pool_bwd(const float *gy, const uint8_t *amax, float *gx, int 
 }
 
 // ---------------------------------------------------------------------------
+// fused bias + activation + pooling  (the brelu -> pool tail of every cgcnn layer,
+// lib/models.py:226-266 as sequenced by _inference): one pass over the filter output
+// instead of three, one pass over its gradient instead of two.
+//   max pooling : aux = index of the FIRST maximal activated value (TF MaxPoolGrad routing)
+//   avg pooling : aux = bit q set when activated element q is > 0 (relu) -- the relu mask
+// VEC features per thread (4 when F % 4 == 0).
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_bias_act_pool_fwd(const float *__restrict__ x, const float *__restrict__ bias, float *__restrict__ y,
+                    uint8_t *__restrict__ aux, int64_t NJ, int Mp, int F, int p, int bias_kind, int act, int kind) {
+    const int FV = F / VEC;
+    const int64_t total = NJ * FV;
+    const float inv = 1.0f / (float)p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nj = i / FV;
+        const int f = (int)(i - nj * FV) * VEC;
+        const int j = (int)(nj % Mp);                       // pooled vertex: bias kind 2 is indexed by (vertex, f)
+        const float *src = x + nj * p * F + f;
+        float best[VEC], sum[VEC];
+        int arg[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { best[e] = 0.f; sum[e] = 0.f; arg[e] = 0; }
+        for (int q = 0; q < p; ++q) {
+            float v[VEC];
+            if (VEC == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + (int64_t)q * F);
+                v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+            } else {
+                v[0] = src[(int64_t)q * F];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                float a = v[e];
+                if (bias_kind == 1) a += bias[f + e];
+                else if (bias_kind == 2) a += bias[((int64_t)j * p + q) * F + f + e];
+                a = act_fwd(a, act);
+                if (kind == 1) {
+                    if (q == 0 || a > best[e]) { best[e] = a; arg[e] = q; }
+                } else {
+                    sum[e] += a;
+                    if (a > 0.f) arg[e] |= 1 << q;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            y[nj * F + f + e] = kind == 1 ? best[e] : sum[e] * inv;
+            aux[nj * F + f + e] = (uint8_t)arg[e];
+        }
+    }
+}
+
+// gx[n, j*p+q, f] from the pooled gradient; db (optional) accumulates the bias gradient per thread and is
+// flushed with one atomicAdd per (thread, feature[, vertex]).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_bias_act_pool_bwd(const float *__restrict__ gy, const float *__restrict__ yp, const uint8_t *__restrict__ aux,
+                    float *__restrict__ gx, float *__restrict__ dbias, int64_t NJ, int Mp, int F, int p, int bias_kind,
+                    int act, int kind) {
+    const int FV = F / VEC;
+    const int64_t total = NJ * FV;
+    const float inv = 1.0f / (float)p;
+    // with a per-filter bias every thread keeps its feature columns: the grid stride is a multiple of FV
+    float dacc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) dacc[e] = 0.f;
+    int f_keep = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nj = i / FV;
+        const int f = (int)(i - nj * FV) * VEC;
+        const int j = (int)(nj % Mp);
+        f_keep = f;
+        float *dst = gx + nj * p * F + f;
+        float g[VEC];
+        int a[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float go = gy[nj * F + f + e];
+            const float yo = yp[nj * F + f + e];
+            a[e] = aux[nj * F + f + e];
+            // max: the routed element's activation derivative comes from the pooled value itself
+            g[e] = kind == 1 ? act_bwd_from_out(yo, go, act) : go * inv;
+        }
+        for (int q = 0; q < p; ++q) {
+            float o[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (kind == 1) o[e] = q == a[e] ? g[e] : 0.f;
+                else o[e] = (act == 1) ? (((a[e] >> q) & 1) ? g[e] : 0.f) : g[e];
+                if (bias_kind == 1) dacc[e] += o[e];
+                else if (bias_kind == 2 && dbias != nullptr && o[e] != 0.f)
+                    atomicAdd(dbias + ((int64_t)j * p + q) * F + f + e, o[e]);
+            }
+            if (VEC == 4) {
+                *reinterpret_cast<float4 *>(dst + (int64_t)q * F) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+            } else {
+                dst[(int64_t)q * F] = o[0];
+            }
+        }
+    }
+    if (bias_kind == 1 && dbias != nullptr) {
+        // block reduction per feature column (threads t, t + FV, ... of the block share their columns when
+        // 256 % FV == 0; otherwise every thread flushes on its own), then one atomicAdd per block and column
+        __shared__ float red[256 * VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) red[threadIdx.x * VEC + e] = f_keep >= 0 ? dacc[e] : 0.f;
+        __syncthreads();
+        if (256 % FV == 0) {
+            if ((int)threadIdx.x < FV) {
+                const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                const int f = (int)(i0 % FV) * VEC;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    float t = 0.f;
+                    for (int q = threadIdx.x; q < 256; q += FV) t += red[q * VEC + e];
+                    atomicAdd(dbias + f + e, t);
+                }
+            }
+        } else if (f_keep >= 0) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) atomicAdd(dbias + f_keep + e, dacc[e]);
+        }
+    }
+}
+
+static int check_fused_pool(const char *who, int M, int F, int p, int bias_kind, int act, int kind) {
+    CG_REQUIRE(kind == 1 || kind == 2, "%s: kind must be 1 (max) or 2 (avg)", who);
+    CG_REQUIRE(bias_kind >= 0 && bias_kind <= 2 && act >= 0 && act <= 2, "%s: bad bias_kind/act", who);
+    CG_REQUIRE(p >= 1 && p <= 8 && M % p == 0, "%s: p=%d must divide M=%d and be <= 8", who, p, M);
+    CG_REQUIRE(!(kind == 2 && act == 2), "%s: avg pooling after tanh is not fused (use cg_bias_act + cg_pool)", who);
+    CG_REQUIRE(F > 0, "%s: F must be positive", who);
+    return CG_OK;
+}
+
+// grid whose stride is a multiple of the per-row thread count FV (so a thread keeps its feature columns)
+static unsigned fused_pool_grid(int64_t total, int FV) {
+    int64_t blocks = cg_ceil_div(total, 256);
+    const int64_t cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    // gridDim.x * 256 must be a multiple of FV: round the block count up to a multiple of FV / gcd(FV, 256)
+    int64_t a = FV, b = 256;
+    while (b) { const int64_t t = a % b; a = b; b = t; }
+    const int64_t unit = FV / a;
+    blocks = cg_ceil_div(blocks, unit) * unit;
+    return (unsigned)blocks;
+}
+
+extern "C" int cg_bias_act_pool_fwd(const float *x, const float *bias, float *y, uint8_t *aux, int N, int M, int F,
+                                    int p, int bias_kind, int act, int kind, void *stream) {
+    int rc = check_fused_pool("cg_bias_act_pool_fwd", M, F, p, bias_kind, act, kind);
+    if (rc != CG_OK) return rc;
+    const int64_t NJ = (int64_t)N * (M / p);
+    if (NJ == 0) return CG_OK;
+    CG_REQUIRE(x && y && aux && (bias_kind == 0 || bias), "cg_bias_act_pool_fwd: NULL tensor");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v4 = F % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+    CgProfScope prof("bias_act_pool_fwd", s);
+    if (v4)
+        k_bias_act_pool_fwd<4><<<grid_for(NJ * (F / 4), 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+    else
+        k_bias_act_pool_fwd<1><<<grid_for(NJ * F, 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+extern "C" int cg_bias_act_pool_bwd(const float *gy, const float *y, const uint8_t *aux, float *gx, float *dbias,
+                                    int N, int M, int F, int p, int bias_kind, int act, int kind, void *stream) {
+    int rc = check_fused_pool("cg_bias_act_pool_bwd", M, F, p, bias_kind, act, kind);
+    if (rc != CG_OK) return rc;
+    const int64_t NJ = (int64_t)N * (M / p);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bias_kind == 0) dbias = nullptr;
+    if (dbias) CG_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)(bias_kind == 1 ? F : (int64_t)M * F), s));
+    if (NJ == 0) return CG_OK;
+    CG_REQUIRE(gy && y && aux && gx, "cg_bias_act_pool_bwd: NULL tensor");
+    const bool v4 = F % 4 == 0 && ((((uintptr_t)gx)) & 15) == 0;
+    CgProfScope prof("bias_act_pool_bwd", s);
+    if (v4)
+        k_bias_act_pool_bwd<4><<<fused_pool_grid(NJ * (F / 4), F / 4), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                                    bias_kind, act, kind);
+    else
+        k_bias_act_pool_bwd<1><<<fused_pool_grid(NJ * F, F), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                          bias_kind, act, kind);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
 // perm_data
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

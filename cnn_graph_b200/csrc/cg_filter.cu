@@ -122,8 +122,11 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
     if (samples_ok(g, 0, N, Fin, flags, x, stack_out ? stack_out : stack)) {
         float *st = stack_out ? stack_out : stack;                            // [K][N][M][F], rows in y's order
         rc = cg_run_basis_samples(g, 0, x, st, N, Fin, K, s);
-        if (rc == CG_OK) rc = cg_run_contract(st, W, y, N, M, Fin, Fout, K, false, true, s);
-        return rc;
+        if (rc != CG_OK) return rc;
+        if (!(flags & CG_FILTER_NO_FUSED) && (((uintptr_t)y) & 15) == 0 &&
+            cg_contract_umma_supported(N, M, Fin, Fout, K, g->smem_optin))
+            return cg_run_contract_umma(st, W, y, N, M, Fin, Fout, K, g->sm_count, g->smem_optin, s);
+        return cg_run_contract(st, W, y, N, M, Fin, Fout, K, false, true, s);
     }
     CG_REQUIRE(stack_out == nullptr, "cg_cheb_filter_fwd_ex: this call cannot save the basis (unaligned tensors)");
     rc = cg_run_permute_abf(x, stack, N, M, Fin, s);                          // [N][M][F] -> [M][N][F]

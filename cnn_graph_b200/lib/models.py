@@ -57,6 +57,33 @@ class GraphConvOps(object):
         b = self._bias_variable([1, int(x.shape[1]), int(x.shape[2])], regularization=False)
         return ops.bias_act(x, b, 'relu')
 
+    # brelu -> pool in one pass over the filter output (and one over its gradient) when both are the stock
+    # building blocks; values and gradients are those of pool(brelu(x)).  Set to False to run them separately
+    # (then nets['conv*/bias_relu'] is recorded as well).
+    fuse_brelu_pool = True
+
+    def _fused_brelu_pool(self, x, p):
+        """Returns pool(brelu(x), p) through ops.bias_act_pool, or None when this model's brelu / pool are not
+        the stock ones (the plugin surface lets users bind their own)."""
+        if not self.fuse_brelu_pool or p <= 1:
+            return None
+        brelu = getattr(self.brelu, '__func__', None)
+        pool = getattr(self.pool, '__func__', None)
+        stock_act = {GraphConvOps.b1relu: 'relu', GraphConvOps.b2relu: 'relu', GraphConvOps.b1tanh: 'tanh'}
+        stock_pool = {GraphConvOps.mpool1: 'max', GraphConvOps.apool1: 'avg'}
+        if brelu not in stock_act or pool not in stock_pool:
+            return None
+        act, kind = stock_act[brelu], stock_pool[pool]
+        if not ops.bias_act_pool_supported(act, p, kind):
+            return None
+        if brelu is GraphConvOps.b1relu and not self.b1relu_has_bias:
+            b = None
+        elif brelu is GraphConvOps.b2relu:
+            b = self._bias_variable([1, int(x.shape[1]), int(x.shape[2])], regularization=False)
+        else:
+            b = self._bias_variable([1, 1, int(x.shape[2])], regularization=False)
+        return ops.bias_act_pool(x, b, act, p, kind)
+
     # ---- pooling ----------------------------------------------------------------------
     def mpool1(self, x, p):
         """Max pooling of size p over the permuted vertex axis (lib/models.py:249-257)."""
@@ -198,10 +225,12 @@ class cgcnn(GraphConvOps, GraphModel):
                 with self.variable_scope('filter'):
                     x = self.filter(x, self.L[i], self.F[i], self.K[i])
                 with self.variable_scope('bias_relu'):
-                    x = self.brelu(x)
-                    self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
+                    fused = self._fused_brelu_pool(x, self.p[i])        # bias variable lives in this scope
+                    if fused is None:
+                        x = self.brelu(x)
+                        self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
                 with self.variable_scope('pooling'):
-                    x = self.pool(x, self.p[i])
+                    x = fused if fused is not None else self.pool(x, self.p[i])
                     self.nets['conv{}/pooling'.format(i + 1)] = x
         N, Mv, Fv = (int(d) for d in x.shape)
         x = x.reshape(N, Mv * Fv)

@@ -309,6 +309,63 @@ def pool(x, p, kind):
     return PoolFn.apply(x, int(p), 1 if kind in (1, 'max') else 2)
 
 
+class BiasActPoolFn(torch.autograd.Function):
+    """pool_p(act(x + bias)) in one pass (the brelu -> pool tail of a cgcnn layer, lib/models.py:226-266)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, act, p, kind):
+        _require_cuda(x, bias)
+        x = _f32c(x)
+        N, M, F = x.shape
+        bkind = 0
+        if bias is not None:
+            bias = _f32c(bias)
+            if bias.numel() == F:
+                bkind = 1
+            elif bias.numel() == M * F:
+                bkind = 2
+            else:
+                raise ValueError('bias must have F=%d or M*F=%d entries, got %d' % (F, M * F, bias.numel()))
+        if M % p != 0:
+            raise ValueError('pool size %d does not divide M=%d' % (p, M))
+        y = torch.empty((N, M // p, F), dtype=torch.float32, device=x.device)
+        aux = torch.empty((N, M // p, F), dtype=torch.uint8, device=x.device)
+        check(_native.lib().cg_bias_act_pool_fwd(ptr(x), ptr(bias), ptr(y), ptr(aux), N, M, F, p, bkind, act, kind,
+                                                 _stream()), 'cg_bias_act_pool_fwd')
+        ctx.save_for_backward(y, aux)
+        ctx.cfg = (N, M, F, p, bkind, act, kind)
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, aux = ctx.saved_tensors
+        N, M, F, p, bkind, act, kind = ctx.cfg
+        gy = _f32c(gy)
+        gx = torch.empty((N, M, F), dtype=torch.float32, device=y.device)
+        db = None
+        if bkind != 0 and ctx.needs_input_grad[1]:
+            db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=y.device)
+        check(_native.lib().cg_bias_act_pool_bwd(ptr(gy), ptr(y), ptr(aux), ptr(gx), ptr(db), N, M, F, p, bkind, act,
+                                                 kind, _stream()), 'cg_bias_act_pool_bwd')
+        return gx, db, None, None, None
+
+
+def bias_act_pool_supported(act, p, kind):
+    act = ACT[act] if isinstance(act, str) else int(act)
+    kind = 1 if kind in (1, 'max') else 2
+    return 1 < p <= 8 and not (kind == 2 and act == 2)
+
+
+def bias_act_pool(x, bias, act, p, kind):
+    """Fused bias + activation + pooling; same values as pool(bias_act(x, bias, act), p, kind)."""
+    act = ACT[act] if isinstance(act, str) else int(act)
+    kind = 1 if kind in (1, 'max') else 2
+    if x.is_meta:
+        return x.new_empty((x.shape[0], x.shape[1] // p, x.shape[2]))
+    return BiasActPoolFn.apply(x, bias, act, int(p), kind)
+
+
 def pool_argmax(x, p):
     """Pooled values and first-max indices (uint8) -- used by the bit-exact parity tests."""
     _require_cuda(x)

@@ -132,6 +132,19 @@ int cg_pool_fwd(const float *dev_x, float *dev_y, uint8_t *dev_argmax, int N, in
 int cg_pool_bwd(const float *dev_gy, const uint8_t *dev_argmax, float *dev_gx, int N, int M, int F,
                 int p, int kind, void *stream);
 
+/* ---- fused bias + activation + pooling -------------------------------- */
+/* The brelu -> pool tail of a cgcnn layer (lib/models.py:226-266 as sequenced by the model's
+ * _inference) in one pass: dev_y [N, M/p, F] = pool_p(act(x + bias)).  dev_aux [N, M/p, F] uint8:
+ * max pooling -- index of the first maximal activated value; avg pooling -- bit q set when
+ * activated element q is > 0.  The backward takes the pooled gradient, the pooled OUTPUT and aux
+ * and writes the gradient of x (and of the bias, overwritten, when dev_dbias is non-NULL).
+ * p <= 8; avg pooling after tanh is not supported (use the separate entry points).        */
+int cg_bias_act_pool_fwd(const float *dev_x, const float *dev_bias, float *dev_y, uint8_t *dev_aux, int N,
+                         int M, int F, int p, int bias_kind, int act, int kind, void *stream);
+int cg_bias_act_pool_bwd(const float *dev_gy, const float *dev_y, const uint8_t *dev_aux, float *dev_gx,
+                         float *dev_dbias, int N, int M, int F, int p, int bias_kind, int act, int kind,
+                         void *stream);
+
 /* ---- coarsening.perm_data ---------------------------------------------- */
 /* lib/coarsening.py:219-240: out[:, i] = x[:, perm[i]] if perm[i] < M else 0.
  * dev_x [N, M], dev_perm [Mnew] int32, dev_out [N, Mnew] (float32 on device;

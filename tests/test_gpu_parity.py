@@ -248,8 +248,10 @@ def test_full_size_c2_linearity_and_adjoint(ops, c2):
         y12 = ops.cheb_filter(2.0 * x1 - 0.5 * x2, W, L, K)
         close(y12, (2.0 * y1 - 0.5 * y2).detach().cpu().numpy())
         xa = x1.clone().requires_grad_(True)
-        g = torch.randn(N, M, Fout, device='cuda')
         ya = ops.cheb_filter(xa, W, L, K)
+        # g correlated with y: <y, g> ~ |y|^2 / 2 is a well-conditioned sum (an independent g gives a sum of
+        # 3e6 cancelling terms whose value is pure rounding noise at any fp32 precision)
+        g = 0.5 * ya.detach() + 0.5 * ya.detach().std() * torch.randn(N, M, Fout, device='cuda')
         ya.backward(g)
         lhs = float((ya.detach().double() * g.double()).sum())
         assert abs(lhs - float((xa.detach().double() * xa.grad.double()).sum())) <= 1e-4 * abs(lhs)
@@ -368,6 +370,7 @@ def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
     L = [csr_from(c2, 'L%d' % i) for i in range(5)]
     N = 6
     model = models.cgcnn(L, F=[32, 64], K=[25, 25], p=[4, 4], M=[512, 10], batch_size=N, dropout=1)
+    model.fuse_brelu_pool = False          # keep nets['conv*/bias_relu'] (the fused tail is checked below)
     rng = np.random.RandomState(9)
     x = rng.uniform(0, 1, (N, 992)).astype(np.float32)
     labels = rng.randint(0, 10, N)
@@ -411,6 +414,32 @@ def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
     loss = model.train_step(dev(x), torch.from_numpy(labels).cuda())
     assert np.isfinite(float(loss))
     assert not np.array_equal(before, model.get_var('conv1/filter/weights'))
+
+
+def test_cgcnn_fused_brelu_pool_matches_unfused_model(ops, c2):
+    """The default model fuses brelu -> pool into one kernel: same logits and parameter gradients as the
+    model that runs them separately (which the test above checks against the oracle)."""
+    from cnn_graph_b200.lib import models
+    L = [csr_from(c2, 'L%d' % i) for i in range(5)]
+    N = 8
+    rng = np.random.RandomState(4)
+    x = dev(rng.uniform(0, 1, (N, 992)).astype(np.float32))
+    g = dev(rng.standard_normal((N, 10)).astype(np.float32))
+    results = []
+    for fuse in (True, False):
+        torch.manual_seed(77)
+        model = models.cgcnn(L, F=[32, 64], K=[25, 25], p=[4, 4], M=[512, 10], batch_size=N, dropout=1)
+        model.fuse_brelu_pool = fuse
+        logits = model.inference(x, 1)
+        assert ('conv1/bias_relu' in model.nets) == (not fuse)
+        (logits * g).sum().backward()
+        results.append((logits.detach().cpu().numpy(),
+                        {k: p.grad.detach().cpu().numpy() for k, p in model.store.vars.items()}))
+    (lf, gf), (lu, gu) = results
+    close(lf, lu, 1e-6)
+    assert set(gf) == set(gu)
+    for k in gu:
+        close(gf[k], gu[k], 1e-5)
 
 
 def test_graphconv_and_glstm_models_run(ops, tf_ref, c2):
@@ -480,3 +509,53 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
     Lr = ops.rescale_csr(L)
     ref = graph_ref.chebyshev(Lr, np.ascontiguousarray(x.transpose(1, 0, 2).reshape(M, N * Fin)), K)
     close(stack.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 1e-5)
+
+
+@pytest.mark.parametrize('kind', ['max', 'avg'])
+@pytest.mark.parametrize('act,bias_kind', [('relu', 0), ('relu', 1), ('relu', 2), ('tanh', 1), ('none', 1)])
+@pytest.mark.parametrize('N,M,F,p', [(7, 24, 32, 4), (3, 16, 5, 2), (2, 64, 64, 8), (5, 8, 12, 4)])
+def test_fused_bias_act_pool_matches_separate_ops(ops, kind, act, bias_kind, N, M, F, p):
+    """pool(bias_act(x)) in one kernel: pooled values bit-equal to the two-kernel path, same gradients."""
+    if not ops.bias_act_pool_supported(act, p, kind):
+        pytest.skip('combination is not fused')
+    torch.manual_seed(N * 100 + M + F + p)
+    x = torch.randn(N, M, F, device='cuda')
+    x[0, :p] = 0.25                                   # ties inside one pooling window: first index must win
+    bias = None if bias_kind == 0 else (0.3 * torch.randn(F if bias_kind == 1 else M * F, device='cuda'))
+    gy = torch.randn(N, M // p, F, device='cuda')
+    outs = []
+    for fused in (True, False):
+        xt = x.clone().requires_grad_(True)
+        bt = None if bias is None else bias.clone().requires_grad_(True)
+        if fused:
+            y = ops.bias_act_pool(xt, bt, act, p, kind)
+        else:
+            y = ops.pool(ops.bias_act(xt, bt, act), p, kind)
+        y.backward(gy)
+        outs.append((y.detach(), xt.grad, None if bt is None else bt.grad))
+    (y1, gx1, gb1), (y0, gx0, gb0) = outs
+    assert torch.equal(y1, y0)
+    assert torch.equal(gx1, gx0) if kind == 'max' and act != 'tanh' else torch.allclose(gx1, gx0, rtol=1e-6, atol=1e-7)
+    if gb0 is not None:
+        assert torch.allclose(gb1, gb0, rtol=1e-4, atol=1e-5 * float(gb0.abs().max()))
+
+
+@pytest.mark.parametrize('level,N,Fin,Fout,K', [(0, 4, 1, 32, 25), (3, 12, 1, 16, 5), (4, 64, 2, 32, 7), (2, 9, 4, 64, 3),
+                                                (4, 66, 2, 128, 2), (3, 8, 8, 48, 20), (4, 4, 1, 16, 1)])
+def test_tensor_core_contraction_of_hbm_basis(ops, tf_ref, c2, level, N, Fin, Fout, K):
+    """Narrow inputs (Fin < 16) cannot use the fused kernel: sample-major basis in HBM, then the tcgen05
+    contraction kernel (ragged last chunk, Q = K*Fin not a multiple of 16, several chunks per CTA)."""
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(31 * level + K + N)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, K)
+    close(y, tf_ref.chebyshev5(x, L, W, K))
+    close(y, ops.cheb_filter(dev(x), dev(W), L, K, flags=ops.FILTER_NO_FUSED).cpu().numpy())
+    y.backward(dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
