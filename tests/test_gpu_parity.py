@@ -559,3 +559,42 @@ def test_tensor_core_contraction_of_hbm_basis(ops, tf_ref, c2, level, N, Fin, Fo
     dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
     close(xt.grad, dx)
     close(Wt.grad, dW)
+
+
+# --------------------------------------------------------------------------- BASELINE config C1 (usage.ipynb)
+def test_c1_usage_config_filters_and_model(ops, tf_ref, c1):
+    """Config C1: 100-feature kNN graph (irregular rows, up to 31 entries), 3 coarsening levels
+    [104, 52, 26], cgcnn F=[32,64] K=[20,20] p=[4,2] M=[512,3] with average pooling, batch 100.
+    Layer 2 (M = 26) packs several samples into one MMA row tile of the fused kernel."""
+    from cnn_graph_b200.lib import models
+    L = [csr_from(c1, 'L%d' % i) for i in range(3)]
+    N = 100
+    rng = np.random.RandomState(42)
+    # the two graph-conv layers on their own, forward and backward
+    for Lk, Fin, Fout in ((L[0], 1, 32), (L[2], 32, 64)):
+        M = Lk.shape[0]
+        x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+        W = (0.1 * rng.standard_normal((Fin * 20, Fout))).astype(np.float32)
+        gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, Lk, 20)
+        close(y, tf_ref.chebyshev5(x, Lk, W, 20))
+        y.backward(dev(gy))
+        dx, dW = tf_ref.chebyshev5_backward(x, Lk, W, 20, gy)
+        close(xt.grad, dx)
+        close(Wt.grad, dW)
+    # the model: filter -> b1relu -> apool1 twice, then the dense head
+    # the constructor wants all 1 + log2(4) + log2(2) levels; the last one (13 vertices) is never filtered on
+    L4 = L + [scipy.sparse.identity(13, format='csr', dtype=np.float32)]
+    model = models.cgcnn(L4, F=[32, 64], K=[20, 20], p=[4, 2], M=[512, 3], pool='apool1', batch_size=N, dropout=1)
+    x = rng.standard_normal((N, 104)).astype(np.float32)
+    logits = model.inference(dev(x), 1)
+    v = {k: p_.detach().cpu().numpy() for k, p_ in model.store.vars.items()}
+    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/filter/weights'], 20)
+    p1 = tf_ref.apool1(tf_ref.b1relu(a1, v['conv1/bias_relu/bias']), 4)
+    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/filter/weights'], 20)
+    p2 = tf_ref.apool1(tf_ref.b1relu(a2, v['conv2/bias_relu/bias']), 2)
+    f1 = tf_ref.fc(p2.reshape(N, -1), v['fc1/weights'], v['fc1/bias'])
+    close(logits, tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False))
+    close(model.nets['conv1/pooling'], p1)
+    close(model.nets['conv2/pooling'], p2)
