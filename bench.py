@@ -351,6 +351,15 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -365,6 +374,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        _shutdown()
 
 
 if __name__ == '__main__':

@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(XT, 1) k_contract_umma(const CtParams p) {
     const uint32_t st0 = umma::smem_u32(smem + p.off_stage);
     const uint32_t b0 = umma::smem_u32(smem + p.off_b);
     // MN-major canonical layouts: octet of 8 rows (A) / 8 output features (B) = 16 bytes; the 8 q of a k group
-    // are 16 bytes apart (128-byte core matrix), k groups 128 bytes apart, row octets SBO apart (+32: banks)
-    const uint32_t sbo = (uint32_t)(Qp / 8) * 128u + 32u;
+    // are 16 bytes apart (128-byte aligned core matrix), k groups 128 bytes apart, row octets SBO apart
+    const uint32_t sbo = (uint32_t)(Qp / 8) * 128u;
 
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) umma::mbar_init(bars + i, 1);
@@ -178,8 +178,15 @@ __global__ void __launch_bounds__(XT, 1) k_contract_umma(const CtParams p) {
             umma::mbar_wait(full + (c & 1), (uint32_t)((c >> 1) & 1));
             // stage c&1 and accumulator c&1 were last used by chunk c-2, whose epilogue ran in iteration c-1
             // ---- A: for every q the rows of the chunk in octets of 8 -> one 16-byte store
-            for (int e = tid; e < Q * (ROWS / 8); e += XC) {
-                const int q = e / (ROWS / 8), orow = e - q * (ROWS / 8);
+            // blocks of 8 q x 8 row octets dealt diagonally: a quarter-warp stores 8 different q of the same k
+            // group (the 128 contiguous bytes of a core matrix) and reads 8 different ring rows
+            const int nq8 = (Q + 7) / 8;
+            for (int e = tid; e < nq8 * 8 * (ROWS / 8); e += XC) {
+                const int blk = e >> 6, b = e & 63;
+                const int i = b & 7, ph = b >> 3;
+                const int qg = blk % nq8, og = blk / nq8;
+                const int q = qg * 8 + i, orow = og * 8 + ((i + ph) & 7);
+                if (q >= Q) continue;
                 const int k = q / Fa, f = q - k * Fa;
                 const float *src = reinterpret_cast<const float *>(ring + (size_t)k * p.piece) + (size_t)orow * 8 * Fa + f;
                 float v[8];
@@ -225,7 +232,7 @@ static CtPlan ct_plan(long long R, int Fa, int J, int K, size_t smem_limit) {
     if ((R * Fa) % 4 != 0 || (ROWS * Fa) % 4 != 0) return pl;       // 16-byte aligned pieces
     CtParams cp;
     memset(&cp, 0, sizeof(cp));
-    const uint32_t sbo = (uint32_t)(Qp / 8) * 128u + 32u;
+    const uint32_t sbo = (uint32_t)(Qp / 8) * 128u;
     uint32_t off = 0;
     cp.off_bar = off;
     off += 128;

@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
 
     const uint32_t ring0 = umma::smem_u32(smem + p.off_ring);
     const uint32_t st0 = umma::smem_u32(smem + p.off_stage);
-    // stride between 8-element groups along M/N: the k groups of one octet, padded by 32 bytes so that the
-    // four octets a quarter-warp converts land in different banks
-    const uint32_t sbo = (uint32_t)(KD / 8) * 128u + 32u;
+    // stride between 8-element groups along M/N = the k groups of one octet.  Core matrices stay 128-byte
+    // aligned (one shared-memory wavefront each for the tensor core); the conversion below deals (row, octet)
+    // pairs to lanes diagonally so that both its reads and its 16-byte stores spread over the banks.
+    const uint32_t sbo = (uint32_t)(KD / 8) * 128u;
     const uint32_t piece = (uint32_t)KD * Fa * 4u;      // one k piece of the ring: [KD][Fa] fp32
 
     if (tid == 0) {
@@ -203,12 +204,27 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
                 const int OA = Fa / 8;
                 const int total = nk * KD * OA;
                 for (int e = tid; e < total; e += DC) {
-                    int t, oa;
-                    if (p.oa_shift >= 0) { t = e >> p.oa_shift; oa = e & (OA - 1); } else { t = e / OA; oa = e - t * OA; }
-                    const int kr = t & (KD - 1), k = t >> kd_shift;
+                    int kr, k, oa;
+                    if (p.oa_shift >= 0) {
+                        // blocks of 8 rows x OA octets; lane (i, ph) of a block takes row i, octet (i + ph) % OA:
+                        // a quarter-warp stores 8 different rows (128 contiguous bytes of one or more core
+                        // matrices) and reads 4 different 32-byte slots of the ring rows
+                        const int blk = e >> (3 + p.oa_shift), b = e & (8 * OA - 1);
+                        const int i = b & 7, ph = b >> 3;
+                        const int kg = KD >> 3;
+                        k = blk / kg;
+                        kr = (blk - k * kg) * 8 + i;
+                        oa = (i + ph) & (OA - 1);
+                    } else {
+                        const int t = e / OA;
+                        oa = e - t * OA;
+                        kr = t & (KD - 1);
+                        k = t >> kd_shift;
+                    }
+                    const int es = (k * KD + kr) * OA + oa;          // source octet index in the ring
                     float v[8];
                     if (kr < rows) {
-                        const float4 *src = reinterpret_cast<const float4 *>(ring) + (size_t)e * 2;
+                        const float4 *src = reinterpret_cast<const float4 *>(ring) + (size_t)es * 2;
                         const float4 v0 = src[0], v1 = src[1];
                         v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
                         v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
@@ -247,10 +263,18 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
                 const int OB = Fb / 8;
                 for (int e = tid; e < KD * OB; e += DC) {
                     int kr, ob;
-                    if (p.ob_shift >= 0) { kr = e >> p.ob_shift; ob = e & (OB - 1); } else { kr = e / OB; ob = e - kr * OB; }
+                    if (p.ob_shift >= 0) {       // same diagonal dealing as for A
+                        const int blk = e >> (3 + p.ob_shift), b = e & (8 * OB - 1);
+                        const int i = b & 7, ph = b >> 3;
+                        kr = blk * 8 + i;
+                        ob = (i + ph) & (OB - 1);
+                    } else {
+                        kr = e / OB;
+                        ob = e - kr * OB;
+                    }
                     float v[8];
                     if (kr < rows) {
-                        const float4 *src = reinterpret_cast<const float4 *>(ring + p.ring_b_off) + (size_t)e * 2;
+                        const float4 *src = reinterpret_cast<const float4 *>(ring + p.ring_b_off) + (size_t)(kr * OB + ob) * 2;
                         const float4 v0 = src[0], v1 = src[1];
                         v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
                         v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
@@ -351,7 +375,7 @@ static DwPlan dw_plan(int N, int M, int Fa, int Fb, int K, int sm_count, size_t 
             dp.ring_bytes = dp.ring_b_off + (uint32_t)cg_align_up((size_t)Fb * KD * 4, 128);
             off += 2 * dp.ring_bytes;
             dp.off_stage = off;
-            const uint32_t sbo = (uint32_t)(KD / 8) * 128u + 32u;     // must match the kernel
+            const uint32_t sbo = (uint32_t)(KD / 8) * 128u;     // must match the kernel
             dp.stage_a_plane = (uint32_t)(Qp / 8) * sbo;
             dp.stage_b_off = 2 * dp.stage_a_plane;
             dp.stage_b_plane = (uint32_t)(Fb / 8) * sbo;
