@@ -312,3 +312,14 @@ extern "C" int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *de
     CG_REQUIRE(C > 0 && K >= 1, "cg_cheb_basis: C and K must be positive (C=%lld K=%d)", (long long)C, K);
     return run_basis_from(g, transpose, dev_X, dev_Xt, C, K, (cudaStream_t)stream, flags);
 }
+
+// One recurrence step on device-resident slabs: out = alpha * L X1 - X0 (X0 may be NULL).  The building block of
+// the row-partitioned recurrence (config C5): between two steps the caller exchanges the halo rows of X1.
+// Only the first `rows` rows are computed (rows <= M; the remaining rows of the padded operator are halo slots).
+extern "C" int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev_X1, const float *dev_X0,
+                            float *dev_out, int rows, int64_t C, float alpha, void *stream) {
+    CG_REQUIRE(g && dev_X1 && dev_out, "cg_cheb_step: NULL argument");
+    CG_REQUIRE(C > 0 && rows >= 0 && rows <= g->M, "cg_cheb_step: bad C / rows (C=%lld rows=%d M=%d)", (long long)C, rows, g->M);
+    if (rows == 0) return CG_OK;
+    return launch_step(cg_side(g, transpose), rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
+}

@@ -1,0 +1,112 @@
+"""Row-partitioned Chebyshev recurrence for graphs too large for one GPU's comfort (BASELINE config C5,
+SURVEY.md 8(e)(2)): the M rows of L~ and of every X_k are split into `world` contiguous blocks (after a
+locality ordering); one recurrence step needs the rows of X_{k-1} referenced by off-block columns -- the halo --
+which the ranks exchange point to point (NCCL all-to-all over NVLink on the B200 box, gloo in CPU tests).
+The contraction with W is row-local, so the forward needs no other communication.
+
+Every rank holds the whole (host) operator and derives all send / receive lists from it without talking to
+anyone: rank r needs the sorted distinct columns of its row block that fall outside the block; rank p sends, to
+every r, the part of r's list that lies in p's block.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse
+import torch
+import torch.distributed as dist
+
+from . import _native
+from .dist import shard_bounds
+
+
+class RowPartition:
+    """Partition of a square CSR operator over `world` ranks; local data of `rank`."""
+
+    def __init__(self, L, rank, world):
+        L = scipy.sparse.csr_matrix(L, dtype=np.float32)
+        L.sum_duplicates()
+        L.sort_indices()
+        self.M = L.shape[0]
+        self.rank, self.world = rank, world
+        self.bounds = [shard_bounds(self.M, r, world) for r in range(world)]
+        self.r0, self.r1 = self.bounds[rank]
+        self.nloc = self.r1 - self.r0
+        # halo of every rank (needed to know what to send): sorted distinct off-block columns
+        halos = []
+        for r, (b, e) in enumerate(self.bounds):
+            cols = np.unique(L.indices[L.indptr[b]:L.indptr[e]])
+            halos.append(cols[(cols < b) | (cols >= e)])
+        self.halo = halos[rank]
+        self.nhalo = int(self.halo.size)
+        owner_edges = np.array([b for b, _ in self.bounds] + [self.M])
+        # receive counts per peer (my halo, grouped by owner: it is sorted, so groups are contiguous and ordered)
+        own = np.searchsorted(owner_edges, self.halo, side='right') - 1
+        self.recv_counts = [int(np.sum(own == p)) for p in range(world)]
+        # send lists per peer: the part of peer's halo inside my block, as local row indices
+        self.send_idx = [(halos[p][(halos[p] >= self.r0) & (halos[p] < self.r1)] - self.r0).astype(np.int64)
+                         for p in range(world)]
+        self.send_counts = [int(s.size) for s in self.send_idx]
+        # local operator: rows of my block, columns remapped to [0, nloc) for owned and nloc + position for halo;
+        # padded to a square (nloc + nhalo) operator whose halo rows are empty
+        sub = L[self.r0:self.r1].tocoo()
+        col = sub.col.astype(np.int64)
+        inside = (col >= self.r0) & (col < self.r1)
+        newcol = np.where(inside, col - self.r0, self.nloc + np.searchsorted(self.halo, col))
+        n_ext = self.nloc + self.nhalo
+        self.n_ext = n_ext
+        self.local = scipy.sparse.csr_matrix((sub.data, (sub.row, newcol)), shape=(n_ext, n_ext), dtype=np.float32)
+        self.local.sort_indices()
+
+
+def _exchange(part, x_ext, send_index_dev, group=None):
+    """Fill x_ext[nloc:] with the halo rows (x_ext[:nloc] holds this rank's rows); all-to-all of packed rows."""
+    C = x_ext.shape[1]
+    send = x_ext.index_select(0, send_index_dev) if send_index_dev.numel() else x_ext.new_empty((0, C))
+    recv = x_ext[part.nloc:]
+    if part.world == 1:
+        return
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=part.recv_counts,
+                           input_split_sizes=part.send_counts, group=group)
+
+
+class PartitionedBasis:
+    """T_k(L~) X for the rows of this rank.  `step_fn(x1_ext, x0_loc_or_None, alpha) -> out_loc` applies the local
+    operator; the default is the native CUDA step (cg_cheb_step), tests inject a host function."""
+
+    def __init__(self, L_rescaled, rank=None, world=None, device=None, step_fn=None):
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.part = RowPartition(L_rescaled, rank, world)
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.send_index = torch.as_tensor(np.concatenate(self.part.send_idx) if world > 0 else np.zeros(0, np.int64),
+                                          dtype=torch.int64, device=self.device)
+        self._step_fn = step_fn
+        self._handle = None
+        if step_fn is None:
+            from . import ops
+            self._handle = ops.GraphHandle(self.part.local)
+
+    def _native_step(self, x1_ext, x0, alpha, out):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _native.check(_native.lib().cg_cheb_step(self._handle.handle, 0, x1_ext.data_ptr(),
+                                                 None if x0 is None else x0.data_ptr(), out.data_ptr(), self.part.nloc,
+                                                 x1_ext.shape[1], ctypes.c_float(alpha), stream), 'cg_cheb_step')
+
+    def basis(self, x_loc, K):
+        """x_loc [nloc, C] (this rank's rows of X) -> [K, nloc, C] (a view of the [K, nloc + nhalo, C] buffer whose
+        tail rows hold the halo of every X_k: each step writes its block in place, no staging copies)."""
+        part = self.part
+        C = x_loc.shape[1]
+        ext = torch.empty((K, part.n_ext, C), dtype=torch.float32, device=x_loc.device)
+        ext[0, :part.nloc] = x_loc
+        for k in range(1, K):
+            _exchange(part, ext[k - 1], self.send_index)
+            x0 = ext[k - 2, :part.nloc] if k > 1 else None
+            alpha = 2.0 if k > 1 else 1.0
+            if self._step_fn is not None:
+                ext[k, :part.nloc] = self._step_fn(ext[k - 1], x0, alpha)
+            else:
+                self._native_step(ext[k - 1], x0, alpha, ext[k, :part.nloc])
+        return ext[:, :part.nloc]

@@ -71,6 +71,12 @@ int cg_graph_info(const cg_graph_t *g, int64_t info[5]);
 int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float *dev_Xt,
                   int64_t C, int K, int flags, void *stream);
 
+/* One step of the same recurrence on caller-owned slabs: out[0:rows] = alpha * (L~ X1)[0:rows] - X0[0:rows]
+ * (dev_X0 may be NULL).  dev_X1 has all M rows of the (padded) operator; used by the row-partitioned
+ * recurrence of config C5, which exchanges the halo rows of X1 between two steps.              */
+int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev_X1, const float *dev_X0, float *dev_out,
+                 int rows, int64_t C, float alpha, void *stream);
+
 /* ---- Chebyshev filter (chebyshev5 / chebyshev2 / cheby_conv) ---------- */
 /* Forward: lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95
  *   y[n,m,fo] = sum_{fin,k} (T_k(L~) x)[n,m,fin] * W[fin*K+k, fo]
