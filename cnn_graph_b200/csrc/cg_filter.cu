@@ -54,6 +54,10 @@ extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N,
     return wide + cg_align_up(part_a > part_b ? part_a : part_b, 256) + cg_fused_workspace(Fin, Fout, K);
 }
 
+static bool aligned16(const void *a, const void *b, const void *c) {
+    return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15) == 0;
+}
+
 // fused kernel wanted and possible?  (CG_FILTER_FORCE_FUSED turns "not possible" into an error)
 static int want_fused(const char *who, const cg_graph *g, int transpose, int N, int Fin, int Fout, int K, int flags,
                       bool *use) {
@@ -112,6 +116,10 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
     bool fused = false;
     rc = want_fused("cg_cheb_filter_fwd", g, 0, N, Fin, Fout, K, flags, &fused);
     if (rc != CG_OK) return rc;
+    if (fused && !aligned16(x, y, stack_out)) {          // bulk copies and 128-bit accesses need 16-byte alignment
+        CG_REQUIRE(!(flags & CG_FILTER_FORCE_FUSED), "cg_cheb_filter_fwd: fused kernel needs 16-byte aligned tensors");
+        fused = false;
+    }
     if (fused) {
         void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
         return cg_run_fused(g, 0, x, W, y, stack_out, N, Fin, Fout, K, false, wpack, s);
@@ -174,10 +182,15 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
     if (need_dx) {
         bool fused = false;
         const bool allow = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING));
-        const bool clenshaw = allow && !(flags & CG_FILTER_NO_CLENSHAW) && cg_clenshaw_supported(g, N, Fin, Fout, K);
+        const bool al = aligned16(gy, dx, nullptr);
+        const bool clenshaw = allow && al && !(flags & CG_FILTER_NO_CLENSHAW) && cg_clenshaw_supported(g, N, Fin, Fout, K);
         if (!clenshaw) {
             rc = want_fused("cg_cheb_filter_bwd", g, 1, N, Fout, Fin, K, flags, &fused);
             if (rc != CG_OK) return rc;
+            if (fused && !al) {
+                CG_REQUIRE(!(flags & CG_FILTER_FORCE_FUSED), "cg_cheb_filter_bwd: fused kernel needs 16-byte aligned tensors");
+                fused = false;
+            }
         }
         void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
         if (clenshaw) {

@@ -32,9 +32,13 @@ def _require_cuda(*tensors):
 
 
 def _f32c(t):
+    """float32, contiguous and 16-byte aligned (bulk copies and 128-bit accesses of the native kernels)."""
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
 
 
 # ---------------------------------------------------------------------------------------

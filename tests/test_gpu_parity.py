@@ -598,3 +598,35 @@ def test_c1_usage_config_filters_and_model(ops, tf_ref, c1):
     close(logits, tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False))
     close(model.nets['conv1/pooling'], p1)
     close(model.nets['conv2/pooling'], p2)
+
+
+# --------------------------------------------------------------------------- BASELINE config C3 (20NEWS-shaped)
+def test_c3_20news_shaped_config(ops, tf_ref):
+    """Config C3: 10 000-word 16-NN cosine feature graph (no coarsening), cgcnn F=[32] K=[5] p=[1] M=[20],
+    l1-normalised sparse bag-of-words rows densified per batch (lib/graph_model.py:150-151), batch 100.
+    The operator does not fit shared memory: streaming recurrence (one CSR step per launch)."""
+    import scipy.sparse
+    from cnn_graph_b200.lib import graph, models
+    rng = np.random.RandomState(2017)
+    Mw, N = 10000, 100
+    emb = rng.standard_normal((Mw, 100)).astype(np.float32)
+    dist_, idx = graph.distance_sklearn_metrics(emb, k=16, metric='cosine')
+    L = graph.laplacian(graph.adjacency(dist_, idx), normalized=True)
+    assert not ops.get_handle(L).info()['onchip']
+    counts = scipy.sparse.random(N, Mw, density=0.008, random_state=rng, format='csr', dtype=np.float32)
+    counts.data = np.ceil(counts.data * 5)
+    x = np.asarray((counts.multiply(1.0 / counts.sum(axis=1))).todense(), dtype=np.float32)      # rows sum to 1
+    W = (0.1 * rng.standard_normal((5, 32))).astype(np.float32)
+    gy = rng.standard_normal((N, Mw, 32)).astype(np.float32)
+    xt, Wt = dev(x[:, :, None]).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, 5)
+    close(y, tf_ref.chebyshev5(x[:, :, None], L, W, 5))
+    y.backward(dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x[:, :, None], L, W, 5, gy)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
+    model = models.cgcnn([L], F=[32], K=[5], p=[1], M=[20], batch_size=N, dropout=1)
+    logits = model.inference(dev(x), 1)
+    v = {k: p_.detach().cpu().numpy() for k, p_ in model.store.vars.items()}
+    r1 = tf_ref.b1relu(tf_ref.chebyshev5(x[:, :, None], L, v['conv1/filter/weights'], 5), v['conv1/bias_relu/bias'])
+    close(logits, tf_ref.fc(r1.reshape(N, -1), v['logits/weights'], v['logits/bias'], relu=False))
