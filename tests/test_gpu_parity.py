@@ -133,7 +133,7 @@ def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K)
 
 
 @pytest.mark.parametrize('level,N,Fin,Fout,K', [(2, 5, 32, 64, 25), (4, 37, 64, 16, 4), (3, 10, 32, 64, 3),
-                                                (3, 9, 16, 16, 1), (3, 5, 64, 64, 25), (4, 130, 16, 32, 3)])
+                                                (3, 9, 16, 16, 1), (3, 5, 64, 64, 25), (4, 130, 16, 32, 3), (2, 301, 32, 64, 5), (4, 700, 16, 16, 4)])
 @pytest.mark.parametrize('dx_kernel', ['clenshaw', 'forward_form'])
 def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K, dx_kernel):
     """dx through the adjoint (Clenshaw) kernel or the forward-form fused kernel on L~^T; dW from the basis."""
