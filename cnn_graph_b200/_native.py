@@ -50,6 +50,9 @@ _SIGNATURES = {
                                      c_int, c_void_p]),
     'cg_bias_act_pool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_void_p]),
+    'cg_gemm_f32_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'cg_gemm_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'cg_perm_data': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     'cg_lstm_gates_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
                                   c_void_p]),

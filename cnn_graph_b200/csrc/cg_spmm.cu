@@ -223,6 +223,8 @@ static int onchip_cw(const cg_graph *g, const CgCsr &L, int64_t C) {
     }
     // do not pick a group much wider than the problem
     while (best > 8 && best / 2 >= C) best /= 2;
+    // one CTA owns one column group for all K steps: prefer narrower groups while the grid does not fill the SMs
+    while (best > 8 && cg_ceil_div(C, best) < g->sm_count) best /= 2;
     return best;
 }
 

@@ -57,6 +57,9 @@ class GraphConvOps(object):
         b = self._bias_variable([1, int(x.shape[1]), int(x.shape[2])], regularization=False)
         return ops.bias_act(x, b, 'relu')
 
+    # dense head through the library's tensor-core GEMM (fp32-level accuracy); False = torch.addmm (cuBLAS fp32)
+    fc_on_tensor_cores = True
+
     # brelu -> pool in one pass over the filter output (and one over its gradient) when both are the stock
     # building blocks; values and gradients are those of pool(brelu(x)).  Set to False to run them separately
     # (then nets['conv*/bias_relu'] is recorded as well).
@@ -101,6 +104,8 @@ class GraphConvOps(object):
         b = self._bias_variable([Mout], regularization=True)
         if x.is_meta:
             return x.new_empty((N, Mout))
+        if self.fc_on_tensor_cores and x.is_cuda:
+            return ops.linear(x, W, b, relu=relu)         # cg_gemm_f32: bf16 hi+mid split, fp32 accumulate
         x = torch.addmm(b, x, W)
         return torch.relu(x) if relu else x
 

@@ -382,6 +382,60 @@ def pool_argmax(x, p):
 
 
 # ---------------------------------------------------------------------------------------
+# dense head (fc layers) on the tensor cores
+# ---------------------------------------------------------------------------------------
+
+def gemm(A, B, transA=False, transB=False, bias=None, relu=False):
+    """C = op(A) @ op(B) (+ bias) (relu) through cg_gemm_f32; A, B 2-D float32 CUDA tensors (row-major)."""
+    _require_cuda(A, B, bias)
+    A, B = _f32c(A), _f32c(B)
+    M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
+    Kb, N = (B.shape[1], B.shape[0]) if transB else (B.shape[0], B.shape[1])
+    if K != Kb:
+        raise ValueError('inner dimensions differ: %d vs %d' % (K, Kb))
+    if bias is not None:
+        bias = _f32c(bias).reshape(-1)
+        if bias.numel() != N:
+            raise ValueError('bias must have N=%d entries' % N)
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    lib = _native.lib()
+    nbytes = lib.cg_gemm_f32_workspace_bytes(M, N, K)
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=A.device)
+    check(lib.cg_gemm_f32(ptr(A), ptr(B), ptr(C), M, N, K, int(transA), int(transB), A.shape[1], B.shape[1], N,
+                          ptr(bias), int(relu), ptr(ws), nbytes, _stream()), 'cg_gemm_f32')
+    return C
+
+
+class LinearFn(torch.autograd.Function):
+    """y = relu?(x W + b)  (lib/models.py:268-274) with both gradients on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        y = gemm(x, W, bias=b, relu=relu)
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.relu = relu
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        gy = _f32c(gy)
+        if ctx.relu:
+            gy = gy * (y > 0)
+        dx = gemm(gy, W, transB=True) if ctx.needs_input_grad[0] else None          # [N, out] . [in, out]^T
+        dW = gemm(x, gy, transA=True) if ctx.needs_input_grad[1] else None          # [N, in]^T . [N, out]
+        db = gy.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+def linear(x, W, b=None, relu=False):
+    if x.is_meta:
+        return x.new_empty((x.shape[0], W.shape[1]))
+    return LinearFn.apply(x, W, b, bool(relu))
+
+
+# ---------------------------------------------------------------------------------------
 # perm_data on the device
 # ---------------------------------------------------------------------------------------
 

@@ -151,6 +151,17 @@ int cg_bias_act_pool_bwd(const float *dev_gy, const float *dev_y, const uint8_t 
                          float *dev_dbias, int N, int M, int F, int p, int bias_kind, int act, int kind,
                          void *stream);
 
+/* ---- dense head -------------------------------------------------------- */
+/* fc layers of cgcnn (lib/models.py:268-274: relu(x W + b)) and their gradients: a general fp32 GEMM on the
+ * tensor cores, C[M x N] = op(A)[M x K] . op(B)[K x N] (+ bias[N]) (relu), all matrices row-major;
+ * transA != 0: A is stored [K][lda >= M]; transB != 0: B is stored [N][ldb >= K].  Same bf16 hi+mid split
+ * with fp32 accumulation as the filter kernels (fp32-level accuracy).  Scratch (split-K partial tiles) is
+ * sized by cg_gemm_f32_workspace_bytes and may be NULL when that returns 0.                              */
+size_t cg_gemm_f32_workspace_bytes(int M, int N, int K);
+int cg_gemm_f32(const float *dev_A, const float *dev_B, float *dev_C, int M, int N, int K, int transA,
+                int transB, int lda, int ldb, int ldc, const float *dev_bias, int relu, void *dev_workspace,
+                size_t workspace_bytes, void *stream);
+
 /* ---- coarsening.perm_data ---------------------------------------------- */
 /* lib/coarsening.py:219-240: out[:, i] = x[:, perm[i]] if perm[i] < M else 0.
  * dev_x [N, M], dev_perm [Mnew] int32, dev_out [N, Mnew] (float32 on device;

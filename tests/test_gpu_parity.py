@@ -630,3 +630,36 @@ def test_c3_20news_shaped_config(ops, tf_ref):
     v = {k: p_.detach().cpu().numpy() for k, p_ in model.store.vars.items()}
     r1 = tf_ref.b1relu(tf_ref.chebyshev5(x[:, :, None], L, v['conv1/filter/weights'], 5), v['conv1/bias_relu/bias'])
     close(logits, tf_ref.fc(r1.reshape(N, -1), v['logits/weights'], v['logits/bias'], relu=False))
+
+
+# --------------------------------------------------------------------------- dense head GEMM
+@pytest.mark.parametrize('M,N,K', [(1024, 512, 3968), (100, 10, 512), (7, 300, 65), (129, 257, 64), (256, 256, 1000)])
+@pytest.mark.parametrize('transA,transB', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_f32_tensor_core(ops, M, N, K, transA, transB):
+    """cg_gemm_f32 against float64 matmul: fp32-level accuracy (bf16 hi+mid split, fp32 accumulation), all four
+    operand orientations, ragged tiles, split-K."""
+    torch.manual_seed(M + N + K)
+    A = torch.randn((K, M) if transA else (M, K), device='cuda')
+    B = torch.randn((N, K) if transB else (K, N), device='cuda')
+    bias = torch.randn(N, device='cuda')
+    ref = (A.double().t() if transA else A.double()) @ (B.double().t() if transB else B.double())
+    close(ops.gemm(A, B, transA=transA, transB=transB), ref.cpu().numpy())
+    got = ops.gemm(A, B, transA=transA, transB=transB, bias=bias, relu=True)
+    close(got, torch.relu(ref + bias.double()).cpu().numpy())
+
+
+def test_linear_layer_gradients(ops):
+    torch.manual_seed(3)
+    x = torch.randn(64, 200, device='cuda', requires_grad=True)
+    W = (0.1 * torch.randn(200, 48, device='cuda')).requires_grad_(True)
+    b = torch.randn(48, device='cuda', requires_grad=True)
+    g = torch.randn(64, 48, device='cuda')
+    y = ops.linear(x, W, b, relu=True)
+    y.backward(g)
+    xd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+    yd = torch.relu(xd @ Wd + bd)
+    yd.backward(g.double())
+    close(y, yd.detach().cpu().numpy())
+    close(x.grad, xd.grad.cpu().numpy())
+    close(W.grad, Wd.grad.cpu().numpy())
+    close(b.grad, bd.grad.cpu().numpy())
