@@ -133,6 +133,14 @@ bool cg_contract_umma_supported(int N, int M, int Fa, int J, int K, size_t smem_
 int cg_run_contract_umma(const float *stack, const float *W, float *y, int N, int M, int Fa, int J, int K, int sm_count,
                          size_t smem_limit, cudaStream_t s);
 
+// General fp32 GEMM on the tensor cores (cg_gemm_umma.cu) with optional K blocking of the operands:
+//   a_kblk > 0: A element (m, q) at A[(q / a_kblk) * a_kbs + m * lda + q % a_kblk]   (a Chebyshev stack [K][R][F])
+//   b_kblk > 0: B row of q is (q / b_kblk) * b_shi + (q % b_kblk) * b_slo            (W rows f*K + k for q = k*F + f)
+size_t cg_gemm_workspace(int M, int N, int K);
+int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda, int ldb,
+                int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi, int b_slo,
+                void *workspace, size_t workspace_bytes, cudaStream_t s);
+
 // Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,

@@ -7,6 +7,8 @@
 //           dW = x^T Z_k   (stack_t_plain, swapped)   dW[fin*K+k,fo] = sum_{n,m} x[n,m,fin] Z_k[n,m,fo]
 //   without dx (first layer, chebyshev2):  dW = X_k^T gy with X = basis(L~, x).
 // The forward stack is never saved: backward needs only x, gy and W.
+#include <algorithm>
+
 #include "cg_common.cuh"
 
 static size_t stack_bytes(const cg_graph *g, int N, int F, int K) {
@@ -16,14 +18,18 @@ static size_t stack_bytes(const cg_graph *g, int N, int F, int K) {
 extern "C" size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
     (void)flags;
     if (!g) return 0;
-    return (K > 1 ? stack_bytes(g, N, Fin, K) : 0) + cg_fused_workspace(Fin, Fout, K);
+    const int64_t R = (int64_t)N * g->M;
+    const size_t gws = R > 0 && R < (int64_t)INT32_MAX ? cg_align_up(cg_gemm_workspace((int)R, Fout, K * Fin), 256) : 0;
+    return (K > 1 ? stack_bytes(g, N, Fin, K) : 0) + gws + cg_fused_workspace(Fin, Fout, K);
 }
 
 // stack^T x plain: tensor-core kernel when the shape allows it, FFMA kernel otherwise
 static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const size_t a = cg_stack_t_plain_workspace(N, g->M, Fa, Fb, K, g->sm_count);
     const size_t b = cg_dw_umma_workspace(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
-    return a > b ? a : b;
+    const int64_t R = (int64_t)N * g->M;
+    const size_t c = R < (int64_t)INT32_MAX ? cg_gemm_workspace(Fa, Fb, (int)R) : 0;       // per-k GEMM, split over R
+    return std::max(a, std::max(b, c));
 }
 
 static int run_dw(const cg_graph *g, const float *stack, const float *T, float *dW, int N, int Fa, int Fb, int K,
@@ -33,6 +39,24 @@ static int run_dw(const cg_graph *g, const float *stack, const float *T, float *
                     ((((uintptr_t)stack | (uintptr_t)T | (uintptr_t)part) & 15) == 0);
     if (tc)
         return cg_run_dw_umma(stack, T, dW, N, g->M, Fa, Fb, K, swap, sample_major, part, g->sm_count, g->smem_optin, s);
+    const int64_t R = (int64_t)N * g->M;
+    if (sample_major && !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) && R < (int64_t)INT32_MAX) {
+        // shapes the TMEM-resident kernel does not take (Fb > 256, ...): one tensor-core GEMM per k,
+        //   dW_k = stack_k^T T   (rows a*K + k)        or, swapped,   dW_k = T^T stack_k   (rows b*K + k)
+        const size_t ws = cg_gemm_workspace(swap ? Fb : Fa, swap ? Fa : Fb, (int)R);
+        for (int k = 0; k < K; ++k) {
+            const float *sk = stack + (size_t)k * R * Fa;
+            int rc;
+            if (!swap)
+                rc = cg_run_gemm(sk, T, dW + (size_t)k * Fb, Fa, Fb, (int)R, 1, 0, Fa, Fb, K * Fb, nullptr, 0, 0, 0, 0, 0, 0,
+                                 part, ws, s);
+            else
+                rc = cg_run_gemm(T, sk, dW + (size_t)k * Fa, Fb, Fa, (int)R, 1, 0, Fb, Fa, K * Fa, nullptr, 0, 0, 0, 0, 0, 0,
+                                 part, ws, s);
+            if (rc != CG_OK) return rc;
+        }
+        return CG_OK;
+    }
     return cg_run_stack_t_plain(stack, T, dW, N, g->M, Fa, Fb, K, swap, sample_major, part, g->sm_count, s);
 }
 
@@ -51,7 +75,9 @@ extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N,
     const size_t part_a = dw_workspace(g, N, Fout, Fin, K);
     const size_t part_b = dw_workspace(g, N, Fin, Fout, K);
     (void)need_dx;
-    return wide + cg_align_up(part_a > part_b ? part_a : part_b, 256) + cg_fused_workspace(Fin, Fout, K);
+    const int64_t R = (int64_t)N * g->M;
+    const size_t gdx = R > 0 && R < (int64_t)INT32_MAX ? cg_gemm_workspace((int)R, Fin, K * Fout) : 0;
+    return wide + cg_align_up(std::max(gdx, std::max(part_a, part_b)), 256) + cg_fused_workspace(Fin, Fout, K);
 }
 
 static bool aligned16(const void *a, const void *b, const void *c) {
@@ -134,6 +160,14 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
         if (!(flags & CG_FILTER_NO_FUSED) && (((uintptr_t)y) & 15) == 0 &&
             cg_contract_umma_supported(N, M, Fin, Fout, K, g->smem_optin))
             return cg_run_contract_umma(st, W, y, N, M, Fin, Fout, K, g->sm_count, g->smem_optin, s);
+        if (!(flags & CG_FILTER_NO_FUSED) && (int64_t)N * M < (int64_t)INT32_MAX) {
+            // wide outputs (Fout > 128, e.g. the 4H gates of the gconv-LSTM): general tensor-core GEMM over the
+            // K-blocked basis, q = k*Fin + f  <->  W row f*K + k
+            const int64_t R = (int64_t)N * M;
+            void *gws = reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K);
+            return cg_run_gemm(st, W, y, (int)R, Fout, K * Fin, 0, 0, Fin, Fout, Fout, nullptr, 0, Fin, (long long)R * Fin,
+                               Fin, 1, K, gws, cg_gemm_workspace((int)R, Fout, K * Fin), s);
+        }
         return cg_run_contract(st, W, y, N, M, Fin, Fout, K, false, true, s);
     }
     CG_REQUIRE(stack_out == nullptr, "cg_cheb_filter_fwd_ex: this call cannot save the basis (unaligned tensors)");
@@ -211,7 +245,16 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
                 rc = cg_run_permute_abf(gy, stack, N, M, Fout, s);
                 if (rc == CG_OK) rc = cg_run_basis(g, 1, stack, (int64_t)N * Fout, K, s, flags);
             }
-            if (rc == CG_OK) rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, sm, s);
+            if (rc == CG_OK) {
+                const int64_t R = (int64_t)N * M;
+                if (sm && !(flags & CG_FILTER_NO_FUSED) && R < (int64_t)INT32_MAX) {
+                    // dx = [Z_0 .. Z_{K-1}] W^T: A = K-blocked Z stack, B = W read as [fin][k*Fout + fo] (transposed)
+                    rc = cg_run_gemm(stack, W, dx, (int)R, Fin, K * Fout, 0, 1, Fout, K * Fout, Fin, nullptr, 0, Fout,
+                                     (long long)R * Fout, 0, 0, 0, part, cg_gemm_workspace((int)R, Fin, K * Fout), s);
+                } else {
+                    rc = cg_run_contract(stack, W, dx, N, M, Fout, Fin, K, true, sm, s);
+                }
+            }
             if (rc == CG_OK && !have_dW) rc = run_dw(g, stack, x, dW, N, Fout, Fin, K, true, sm, part, flags, s);
             if (rc != CG_OK) return rc;
             have_dW = true;

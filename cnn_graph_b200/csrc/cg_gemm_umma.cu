@@ -32,6 +32,10 @@ struct GemmParams {
     const float *A, *B, *bias;
     float *C;                    // [M][ldc] (split == 1) or partials [split][M][N]
     int M, N, K, lda, ldb, ldc, transA, transB, relu, BN, split, k_per_split, vecA, vecB;
+    // K-blocked operands (contractions over a Chebyshev stack): A element (m, q) at A[(q / a_kblk) * a_kbs + m * lda +
+    // q % a_kblk] (transA == 0 only); B row of q (transB == 0 only) is (q / b_kblk) * b_shi + (q % b_kblk) * b_slo
+    long long a_kbs;
+    int a_kblk, b_kblk, b_shi, b_slo;
     uint32_t off_a, off_b, stage_bytes, a_plane, b_plane, off_bar;
 };
 
@@ -41,9 +45,12 @@ struct GemmParams {
 //   KC = false: the row index is contiguous (element (r, k) at src[k * ld + r]); MN-major layout
 //               offset = (r/8) * (BK * 16) + (k/8) * 128 + (k%8) * 16
 // r < r_lim, k < k_lim are the valid ranges (zero fill outside); `vec` = 128-bit loads allowed.
+// K blocking: KC = true  -> element (r, q) at src[(q / kblk) * kbs + r * ld + q % kblk]   (kblk % 8 == 0 for `vec`)
+//             KC = false -> source row of q is (q / kblk) * shi + (q % kblk) * slo
 template <bool KC>
 __device__ __forceinline__ void stage_operand(unsigned char *hi_plane, uint32_t plane_bytes, const float *src, int ld, int rows,
-                                              int r0, int r_lim, int k0, int k_lim, int vec, int tid) {
+                                              int r0, int r_lim, int k0, int k_lim, int vec, int tid, int kblk, long long kbs,
+                                              int shi, int slo) {
     const int n_r8 = rows / 8;                 // row octets (or rows / 8 blocks)
     const int total = n_r8 * (BK / 8) * 8;     // items: (8 x 8) blocks of (row-or-k, octet)
     for (int e = tid; e < total; e += GC) {
@@ -55,13 +62,21 @@ __device__ __forceinline__ void stage_operand(unsigned char *hi_plane, uint32_t 
             // block = 8 rows x 8 k-octets; lane (i, ph): row i of the block, octet (i + ph) & 7  (BK / 8 == 8)
             const int r = blk * 8 + i, ko = (i + ph) & 7;
             const int gr = r0 + r, gk = k0 + ko * 8;
-            const float *p = src + (size_t)gr * ld + gk;
             if (gr < r_lim && gk + 7 < k_lim && vec) {
+                const int kb = gk / kblk, ki = gk - kb * kblk;
+                const float *p = src + (size_t)kb * kbs + (size_t)gr * ld + ki;
                 const float4 a = *reinterpret_cast<const float4 *>(p), c = *reinterpret_cast<const float4 *>(p + 4);
                 v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (gr < r_lim && gk + j < k_lim) ? p[j] : 0.f;
+                for (int j = 0; j < 8; ++j) {
+                    float x = 0.f;
+                    if (gr < r_lim && gk + j < k_lim) {
+                        const int kb = (gk + j) / kblk, ki = (gk + j) - kb * kblk;
+                        x = src[(size_t)kb * kbs + (size_t)gr * ld + ki];
+                    }
+                    v[j] = x;
+                }
             }
             off = (uint32_t)ko * (uint32_t)(rows * 16) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
         } else {
@@ -70,7 +85,8 @@ __device__ __forceinline__ void stage_operand(unsigned char *hi_plane, uint32_t 
             const int kb = blk / nb_r, rb = blk - kb * nb_r;
             const int k = kb * 8 + i, ro = rb * 8 + ((i + ph) & 7);
             const int gk = k0 + k, gr = r0 + ro * 8;
-            const float *p = src + (size_t)gk * ld + gr;
+            const int qb = gk / kblk;
+            const float *p = src + ((size_t)qb * shi + (size_t)(gk - qb * kblk) * slo) * ld + gr;
             if (gk < k_lim && gr + 7 < r_lim && vec) {
                 const float4 a = *reinterpret_cast<const float4 *>(p), c = *reinterpret_cast<const float4 *>(p + 4);
                 v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
@@ -149,13 +165,13 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_umma(const GemmParams p) {
             unsigned char *sb = smem + (size_t)(s & 1) * p.stage_bytes;
             const int k0 = k_beg + s * BK;
             if (p.transA)
-                stage_operand<false>(sb + p.off_a, p.a_plane, p.A, p.lda, BM, m0, p.M, k0, k_end, p.vecA, tid);
+                stage_operand<false>(sb + p.off_a, p.a_plane, p.A, p.lda, BM, m0, p.M, k0, k_end, p.vecA, tid, 1 << 30, 0, 0, 1);
             else
-                stage_operand<true>(sb + p.off_a, p.a_plane, p.A, p.lda, BM, m0, p.M, k0, k_end, p.vecA, tid);
+                stage_operand<true>(sb + p.off_a, p.a_plane, p.A, p.lda, BM, m0, p.M, k0, k_end, p.vecA, tid, p.a_kblk, p.a_kbs, 0, 1);
             if (p.transB)
-                stage_operand<true>(sb + p.off_b, p.b_plane, p.B, p.ldb, BN, n0, p.N, k0, k_end, p.vecB, tid);
+                stage_operand<true>(sb + p.off_b, p.b_plane, p.B, p.ldb, BN, n0, p.N, k0, k_end, p.vecB, tid, 1 << 30, 0, 0, 1);
             else
-                stage_operand<false>(sb + p.off_b, p.b_plane, p.B, p.ldb, BN, n0, p.N, k0, k_end, p.vecB, tid);
+                stage_operand<false>(sb + p.off_b, p.b_plane, p.B, p.ldb, BN, n0, p.N, k0, k_end, p.vecB, tid, p.b_kblk, 0, p.b_shi, p.b_slo);
             umma::fence_proxy_async();
             __syncthreads();
         }
@@ -260,14 +276,15 @@ extern "C" size_t cg_gemm_f32_workspace_bytes(int M, int N, int K) {
     return gemm_plan(M, N, K, sms).ws;
 }
 
-extern "C" int cg_gemm_f32(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda,
-                           int ldb, int ldc, const float *bias, int relu, void *workspace, size_t workspace_bytes,
-                           void *stream) {
+// C = op(A) op(B) with optional K blocking (see GemmParams); a_kblk <= 0 / b_kblk <= 0 mean "not blocked"
+int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda, int ldb,
+                int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi, int b_slo,
+                void *workspace, size_t workspace_bytes, cudaStream_t s) {
     CG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "cg_gemm_f32: negative dimension");
     if (M == 0 || N == 0) return CG_OK;
     CG_REQUIRE(A && B && C, "cg_gemm_f32: NULL matrix");
     CG_REQUIRE(K > 0, "cg_gemm_f32: K must be positive");
-    cudaStream_t s = (cudaStream_t)stream;
+    CG_REQUIRE(!(a_kblk > 0 && transA) && !(b_kblk > 0 && transB), "cg_gemm_f32: K blocking needs the untransposed operand");
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -291,7 +308,12 @@ extern "C" int cg_gemm_f32(const float *A, const float *B, float *C, int M, int 
     gp.BN = pl.BN;
     gp.split = pl.split;
     gp.k_per_split = pl.k_per_split;
-    gp.vecA = (lda % 4 == 0) && ((((uintptr_t)A) & 15) == 0);
+    gp.a_kblk = a_kblk > 0 ? a_kblk : (1 << 30);
+    gp.a_kbs = a_kblk > 0 ? a_kbs : 0;
+    gp.b_kblk = b_kblk > 0 ? b_kblk : (1 << 30);
+    gp.b_shi = b_kblk > 0 ? b_shi : 0;
+    gp.b_slo = b_kblk > 0 ? b_slo : 1;
+    gp.vecA = (lda % 4 == 0) && ((((uintptr_t)A) & 15) == 0) && (a_kblk <= 0 || (a_kblk % 8 == 0 && a_kbs % 4 == 0));
     gp.vecB = (ldb % 4 == 0) && ((((uintptr_t)B) & 15) == 0);
     CG_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     {
@@ -308,4 +330,13 @@ extern "C" int cg_gemm_f32(const float *A, const float *B, float *C, int M, int 
         CG_LAUNCH_CHECK();
     }
     return CG_OK;
+}
+
+size_t cg_gemm_workspace(int M, int N, int K) { return cg_gemm_f32_workspace_bytes(M, N, K); }
+
+extern "C" int cg_gemm_f32(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda,
+                           int ldb, int ldc, const float *bias, int relu, void *workspace, size_t workspace_bytes,
+                           void *stream) {
+    return cg_run_gemm(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, 0, 0, 0, 0, 0, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
 }

@@ -89,11 +89,12 @@ class GConvLSTMCell(object):
             H = self._num_units
             feat_in = int(inputs.shape[2])
             Wx, Wh, b = self._variables(K, feat_in, H)
-            # rows: all x features then all h features (fin-major); columns: z | i | f | o
-            W = torch.cat([torch.cat(Wx, dim=1), torch.cat(Wh, dim=1)], dim=0)
+            # the eight filters of the reference (lib/gconv_lstm.py:185-207) as two: columns z | i | f | o.
+            # x and h are filtered separately and summed, as in the reference; the hidden path then has a
+            # feature count (H) that the vectorised tensor-core kernels take, unlike [x | h] (Fin + H)
             bias = torch.cat(b, dim=0)
-            xh = torch.cat([inputs, h], dim=2)
-            pre = self.filter(xh, self._laplacian, self._lmax, 4 * H, K, W)
+            pre = (self.filter(inputs, self._laplacian, self._lmax, 4 * H, K, torch.cat(Wx, dim=1)) +
+                   self.filter(h, self._laplacian, self._lmax, 4 * H, K, torch.cat(Wh, dim=1)))
             new_h, new_c = ops.lstm_gates(pre, bias, c, self.gate_variant)
             if self._state_is_tuple:
                 new_state = LSTMStateTuple(new_c, new_h)

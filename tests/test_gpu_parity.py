@@ -338,6 +338,48 @@ def test_lstm_cell_step_vs_oracle(ops, tf_ref, c2, variant):
     assert state.h is new_h and cell.output_size == H and cell.state_size.c == (M, H)
 
 
+def test_c4_humanflow_shaped_cell_forward_backward(ops, tf_ref):
+    """Config C4: 32x32 8-NN grid (M = 1024, gconvTest.py:79), Fin = 2, H = 128, K = 3 -- the gate filters have
+    Fout = 4H = 512 and Fin in {2, 128}: the wide-output tensor-core contraction and its two backward GEMMs."""
+    from cnn_graph_b200.lib import graph
+    from oracle import graph_ref
+    A = graph_ref.adjacency(*graph_ref.distance_sklearn_metrics(graph_ref.grid(32), k=8, metric='euclidean'))
+    L = graph_ref.laplacian(A, normalized=True)
+    M, N, Fin, H, K = 1024, 3, 2, 128, 3
+    assert L.shape == (M, M)
+    rng = np.random.RandomState(11)
+    x = rng.uniform(0, 1, (N, M, Fin)).astype(np.float32)
+    h = (0.3 * rng.standard_normal((N, M, H))).astype(np.float32)
+    c = (0.3 * rng.standard_normal((N, M, H))).astype(np.float32)
+    Wx = rng.uniform(-0.1, 0.1, (Fin * K, 4 * H)).astype(np.float32)
+    Wh = rng.uniform(-0.1, 0.1, (H * K, 4 * H)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, 4 * H).astype(np.float32)
+    gh = rng.standard_normal((N, M, H)).astype(np.float32)
+    xt, ht, Wxt, Wht = (dev(a).requires_grad_(True) for a in (x, h, Wx, Wh))
+    px = ops.cheb_filter(xt, Wxt, L, K)
+    ph = ops.cheb_filter(ht, Wht, L, K)
+    close(px, tf_ref.chebyshev5(x, L, Wx, K))
+    close(ph, tf_ref.chebyshev5(h, L, Wh, K))
+    new_h, new_c = ops.lstm_gates(px + ph, dev(b), dev(c), 'standard')
+    sl = {g: slice(i * H, (i + 1) * H) for i, g in enumerate('zifo')}
+    ref_h, ref_c = tf_ref.gconv_lstm_step(x, c, h, L, 2, K, {g: Wx[:, s] for g, s in sl.items()},
+                                          {g: Wh[:, s] for g, s in sl.items()}, {g: b[s] for g, s in sl.items()},
+                                          'standard')
+    close(new_c, ref_c)
+    close(new_h, ref_h)
+    # backward of the two filters against the oracle's adjoint, seeded with the gate gradient the GPU produced
+    new_h.backward(dev(gh))
+    pre = (px + ph).detach().requires_grad_(True)
+    ops.lstm_gates(pre, dev(b), dev(c), 'standard')[0].backward(dev(gh))
+    g = pre.grad.cpu().numpy()
+    dx, dWx = tf_ref.chebyshev5_backward(x, L, Wx, K, g)
+    dh, dWh = tf_ref.chebyshev5_backward(h, L, Wh, K, g)
+    close(xt.grad, dx)
+    close(ht.grad, dh)
+    close(Wxt.grad, dWx)
+    close(Wht.grad, dWh)
+
+
 @pytest.mark.parametrize('variant', ['fork', 'standard'])
 def test_lstm_gates_gradients_vs_torch(ops, variant):
     torch.manual_seed(2)
