@@ -141,6 +141,15 @@ int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, i
                 int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi, int b_slo,
                 void *workspace, size_t workspace_bytes, cudaStream_t s);
 
+// Pipelined fast path of the same GEMM (cg_gemm_pipe.cu): 16-byte aligned operands, power-of-two K blocks
+bool cg_gemm_pipe_eligible(const float *A, const float *B, int M, int N, int K, int lda, int ldb, int transA, int transB,
+                           int a_kblk, long long a_kbs, int b_kblk);
+size_t cg_gemm_pipe_workspace(int M, int N, int K, int sm_count);
+int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda,
+                     int ldb, int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi,
+                     int b_slo, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s);
+int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s);
+
 // Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,

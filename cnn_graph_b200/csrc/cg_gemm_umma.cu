@@ -273,7 +273,16 @@ extern "C" size_t cg_gemm_f32_workspace_bytes(int M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return gemm_plan(M, N, K, sms).ws;
+    return std::max(gemm_plan(M, N, K, sms).ws, cg_gemm_pipe_workspace(M, N, K, sms));
+}
+
+int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s) {
+    CgProfScope prof("gemm_reduce", s);
+    const size_t total = (size_t)M * N;
+    k_gemm_reduce<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(part, bias, C, M, N, ldc, split,
+                                                                                            relu ? 1 : 0);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
 }
 
 // C = op(A) op(B) with optional K blocking (see GemmParams); a_kblk <= 0 / b_kblk <= 0 mean "not blocked"
@@ -288,6 +297,9 @@ int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, i
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cg_gemm_pipe_eligible(A, B, M, N, K, lda, ldb, transA, transB, a_kblk, a_kbs, b_kblk))
+        return cg_run_gemm_pipe(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, a_kblk, a_kbs, b_kblk, b_shi,
+                                b_slo, workspace, workspace_bytes, sms, s);
     GPlan pl = gemm_plan(M, N, K, sms);
     CG_REQUIRE(pl.ws == 0 || (workspace && workspace_bytes >= pl.ws), "cg_gemm_f32: workspace too small (%zu < %zu bytes)",
                workspace_bytes, pl.ws);
@@ -322,13 +334,8 @@ int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, i
         k_gemm_umma<<<grid, GT, pl.smem, s>>>(gp);
         CG_LAUNCH_CHECK();
     }
-    if (pl.split > 1) {
-        CgProfScope prof("gemm_reduce", s);
-        const size_t total = (size_t)M * N;
-        k_gemm_reduce<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(
-            reinterpret_cast<const float *>(workspace), bias, C, M, N, ldc, pl.split, relu ? 1 : 0);
-        CG_LAUNCH_CHECK();
-    }
+    if (pl.split > 1)
+        return cg_gemm_reduce(reinterpret_cast<const float *>(workspace), bias, C, M, N, ldc, pl.split, relu, s);
     return CG_OK;
 }
 

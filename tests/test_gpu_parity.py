@@ -675,7 +675,11 @@ def test_c3_20news_shaped_config(ops, tf_ref):
 
 
 # --------------------------------------------------------------------------- dense head GEMM
-@pytest.mark.parametrize('M,N,K', [(1024, 512, 3968), (100, 10, 512), (7, 300, 65), (129, 257, 64), (256, 256, 1000)])
+@pytest.mark.parametrize('M,N,K', [(1024, 512, 3968), (100, 10, 512), (7, 300, 65), (129, 257, 64), (256, 256, 1000),
+                                   # 16-byte aligned leading dimensions: the pipelined kernel (ragged M/N/K tails, every BN,
+                                   # several work items per CTA, split-K)
+                                   (132, 260, 68), (20000, 512, 384), (4, 12, 4), (384, 512, 5120), (1000, 36, 200),
+                                   (300, 100, 36), (2560, 128, 1536)])
 @pytest.mark.parametrize('transA,transB', [(False, False), (False, True), (True, False), (True, True)])
 def test_gemm_f32_tensor_core(ops, M, N, K, transA, transB):
     """cg_gemm_f32 against float64 matmul: fp32-level accuracy (bf16 hi+mid split, fp32 accumulation), all four
