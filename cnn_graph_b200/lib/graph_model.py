@@ -52,7 +52,7 @@ class GraphModel(object):
 
     def _make_optimizer(self):
         # lib/graph_model.py:293 -- the fork trains with Adam at the (decayed) learning rate
-        return torch.optim.Adam(self.store.parameters(), lr=self.learning_rate)
+        return torch.optim.Adam(self.store.parameters(), lr=self.learning_rate, capturable=torch.cuda.is_available())
 
     def _current_lr(self):
         # tf.train.exponential_decay(..., staircase=True), lib/graph_model.py:282-284
@@ -119,6 +119,74 @@ class GraphModel(object):
         self.is_train = False
         return loss
 
+    # ------------------------------------------------------------------ captured step / pipelined feeding
+    def train_step_graphed(self, batch_data, batch_labels):
+        """``train_step`` replayed from a CUDA graph (one launch per step instead of ~80): the step is captured on
+        first use -- after three eager warm-up steps, which also build the packed operators -- and re-captured when
+        the staircase learning rate or the batch shape changes.  The batch is copied into the graph's static
+        input buffers; the returned loss tensor is overwritten by the next replay."""
+        lr = self._current_lr()
+        key = (tuple(batch_data.shape), batch_data.dtype, tuple(batch_labels.shape), batch_labels.dtype, lr)
+        cap = getattr(self, '_captured', None)
+        if cap is None or cap['key'] != key:
+            cap = self._capture_step(batch_data, batch_labels, key)
+        if batch_data.data_ptr() != cap['x'].data_ptr():
+            cap['x'].copy_(batch_data, non_blocking=True)
+        if batch_labels.data_ptr() != cap['y'].data_ptr():
+            cap['y'].copy_(batch_labels, non_blocking=True)
+        cap['graph'].replay()
+        self.global_step += 1
+        return cap['loss']
+
+    def _capture_step(self, batch_data, batch_labels, key):
+        from .. import _native
+        x, y = batch_data.clone(), batch_labels.clone()
+        # warm-up (allocator, packed operators, optimiser state) must not advance the training: snapshot, restore
+        params = list(self.store.parameters())
+        step0 = self.global_step
+        snap_p = [q.detach().clone() for q in params]
+        snap_s = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state.get(q, {}).items()}
+                  for q in params]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.train_step(x, y)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for q, old_p, old_s in zip(params, snap_p, snap_s):
+                q.copy_(old_p)
+                state = self.optimizer.state.get(q, {})
+                for k in list(state.keys()):
+                    v = state[k]
+                    if torch.is_tensor(v):
+                        if k in old_s and old_s[k] is not None:
+                            v.copy_(old_s[k])
+                        else:
+                            v.zero_()           # created by the warm-up: back to its initial value
+                    elif k in old_s:
+                        state[k] = old_s[k]
+        self.global_step = step0
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _native.lib().cg_launch_count()
+        with torch.cuda.graph(graph):
+            loss = self.train_step(x, y)
+        self.global_step = step0            # the capture itself runs nothing
+        self._captured = {'key': key, 'graph': graph, 'x': x, 'y': y, 'loss': loss,
+                          'native_launches': int(_native.lib().cg_launch_count() - n0)}
+        return self._captured
+
+    def graphed_native_launches(self):
+        """Native (this library's) kernel launches inside one captured step; 0 before the first capture."""
+        cap = getattr(self, '_captured', None)
+        return cap['native_launches'] if cap else 0
+
+    def pipelined_trainer(self, perm=None, depth=2, use_graph=True):
+        """Feeder for training from pinned host batches: see ``PipelinedTrainer``."""
+        return PipelinedTrainer(self, perm=perm, depth=depth, use_graph=use_graph)
+
     def fit(self, train_data, train_labels, val_data, val_labels):
         """Mini-batch training loop (reference lib/graph_model.py:124-197).  Returns
         (validation scores, validation losses, seconds per step)."""
@@ -181,3 +249,77 @@ class GraphModel(object):
         if sess is None:
             string += '\ntime: {:.0f}s (wall {:.0f}s)'.format(time.process_time() - t_process, time.time() - t_wall)
         return string, mse, 0, loss, predictions
+
+
+class PipelinedTrainer(object):
+    """Training from HOST batches with the copies off the critical path.
+
+    ``submit(x_host, y_host)`` (pinned tensors; ``x_host`` is the raw [N, M0] signal when ``perm`` is given, as
+    the reference feeds ``coarsening.perm_data(X, perm)``, lib/coarsening.py:219) enqueues
+      copy stream:     H2D of the batch into one of ``depth`` device buffers (waits until the step that last used
+                       the buffer has consumed it)
+      compute stream:  wait for the copy, ``cg_perm_data`` into the step's input, the training step (CUDA graph
+                       replay, or eager), an asynchronous D2H copy of the loss into a pinned slot
+    and returns at once; the host blocks only when all ``depth`` slots are in flight.  ``drain()`` waits for
+    everything and returns the losses in submission order.  The reference round-trips every step through
+    ``feed_dict`` and fetches every tensor back (lib/graph_model.py:142-163)."""
+
+    def __init__(self, model, perm=None, depth=2, use_graph=True):
+        self.model, self.depth, self.use_graph = model, int(depth), bool(use_graph)
+        self.device = model.device
+        self.perm = None if perm is None else torch.as_tensor(np.asarray(perm, dtype=np.int32), device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.raw, self.lab, self.x, self.y = [None] * self.depth, [None] * self.depth, None, None
+        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
+        self.loss_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.loss_host = torch.zeros(self.depth, dtype=torch.float32).pin_memory()
+        self.count, self.losses = 0, []
+        self.h2d_bytes_per_step = 0
+
+    def _collect(self, slot):
+        self.loss_done[slot].synchronize()
+        self.losses.append(float(self.loss_host[slot]))
+
+    def submit(self, x_host, y_host):
+        from .. import ops
+        i, b = self.count, self.count % self.depth
+        if i >= self.depth:
+            self._collect(b)                      # bounds the run-ahead; frees the pinned loss slot
+        if self.raw[b] is None:
+            self.raw[b] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
+            self.lab[b] = torch.empty(y_host.shape, dtype=y_host.dtype, device=self.device)
+        self.h2d_bytes_per_step = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if i >= self.depth:
+                self.copy_stream.wait_event(self.consumed[b])
+            self.raw[b].copy_(x_host, non_blocking=True)
+            self.lab[b].copy_(y_host, non_blocking=True)
+            self.copied[b].record(self.copy_stream)
+        cur.wait_event(self.copied[b])
+        if self.perm is not None:
+            if self.x is None:
+                self.x = torch.empty((x_host.shape[0], self.perm.numel()), dtype=torch.float32, device=self.device)
+            ops.perm_data_device(self.raw[b], None, out=self.x, perm_t=self.perm)
+        else:
+            if self.x is None:
+                self.x = torch.empty_like(self.raw[b])
+            self.x.copy_(self.raw[b], non_blocking=True)
+        if self.y is None:
+            self.y = torch.empty_like(self.lab[b])
+        self.y.copy_(self.lab[b], non_blocking=True)
+        self.consumed[b].record(cur)
+        step = self.model.train_step_graphed if self.use_graph else self.model.train_step
+        loss = step(self.x, self.y)
+        self.loss_host[b:b + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.loss_done[b].record(cur)
+        self.count += 1
+
+    def drain(self):
+        first = max(0, self.count - self.depth)
+        for i in range(first, self.count):
+            self._collect(i % self.depth)
+        out, self.losses = self.losses, []
+        self.count = 0
+        return out

@@ -439,13 +439,18 @@ def linear(x, W, b=None, relu=False):
 # perm_data on the device
 # ---------------------------------------------------------------------------------------
 
-def perm_data_device(x, perm):
-    """out[:, i] = x[:, perm[i]] if perm[i] < M else 0  (lib/coarsening.py:219-240), float32."""
+def perm_data_device(x, perm, out=None, perm_t=None):
+    """out[:, i] = x[:, perm[i]] if perm[i] < M else 0  (lib/coarsening.py:219-240), float32.
+    ``perm_t`` (int32 device tensor) skips the upload of ``perm``; ``out`` is written in place when given."""
     _require_cuda(x)
     x = _f32c(x)
     N, M = x.shape
-    perm_t = torch.as_tensor(np.asarray(perm, dtype=np.int32), device=x.device)
-    out = torch.empty((N, perm_t.numel()), dtype=torch.float32, device=x.device)
+    if perm_t is None:
+        perm_t = torch.as_tensor(np.asarray(perm, dtype=np.int32), device=x.device)
+    if out is None:
+        out = torch.empty((N, perm_t.numel()), dtype=torch.float32, device=x.device)
+    elif out.shape != (N, perm_t.numel()) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError('perm_data_device: out must be a contiguous float32 [N, len(perm)] tensor')
     check(_native.lib().cg_perm_data(ptr(x), ptr(perm_t), ptr(out), N, M, perm_t.numel(), _stream()), 'cg_perm_data')
     return out
 

@@ -709,3 +709,58 @@ def test_linear_layer_gradients(ops):
     close(x.grad, xd.grad.cpu().numpy())
     close(W.grad, Wd.grad.cpu().numpy())
     close(b.grad, bd.grad.cpu().numpy())
+
+
+# --------------------------------------------------------------------------- captured step / pipelined feeder
+def _small_cgcnn(c2, seed):
+    from cnn_graph_b200.lib import models
+    L = [csr_from(c2, 'L%d' % i) for i in range(5)]
+    torch.manual_seed(seed)
+    return models.cgcnn(L, F=[8, 16], K=[5, 4], p=[4, 4], M=[32, 10], batch_size=16, dropout=1, learning_rate=0.05,
+                        decay_rate=0.9, decay_steps=3, momentum=0.9, regularization=1e-3)
+
+
+def test_graphed_step_matches_eager_steps(ops, c2):
+    """train_step_graphed (CUDA-graph replay; re-captured when the staircase learning rate changes) walks the same
+    trajectory as eager train_step on the same batches."""
+    rng = np.random.RandomState(3)
+    M = csr_from(c2, 'L0').shape[0]
+    batches = [(dev(rng.rand(16, M).astype(np.float32)), torch.from_numpy(rng.randint(0, 10, 16)).cuda())
+               for _ in range(6)]
+    a, b = _small_cgcnn(c2, 7), _small_cgcnn(c2, 7)
+    for pa, pb in zip(a.store.parameters(), b.store.parameters()):
+        pb.data.copy_(pa.data)
+    for x, y in batches:                    # decay_steps = 3: the fourth step re-captures with the decayed rate
+        la = a.train_step(x, y)
+        lb = b.train_step_graphed(x, y).clone()
+        close(lb, la.detach().cpu().numpy(), 2e-4)
+    assert a.global_step == b.global_step == len(batches)
+    assert b.graphed_native_launches() > 0
+    for pa, pb in zip(a.store.parameters(), b.store.parameters()):
+        close(pb, pa.detach().cpu().numpy(), 1e-3)
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_pipelined_trainer_matches_direct_steps(ops, c2, use_graph):
+    """PipelinedTrainer (H2D on a copy stream, lagged loss read-back) returns the losses of the same steps driven
+    one by one from device tensors, in order."""
+    from cnn_graph_b200.lib import coarsening
+    rng = np.random.RandomState(5)
+    perm = [int(v) for v in c2['perm']]
+    raw = [torch.from_numpy(rng.rand(16, 784).astype(np.float32)).pin_memory() for _ in range(5)]
+    lab = [torch.from_numpy(rng.randint(0, 10, 16)).pin_memory() for _ in range(5)]
+    a, b = _small_cgcnn(c2, 11), _small_cgcnn(c2, 11)
+    for pa, pb in zip(a.store.parameters(), b.store.parameters()):
+        pb.data.copy_(pa.data)
+    step = a.train_step_graphed if use_graph else a.train_step
+    want = []
+    for x, y in zip(raw, lab):
+        xd = dev(coarsening.perm_data(x.numpy(), perm).astype(np.float32))
+        want.append(float(step(xd, y.cuda())))
+    tr = b.pipelined_trainer(perm=perm, depth=2, use_graph=use_graph)
+    for x, y in zip(raw, lab):
+        tr.submit(x, y)
+    got = tr.drain()
+    assert len(got) == len(want)
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-6)
+    assert tr.h2d_bytes_per_step == 16 * 784 * 4 + 16 * 8
