@@ -296,6 +296,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     cgdist.barrier()
     ms_e2e = cgdist.max_over_ranks(e0.elapsed_time(e1), device)
+    h2d_bytes = int(trainer.h2d_bytes_per_step)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     # per-kernel device time of the same step, CUDA events on the launch stream (profiling pass)
@@ -360,6 +361,13 @@ def run_ours(args):
                                 'note': 'algorithmic bytes of an unfused CSR recurrence (SURVEY 8d B_stream); the fused '
                                         'kernels keep the slabs in shared memory, their DRAM traffic is in `traffic`'}
 
+    # captured graphs hold NCCL work: release them before the process group goes away
+    trainer = None
+    model._captured = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    cgdist.barrier()
     if rank != 0:
         return
     cpu = None
@@ -382,7 +390,7 @@ def run_ours(args):
                                'cg_perm_data -> training step -> loss D2H; K steps in one event pair, no L2 flush '
                                '(inputs come from the host every step)'},
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': int(trainer.h2d_bytes_per_step),
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'roofline': roof, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernel_ms,
@@ -391,15 +399,22 @@ def run_ours(args):
 
 
 def _shutdown():
+    """Leave without the blocking NCCL teardown: destroy_process_group() was seen to hang after graph-captured
+    collectives; every rank has passed the final barrier and printed by now."""
     try:
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
     except Exception:
         pass
 
 
 def main():
+    if os.environ.get('CG_BENCH_WATCHDOG'):      # debugging aid: dump every thread's stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['CG_BENCH_WATCHDOG']), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

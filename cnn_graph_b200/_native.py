@@ -37,6 +37,7 @@ _SIGNATURES = {
     'cg_cheb_filter_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     'cg_cheb_filter_stack_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    'cg_cheb_filter_stack_planes': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     'cg_cheb_filter_fwd_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_size_t, c_int, c_void_p]),
     'cg_cheb_filter_bwd_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

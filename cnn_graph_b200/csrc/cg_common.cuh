@@ -125,8 +125,16 @@ int cg_pack_w(const float *W, unsigned char *wp, int Q, int Nn, int K, bool tran
 bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K);
 size_t cg_fused_workspace(int Fin, int Fout, int K);
 //   stack_out (optional): the basis X_k, [K][N][M][Fin] (sample-major), for a later weight gradient.
+//   stack_planes: stack_out receives the staged bf16 hi | mid planes instead ([2][K][Fin/8][N*M][8], same byte size),
+//   the input format of cg_run_dw_planes.
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
-                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s);
+                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s, bool stack_planes = false);
+
+// Weight gradient straight from that plane image (cg_dw_planes.cu): no conversion on the stack side.
+bool cg_dw_planes_supported(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+size_t cg_dw_planes_workspace(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+int cg_run_dw_planes(const void *planes, const float *T, float *dW, long long R, int Fa, int Fb, int K, float *workspace,
+                     int sm_count, size_t smem_limit, cudaStream_t s);
 
 // Tensor-core contraction of a sample-major basis that lives in HBM (cg_contract_umma.cu).
 bool cg_contract_umma_supported(int N, int M, int Fa, int J, int K, size_t smem_limit);

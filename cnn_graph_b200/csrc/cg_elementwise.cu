@@ -273,10 +273,12 @@ extern "C" int cg_pool_bwd(const float *gy, const uint8_t *amax, float *gx, int 
 //   avg pooling : aux = bit q set when activated element q is > 0 (relu) -- the relu mask
 // VEC features per thread (4 when F % 4 == 0).
 // ---------------------------------------------------------------------------
-template <int VEC>
+// P > 0: pool size known at compile time (the q loops unroll and all loads of a thread are issued together)
+template <int VEC, int P>
 __global__ void __launch_bounds__(256)
 k_bias_act_pool_fwd(const float *__restrict__ x, const float *__restrict__ bias, float *__restrict__ y,
-                    uint8_t *__restrict__ aux, int64_t NJ, int Mp, int F, int p, int bias_kind, int act, int kind) {
+                    uint8_t *__restrict__ aux, int64_t NJ, int Mp, int F, int p_rt, int bias_kind, int act, int kind) {
+    const int p = P > 0 ? P : p_rt;
     const int FV = F / VEC;
     const int64_t total = NJ * FV;
     const float inv = 1.0f / (float)p;
@@ -289,10 +291,11 @@ k_bias_act_pool_fwd(const float *__restrict__ x, const float *__restrict__ bias,
         int arg[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { best[e] = 0.f; sum[e] = 0.f; arg[e] = 0; }
+#pragma unroll
         for (int q = 0; q < p; ++q) {
             float v[VEC];
             if (VEC == 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(src + (int64_t)q * F);
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(src + (int64_t)q * F));
                 v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
             } else {
                 v[0] = src[(int64_t)q * F];
@@ -311,21 +314,31 @@ k_bias_act_pool_fwd(const float *__restrict__ x, const float *__restrict__ bias,
                 }
             }
         }
+        if (VEC == 4) {      // F % 4 == 0: 16-byte aligned pooled row piece, 4-byte aligned aux piece
+            float o[4];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            y[nj * F + f + e] = kind == 1 ? best[e] : sum[e] * inv;
-            aux[nj * F + f + e] = (uint8_t)arg[e];
+            for (int e = 0; e < 4; ++e) o[e] = kind == 1 ? best[e % VEC] : sum[e % VEC] * inv;
+            *reinterpret_cast<float4 *>(y + nj * F + f) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uchar4 *>(aux + nj * F + f) =
+                make_uchar4((uint8_t)arg[0], (uint8_t)arg[1 % VEC], (uint8_t)arg[2 % VEC], (uint8_t)arg[3 % VEC]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                y[nj * F + f + e] = kind == 1 ? best[e] : sum[e] * inv;
+                aux[nj * F + f + e] = (uint8_t)arg[e];
+            }
         }
     }
 }
 
 // gx[n, j*p+q, f] from the pooled gradient; db (optional) accumulates the bias gradient per thread and is
 // flushed with one atomicAdd per (thread, feature[, vertex]).
-template <int VEC>
+template <int VEC, int P>
 __global__ void __launch_bounds__(256)
 k_bias_act_pool_bwd(const float *__restrict__ gy, const float *__restrict__ yp, const uint8_t *__restrict__ aux,
-                    float *__restrict__ gx, float *__restrict__ dbias, int64_t NJ, int Mp, int F, int p, int bias_kind,
+                    float *__restrict__ gx, float *__restrict__ dbias, int64_t NJ, int Mp, int F, int p_rt, int bias_kind,
                     int act, int kind) {
+    const int p = P > 0 ? P : p_rt;
     const int FV = F / VEC;
     const int64_t total = NJ * FV;
     const float inv = 1.0f / (float)p;
@@ -342,14 +355,26 @@ k_bias_act_pool_bwd(const float *__restrict__ gy, const float *__restrict__ yp, 
         float *dst = gx + nj * p * F + f;
         float g[VEC];
         int a[VEC];
+        float go[VEC], yo[VEC];
+        if (VEC == 4) {
+            const float4 g4 = __ldcs(reinterpret_cast<const float4 *>(gy + nj * F + f));
+            const float4 y4 = __ldcs(reinterpret_cast<const float4 *>(yp + nj * F + f));
+            const uchar4 a4 = *reinterpret_cast<const uchar4 *>(aux + nj * F + f);
+            go[0] = g4.x; go[1 % VEC] = g4.y; go[2 % VEC] = g4.z; go[3 % VEC] = g4.w;
+            yo[0] = y4.x; yo[1 % VEC] = y4.y; yo[2 % VEC] = y4.z; yo[3 % VEC] = y4.w;
+            a[0] = a4.x; a[1 % VEC] = a4.y; a[2 % VEC] = a4.z; a[3 % VEC] = a4.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const float go = gy[nj * F + f + e];
-            const float yo = yp[nj * F + f + e];
-            a[e] = aux[nj * F + f + e];
-            // max: the routed element's activation derivative comes from the pooled value itself
-            g[e] = kind == 1 ? act_bwd_from_out(yo, go, act) : go * inv;
+            for (int e = 0; e < VEC; ++e) {
+                go[e] = gy[nj * F + f + e];
+                yo[e] = yp[nj * F + f + e];
+                a[e] = aux[nj * F + f + e];
+            }
         }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)   // max: the routed element's activation derivative comes from the pooled value itself
+            g[e] = kind == 1 ? act_bwd_from_out(yo[e], go[e], act) : go[e] * inv;
+#pragma unroll
         for (int q = 0; q < p; ++q) {
             float o[VEC];
 #pragma unroll
@@ -361,7 +386,7 @@ k_bias_act_pool_bwd(const float *__restrict__ gy, const float *__restrict__ yp, 
                     atomicAdd(dbias + ((int64_t)j * p + q) * F + f + e, o[e]);
             }
             if (VEC == 4) {
-                *reinterpret_cast<float4 *>(dst + (int64_t)q * F) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+                __stcs(reinterpret_cast<float4 *>(dst + (int64_t)q * F), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
             } else {
                 dst[(int64_t)q * F] = o[0];
             }
@@ -422,12 +447,16 @@ extern "C" int cg_bias_act_pool_fwd(const float *x, const float *bias, float *y,
     if (NJ == 0) return CG_OK;
     CG_REQUIRE(x && y && aux && (bias_kind == 0 || bias), "cg_bias_act_pool_fwd: NULL tensor");
     cudaStream_t s = (cudaStream_t)stream;
-    const bool v4 = F % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+    const bool v4 = F % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (((uintptr_t)aux) & 3) == 0;
     CgProfScope prof("bias_act_pool_fwd", s);
-    if (v4)
-        k_bias_act_pool_fwd<4><<<grid_for(NJ * (F / 4), 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+    if (v4 && p == 4)
+        k_bias_act_pool_fwd<4, 4><<<grid_for(NJ * (F / 4), 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+    else if (v4 && p == 2)
+        k_bias_act_pool_fwd<4, 2><<<grid_for(NJ * (F / 4), 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+    else if (v4)
+        k_bias_act_pool_fwd<4, 0><<<grid_for(NJ * (F / 4), 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
     else
-        k_bias_act_pool_fwd<1><<<grid_for(NJ * F, 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
+        k_bias_act_pool_fwd<1, 0><<<grid_for(NJ * F, 256), 256, 0, s>>>(x, bias, y, aux, NJ, M / p, F, p, bias_kind, act, kind);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
@@ -442,14 +471,20 @@ extern "C" int cg_bias_act_pool_bwd(const float *gy, const float *y, const uint8
     if (dbias) CG_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)(bias_kind == 1 ? F : (int64_t)M * F), s));
     if (NJ == 0) return CG_OK;
     CG_REQUIRE(gy && y && aux && gx, "cg_bias_act_pool_bwd: NULL tensor");
-    const bool v4 = F % 4 == 0 && ((((uintptr_t)gx)) & 15) == 0;
+    const bool v4 = F % 4 == 0 && ((((uintptr_t)gx) | ((uintptr_t)gy) | ((uintptr_t)y)) & 15) == 0 && (((uintptr_t)aux) & 3) == 0;
     CgProfScope prof("bias_act_pool_bwd", s);
-    if (v4)
-        k_bias_act_pool_bwd<4><<<fused_pool_grid(NJ * (F / 4), F / 4), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
-                                                                                    bias_kind, act, kind);
+    if (v4 && p == 4)
+        k_bias_act_pool_bwd<4, 4><<<fused_pool_grid(NJ * (F / 4), F / 4), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                                       bias_kind, act, kind);
+    else if (v4 && p == 2)
+        k_bias_act_pool_bwd<4, 2><<<fused_pool_grid(NJ * (F / 4), F / 4), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                                       bias_kind, act, kind);
+    else if (v4)
+        k_bias_act_pool_bwd<4, 0><<<fused_pool_grid(NJ * (F / 4), F / 4), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                                       bias_kind, act, kind);
     else
-        k_bias_act_pool_bwd<1><<<fused_pool_grid(NJ * F, F), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
-                                                                          bias_kind, act, kind);
+        k_bias_act_pool_bwd<1, 0><<<fused_pool_grid(NJ * F, F), 256, 0, s>>>(gy, y, aux, gx, dbias, NJ, M / p, F, p,
+                                                                             bias_kind, act, kind);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

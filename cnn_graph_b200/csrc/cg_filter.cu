@@ -29,7 +29,8 @@ static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const size_t b = cg_dw_umma_workspace(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
     const int64_t R = (int64_t)N * g->M;
     const size_t c = R < (int64_t)INT32_MAX ? cg_gemm_workspace(Fa, Fb, (int)R) : 0;       // per-k GEMM, split over R
-    return std::max(a, std::max(b, c));
+    const size_t d = cg_dw_planes_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
+    return std::max(std::max(a, d), std::max(b, c));
 }
 
 static int run_dw(const cg_graph *g, const float *stack, const float *T, float *dW, int N, int Fa, int Fb, int K,
@@ -113,6 +114,19 @@ static bool can_save_stack(const cg_graph *g, int N, int Fin, int Fout, int K, i
     return cg_basis_samples_supported(g, 0, N, Fin);
 }
 
+// The saved basis can be the fused kernel's own bf16 operand planes (CG_FILTER_STACK_PLANES) when the fused
+// forward kernel runs and the plane-streaming dW kernel takes the shape.
+static bool planes_ok(const cg_graph *g, int N, int Fin, int Fout, int K, int flags) {
+    if (N <= 0 || K < 2 || (flags & (CG_FILTER_FORCE_STREAMING | CG_FILTER_NO_FUSED))) return false;
+    return Fin % 8 == 0 && cg_fused_supported(g, 0, N, Fin, Fout, K) &&
+           cg_dw_planes_supported((long long)N * g->M, Fin, Fout, K, g->sm_count, g->smem_optin);
+}
+
+extern "C" int cg_cheb_filter_stack_planes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
+    if (!g || Fin <= 0 || Fout <= 0 || K < 1) return 0;
+    return planes_ok(g, N, Fin, Fout, K, flags) ? 1 : 0;
+}
+
 extern "C" size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
     if (!g || Fin <= 0 || Fout <= 0 || K < 1) return 0;
     return can_save_stack(g, N, Fin, Fout, K, flags) ? sizeof(float) * (size_t)K * N * g->M * Fin : 0;
@@ -146,9 +160,12 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
         CG_REQUIRE(!(flags & CG_FILTER_FORCE_FUSED), "cg_cheb_filter_fwd: fused kernel needs 16-byte aligned tensors");
         fused = false;
     }
+    const bool planes = stack_out != nullptr && (flags & CG_FILTER_STACK_PLANES);
+    CG_REQUIRE(!planes || (fused && planes_ok(g, N, Fin, Fout, K, flags)),
+               "cg_cheb_filter_fwd_ex: CG_FILTER_STACK_PLANES needs cg_cheb_filter_stack_planes() == 1 and aligned tensors");
     if (fused) {
         void *wpack = reinterpret_cast<char *>(workspace) + (need - cg_fused_workspace(Fin, Fout, K));
-        return cg_run_fused(g, 0, x, W, y, stack_out, N, Fin, Fout, K, false, wpack, s);
+        return cg_run_fused(g, 0, x, W, y, stack_out, N, Fin, Fout, K, false, wpack, s, planes);
     }
     if (K == 1)   // y = x W: a per-vertex linear map (lib/models.py:205-206 with no SpMM)
         return cg_run_contract(x, W, y, 1, N * M, Fin, Fout, 1, false, false, s);
@@ -209,7 +226,13 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
         // dW[fin*K+k, fo] = sum_{n,m} X_k[n,m,fin] gy[n,m,fo] straight from the basis the forward pass left behind
         CG_REQUIRE(can_save_stack(g, N, Fin, Fout, K, flags), "cg_cheb_filter_bwd_ex: saved stack given for a shape that cannot save one");
         float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fin, K));
-        rc = run_dw(g, saved_stack, gy, dW, N, Fin, Fout, K, false, true, part, flags, s);
+        if (flags & CG_FILTER_STACK_PLANES) {
+            CG_REQUIRE(planes_ok(g, N, Fin, Fout, K, flags) && (((uintptr_t)gy) & 15) == 0,
+                       "cg_cheb_filter_bwd_ex: CG_FILTER_STACK_PLANES given for a shape without plane support");
+            rc = cg_run_dw_planes(saved_stack, gy, dW, (long long)N * M, Fin, Fout, K, part, g->sm_count, g->smem_optin, s);
+        } else {
+            rc = run_dw(g, saved_stack, gy, dW, N, Fin, Fout, K, false, true, part, flags, s);
+        }
         if (rc != CG_OK) return rc;
         have_dW = true;
     }

@@ -38,6 +38,9 @@ struct FusedParams {
     const unsigned char *wp;     // packed W: [K][hi|mid][Fin*Fout] bf16, canonical K-major B operand
     float *y;                    // [N][M][Fout]
     float *stack_out;            // optional: X_k for the weight gradient, [K][N][M][Fin] (sample-major)
+    unsigned char *planes_out;   // optional, instead of stack_out: the staged bf16 hi | mid planes themselves,
+                                 // [2][K][Fin/8][N*M rows][8 features] (cg_dw_planes.cu reads them without conversion)
+    long long planes_kf, planes_pl;     // bytes between (k, feature octet) runs / between the hi and mid halves
     long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][8]
     int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab, nw, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
@@ -53,7 +56,8 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
     uint64_t *xbar = bars;            // [2] x slab of a group landed
     uint64_t *wbar = bars + 2;        // [2] W_k landed
     uint64_t *mbar = bars + 4;        // MMAs of the last issued step completed
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+    uint64_t *sbar = bars + 5;        // staging planes free again (MMAs done and, with planes_out, bulk stores read)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
         for (int i = tid; i < n16; i += FT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) umma::mbar_init(bars + i, 1);
+        for (int i = 0; i < 6; ++i) umma::mbar_init(bars + i, 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -186,6 +190,17 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                     wpar ^= 1u << b;
                     umma::fence_after_sync();
                     if (tr) p.trace[k * 8 + 5] = clock64();
+                    if (p.planes_out != nullptr) {
+                        // the staged planes are, per feature octet, one contiguous run over the group's rows in the
+                        // MN-major core-matrix order the weight-gradient kernel wants: ship them as they are
+                        const uint32_t run = (uint32_t)Rg * 16u;
+                        for (int fo = 0; fo < Fin / 8; ++fo) {
+                            unsigned char *dst = p.planes_out + ((size_t)k * (Fin / 8) + fo) * p.planes_kf + (size_t)n0 * M * 16;
+                            bulk_s2g(dst, a0 + (uint32_t)fo * p.lbo_a, run);
+                            bulk_s2g(dst + p.planes_pl, a0 + p.plane_bytes + (uint32_t)fo * p.lbo_a, run);
+                        }
+                        bulk_commit();
+                    }
                     const uint32_t wb = w0 + (uint32_t)b * wbytes;
                     // descriptors advance by plain adds on the low word (units of 16 bytes)
                     const uint32_t a_lo = umma::desc_lo(a0, p.lbo_a), b_lo = umma::desc_lo(wb, lbo_w);
@@ -210,6 +225,8 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                     // W_{k+nw} goes where W_k was, once the MMAs of step k have read it; waiting for every
                     // step also guarantees that nothing is in flight when the group ends
                     umma::mbar_wait(mbar, mpar);
+                    if (p.planes_out != nullptr) bulk_wait_read();
+                    mbar_arrive(sbar);                      // compute warps may overwrite the planes
                     if (tr) p.trace[k * 8 + 7] = clock64();
                     if (k + p.nw < K) {
                         mbar_expect_tx(wbar + b, wbytes);
@@ -273,9 +290,9 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                         if (a_soff[i0] < limb) sts128(cur + a_soff[i0], acc0);
                         if (a_soff[i1] < limb) sts128(cur + a_soff[i1], acc1);
                     }
-                    // the staging planes are free once the MMAs of step k-1 have completed
+                    // the staging planes are free once the MMAs (and bulk stores) of step k-1 have read them
                     if (tr) p.trace[k * 8 + 1] = clock64();
-                    umma::mbar_wait(mbar, mpar);
+                    umma::mbar_wait(sbar, mpar);
                     mpar ^= 1;
                 }
                 if (tr) p.trace[k * 8 + 2] = clock64();
@@ -300,7 +317,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 __syncthreads();
             }
             // ---- epilogue: TMEM -> registers -> y
-            umma::mbar_wait(mbar, mpar);
+            umma::mbar_wait(sbar, mpar);
             mpar ^= 1;
             umma::fence_after_sync();
             const int q = warp & 3, wq = warp >> 2;
@@ -481,7 +498,7 @@ bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fo
 size_t cg_fused_workspace(int Fin, int Fout, int K) { return cg_align_up((size_t)K * Fin * Fout * 4, 256); }
 
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
-                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s) {
+                 int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s, bool stack_planes) {
     Plan pl = make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K);
     CG_REQUIRE(pl.ok, "cg_run_fused: shape not supported by the fused kernel (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
     CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
@@ -497,7 +514,11 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.x = x;
     fp.wp = wp;
     fp.y = y;
-    fp.stack_out = stack_out;
+    fp.stack_out = stack_planes ? nullptr : stack_out;
+    fp.planes_out = stack_planes ? reinterpret_cast<unsigned char *>(stack_out) : nullptr;
+    fp.planes_kf = (long long)N * g->M * 16;                    // one (k, feature octet) run: all rows x 8 bf16
+    fp.planes_pl = (long long)K * (Fin / 8) * fp.planes_kf;     // hi half, then mid half
+    CG_REQUIRE(!stack_planes || Fin % 8 == 0, "cg_run_fused: the plane side output needs Fin %% 8 == 0");
     fp.N = N;
     fp.M = g->M;
     fp.Fin = Fin;

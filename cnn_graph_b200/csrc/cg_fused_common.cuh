@@ -17,6 +17,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  : "memory");
 }
 
+// 1-D bulk copy shared -> global (TMA engine), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &mid) {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
     const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);

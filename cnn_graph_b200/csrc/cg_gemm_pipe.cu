@@ -66,9 +66,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
-}
 // one lane polls the barrier (a spinning warp costs an LSU wavefront per probe), the others wait at the warp barrier;
 // SLEEP > 0: back off between probes (long waits: accumulator hand-over)
 template <int SLEEP>

@@ -160,8 +160,19 @@ _STACK_SAVE_LIMIT = 8 << 30      # bytes: larger bases are recomputed in the bac
 _save_stack = True
 
 
+_stack_planes = True
+FILTER_STACK_PLANES = 32
+
+
 def save_stack_enabled():
     return _save_stack
+
+
+def set_stack_planes(flag):
+    """Saved basis as the fused kernel's bf16 operand planes (default, where the library supports the shape) or
+    always as the fp32 [K, N, M, Fin] stack (the layout of the reference's graph.chebyshev)."""
+    global _stack_planes
+    _stack_planes = bool(flag)
 
 
 def set_save_stack(flag):
@@ -194,9 +205,12 @@ class ChebFilterFn(torch.autograd.Function):
             sbytes = lib.cg_cheb_filter_stack_bytes(handle.handle, N, Fin, Fout, K, flags)
             if 0 < sbytes <= _STACK_SAVE_LIMIT:
                 stack = torch.empty((K, N, M, Fin), dtype=torch.float32, device=x.device)
+                if _stack_planes and lib.cg_cheb_filter_stack_planes(handle.handle, N, Fin, Fout, K, flags):
+                    flags |= FILTER_STACK_PLANES      # same bytes, holding bf16 hi | mid planes for the dW kernel
         check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, Fin, Fout, K, ptr(ws),
                                         nbytes, flags, _stream()), 'cg_cheb_filter_fwd_ex')
         ctx.stack = stack
+        ctx.stack_planes = bool(flags & FILTER_STACK_PLANES)
         ctx.save_for_backward(x, W)
         ctx.handle, ctx.K, ctx.grad_x, ctx.flags = handle, K, grad_x, flags
         return y

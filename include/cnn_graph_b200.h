@@ -92,7 +92,10 @@ enum {
     CG_FILTER_FORCE_ONCHIP = 2,    /* fail with CG_ERR_ARG if the on-chip kernels do not fit */
     CG_FILTER_NO_FUSED = 4,        /* never use the fused recurrence+contraction (tcgen05) kernel */
     CG_FILTER_FORCE_FUSED = 8,     /* fail with CG_ERR_ARG if the fused kernel does not support the shape */
-    CG_FILTER_NO_CLENSHAW = 16     /* input gradient by the forward-form fused kernel on L~^T, not the adjoint recurrence */
+    CG_FILTER_NO_CLENSHAW = 16,    /* input gradient by the forward-form fused kernel on L~^T, not the adjoint recurrence */
+    CG_FILTER_STACK_PLANES = 32    /* the saved basis (fwd_ex stack_out / bwd_ex saved_stack) is the fused kernel's bf16 hi|mid
+                                      operand plane image [2][K][Fin/8][N*M][8] (same byte size); only where
+                                      cg_cheb_filter_stack_planes() returns 1.  Pass the same flag to both calls. */
 };
 size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
 size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,
@@ -111,6 +114,9 @@ int cg_cheb_filter_bwd(const cg_graph_t *g, const float *dev_x, const float *dev
  * cg_cheb_filter_stack_bytes returns the size of that buffer, or 0 when the shape cannot use it
  * (then pass NULL).  dev_saved_stack in the backward may be NULL (the basis is recomputed). */
 size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
+/* 1 when the saved basis of this shape can use the CG_FILTER_STACK_PLANES format (fused forward kernel + the
+ * plane-streaming weight-gradient kernel), else 0. */
+int cg_cheb_filter_stack_planes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
 int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *dev_x, const float *dev_W, float *dev_y,
                           float *dev_stack_out, int N, int Fin, int Fout, int K, void *dev_workspace,
                           size_t workspace_bytes, int flags, void *stream);

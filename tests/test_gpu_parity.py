@@ -542,15 +542,29 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
     for gx, gw in grads:
         close(gx, dx)
         close(gw, dW)
-    # the saved basis itself is the reference's graph.chebyshev of every sample
+    # default format of the saved basis for this shape (the loop above used it): the fused kernel's bf16 operand
+    # planes [2][K][Fin/8][N*M][8]; hi + mid reproduce the reference's graph.chebyshev of every sample to 2^-16
     from oracle import graph_ref
-    h = ops.get_handle(L)
-    xt = dev(x).requires_grad_(True)
-    y = ops.cheb_filter(xt, dev(W), L, K)
-    stack = y.grad_fn.stack.cpu().numpy()                       # [K, N, M, Fin]
     Lr = ops.rescale_csr(L)
     ref = graph_ref.chebyshev(Lr, np.ascontiguousarray(x.transpose(1, 0, 2).reshape(M, N * Fin)), K)
+    y = ops.cheb_filter(dev(x).requires_grad_(True), dev(W), L, K)
+    assert y.grad_fn.stack_planes
+    pl = y.grad_fn.stack.view(torch.bfloat16).reshape(2, K, Fin // 8, N * M, 8).float().sum(0)
+    basis = pl.permute(0, 2, 1, 3).reshape(K, N, M, Fin).cpu().numpy()
+    close(basis.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 3e-5)
+    # the fp32 format [K, N, M, Fin] on request: same basis, same gradients
+    ops.set_stack_planes(False)
+    try:
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, K)
+        assert not y.grad_fn.stack_planes
+        stack = y.grad_fn.stack.cpu().numpy()
+        y.backward(dev(gy))
+    finally:
+        ops.set_stack_planes(True)
     close(stack.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 1e-5)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
 
 
 @pytest.mark.parametrize('kind', ['max', 'avg'])
