@@ -129,6 +129,8 @@ extern "C" int cg_cheb_filter_stack_planes(const cg_graph_t *g, int N, int Fin, 
 
 extern "C" size_t cg_cheb_filter_stack_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags) {
     if (!g || Fin <= 0 || Fout <= 0 || K < 1) return 0;
+    if ((flags & CG_FILTER_STACK_PLANES) && planes_ok(g, N, Fin, Fout, K, flags))      // rows padded to whole chunks of 128
+        return sizeof(float) * (size_t)K * Fin * (size_t)(cg_ceil_div((int64_t)N * g->M, 128) * 128);
     return can_save_stack(g, N, Fin, Fout, K, flags) ? sizeof(float) * (size_t)K * N * g->M * Fin : 0;
 }
 

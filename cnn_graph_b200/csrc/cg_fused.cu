@@ -39,8 +39,9 @@ struct FusedParams {
     float *y;                    // [N][M][Fout]
     float *stack_out;            // optional: X_k for the weight gradient, [K][N][M][Fin] (sample-major)
     unsigned char *planes_out;   // optional, instead of stack_out: the staged bf16 hi | mid planes themselves,
-                                 // [2][K][Fin/8][N*M rows][8 features] (cg_dw_planes.cu reads them without conversion)
-    long long planes_kf, planes_pl;     // bytes between (k, feature octet) runs / between the hi and mid halves
+                                 // [2][K][chunks of 128 rows][Fin/8][128 rows][8 features] over the rows n*M + m
+                                 // (cg_dw_planes.cu reads them without conversion)
+    long long planes_k, planes_pl;      // bytes per k (all chunks) / between the hi and mid halves
     long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][8]
     int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab, nw, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
@@ -193,11 +194,17 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                     if (p.planes_out != nullptr) {
                         // the staged planes are, per feature octet, one contiguous run over the group's rows in the
                         // MN-major core-matrix order the weight-gradient kernel wants: ship them as they are
-                        const uint32_t run = (uint32_t)Rg * 16u;
-                        for (int fo = 0; fo < Fin / 8; ++fo) {
-                            unsigned char *dst = p.planes_out + ((size_t)k * (Fin / 8) + fo) * p.planes_kf + (size_t)n0 * M * 16;
-                            bulk_s2g(dst, a0 + (uint32_t)fo * p.lbo_a, run);
-                            bulk_s2g(dst + p.planes_pl, a0 + p.plane_bytes + (uint32_t)fo * p.lbo_a, run);
+                        // (global image: chunks of 128 rows, so that a chunk of one k is one contiguous block)
+                        const long long g0 = (long long)n0 * M, g1 = g0 + Rg;
+                        const uint32_t cs = (uint32_t)(Fin / 8) * 2048u;
+                        for (long long c = g0 >> 7; c <= (g1 - 1) >> 7; ++c) {
+                            const long long a = max(g0, c << 7), b = min(g1, (c + 1) << 7);
+                            const uint32_t run = (uint32_t)(b - a) * 16u, so = (uint32_t)(a - g0) * 16u;
+                            unsigned char *dst = p.planes_out + (size_t)k * p.planes_k + (size_t)c * cs + (size_t)(a & 127) * 16;
+                            for (int fo = 0; fo < Fin / 8; ++fo) {
+                                bulk_s2g(dst + fo * 2048, a0 + (uint32_t)fo * p.lbo_a + so, run);
+                                bulk_s2g(dst + p.planes_pl + fo * 2048, a0 + p.plane_bytes + (uint32_t)fo * p.lbo_a + so, run);
+                            }
                         }
                         bulk_commit();
                     }
@@ -516,8 +523,8 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.y = y;
     fp.stack_out = stack_planes ? nullptr : stack_out;
     fp.planes_out = stack_planes ? reinterpret_cast<unsigned char *>(stack_out) : nullptr;
-    fp.planes_kf = (long long)N * g->M * 16;                    // one (k, feature octet) run: all rows x 8 bf16
-    fp.planes_pl = (long long)K * (Fin / 8) * fp.planes_kf;     // hi half, then mid half
+    fp.planes_k = cg_ceil_div((long long)N * g->M, 128) * (Fin / 8) * 2048;     // all 128-row chunks of one k
+    fp.planes_pl = (long long)K * fp.planes_k;                                  // hi half, then mid half
     CG_REQUIRE(!stack_planes || Fin % 8 == 0, "cg_run_fused: the plane side output needs Fin %% 8 == 0");
     fp.N = N;
     fp.M = g->M;

@@ -204,9 +204,13 @@ class ChebFilterFn(torch.autograd.Function):
         if any(ctx.needs_input_grad[:2]) and save_stack_enabled():
             sbytes = lib.cg_cheb_filter_stack_bytes(handle.handle, N, Fin, Fout, K, flags)
             if 0 < sbytes <= _STACK_SAVE_LIMIT:
-                stack = torch.empty((K, N, M, Fin), dtype=torch.float32, device=x.device)
                 if _stack_planes and lib.cg_cheb_filter_stack_planes(handle.handle, N, Fin, Fout, K, flags):
-                    flags |= FILTER_STACK_PLANES      # same bytes, holding bf16 hi | mid planes for the dW kernel
+                    # bf16 hi | mid operand planes for the dW kernel: [2, K, ceil(N*M/128), Fin/8, 128, 8]
+                    flags |= FILTER_STACK_PLANES
+                    sbytes = lib.cg_cheb_filter_stack_bytes(handle.handle, N, Fin, Fout, K, flags)
+                    stack = torch.empty((sbytes // 2,), dtype=torch.bfloat16, device=x.device)
+                else:
+                    stack = torch.empty((K, N, M, Fin), dtype=torch.float32, device=x.device)
         check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, Fin, Fout, K, ptr(ws),
                                         nbytes, flags, _stream()), 'cg_cheb_filter_fwd_ex')
         ctx.stack = stack

@@ -94,8 +94,9 @@ enum {
     CG_FILTER_FORCE_FUSED = 8,     /* fail with CG_ERR_ARG if the fused kernel does not support the shape */
     CG_FILTER_NO_CLENSHAW = 16,    /* input gradient by the forward-form fused kernel on L~^T, not the adjoint recurrence */
     CG_FILTER_STACK_PLANES = 32    /* the saved basis (fwd_ex stack_out / bwd_ex saved_stack) is the fused kernel's bf16 hi|mid
-                                      operand plane image [2][K][Fin/8][N*M][8] (same byte size); only where
-                                      cg_cheb_filter_stack_planes() returns 1.  Pass the same flag to both calls. */
+                                      operand plane image [2][K][ceil(N*M/128)][Fin/8][128][8]; only where
+                                      cg_cheb_filter_stack_planes() returns 1.  Pass the same flag to both calls and to
+                                      cg_cheb_filter_stack_bytes (rows are padded to whole chunks of 128). */
 };
 size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K, int flags);
 size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N, int Fin, int Fout, int K,

@@ -543,14 +543,16 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
         close(gx, dx)
         close(gw, dW)
     # default format of the saved basis for this shape (the loop above used it): the fused kernel's bf16 operand
-    # planes [2][K][Fin/8][N*M][8]; hi + mid reproduce the reference's graph.chebyshev of every sample to 2^-16
+    # planes [2][K][128-row chunks][Fin/8][128][8]; hi + mid reproduce the reference's graph.chebyshev of every sample
+    # to 2^-16
     from oracle import graph_ref
     Lr = ops.rescale_csr(L)
     ref = graph_ref.chebyshev(Lr, np.ascontiguousarray(x.transpose(1, 0, 2).reshape(M, N * Fin)), K)
     y = ops.cheb_filter(dev(x).requires_grad_(True), dev(W), L, K)
     assert y.grad_fn.stack_planes
-    pl = y.grad_fn.stack.view(torch.bfloat16).reshape(2, K, Fin // 8, N * M, 8).float().sum(0)
-    basis = pl.permute(0, 2, 1, 3).reshape(K, N, M, Fin).cpu().numpy()
+    nch = (N * M + 127) // 128
+    pl = y.grad_fn.stack.reshape(2, K, nch, Fin // 8, 128, 8).float().sum(0)          # [K, chunk, octet, row, 8]
+    basis = pl.permute(0, 1, 3, 2, 4).reshape(K, nch * 128, Fin)[:, :N * M].reshape(K, N, M, Fin).cpu().numpy()
     close(basis.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 3e-5)
     # the fp32 format [K, N, M, Fin] on request: same basis, same gradients
     ops.set_stack_planes(False)
