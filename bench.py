@@ -85,8 +85,10 @@ def step_work(L, N):
         'fused_fwd': {'bound': 'hbm', 'launches': [(b_stream(M2, z2, N * F[0], K[1]), spmm_flops(M2, z2, N * F[0], K[1]) + g2)]},
         # layer 2 input gradient: adjoint recurrence at width N*32 on L~^T and the 64 -> 32 products G_k
         'clenshaw_dx': {'bound': 'hbm', 'launches': [(b_stream(M2, z2, N * F[0], K[1]), spmm_flops(M2, z2, N * F[0], K[1]) + g2)]},
-        # weight gradients: stream the basis (K N M Fin fp32) and gy (N M Fout fp32) once
-        'dw_umma': {'bound': 'hbm', 'launches': [(dw_bytes(M2, F[0], F[1], K[1]), g2), (dw_bytes(M1, 1, F[0], K[0]), g1)]},
+        # weight gradients: stream the basis (K N M Fin x 4 bytes: fp32, or bf16 hi + mid planes) and gy (N M Fout fp32) once;
+        # layer 2 on the tensor cores from the forward kernel's operand planes, layer 1 (Fin = 1) on the FFMA pipe
+        'dw_umma': {'bound': 'hbm', 'launches': [(dw_bytes(M2, F[0], F[1], K[1]), g2)]},
+        'dw_thin': {'bound': 'hbm', 'launches': [(dw_bytes(M1, 1, F[0], K[0]), g1)]},
         # layer 1 (Fin = 1): unfused recurrence (forward, and again for dW) and FFMA contraction
         'basis_onchip': {'bound': 'hbm', 'launches': [(b_stream(M1, z1, N, K[0]), spmm_flops(M1, z1, N, K[0]))] * 2},
         'contract': {'bound': 'tensor', 'launches': [(0, g1)]},

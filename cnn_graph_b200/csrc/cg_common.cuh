@@ -130,6 +130,12 @@ size_t cg_fused_workspace(int Fin, int Fout, int K);
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
                  int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s, bool stack_planes = false);
 
+// Weight gradient of a first layer (Fa = 1) on the FFMA pipe, HBM-bound streaming (cg_dw_thin.cu).
+bool cg_dw_thin_supported(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+size_t cg_dw_thin_workspace(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
+int cg_run_dw_thin(const float *stack, const float *T, float *dW, long long R, int Fb, int K, float *workspace, int sm_count,
+                   size_t smem_limit, cudaStream_t s);
+
 // Weight gradient straight from that plane image (cg_dw_planes.cu): no conversion on the stack side.
 bool cg_dw_planes_supported(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
 size_t cg_dw_planes_workspace(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);

@@ -30,11 +30,22 @@ static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const int64_t R = (int64_t)N * g->M;
     const size_t c = R < (int64_t)INT32_MAX ? cg_gemm_workspace(Fa, Fb, (int)R) : 0;       // per-k GEMM, split over R
     const size_t d = cg_dw_planes_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
-    return std::max(std::max(a, d), std::max(b, c));
+    const size_t e = cg_dw_thin_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
+    return std::max(std::max(a, std::max(d, e)), std::max(b, c));
+}
+
+// stack^T x plain for a scalar-signal stack (first layers): streaming FFMA kernel
+static bool thin_ok(const cg_graph *g, const float *stack, const float *T, float *part, int N, int Fa, int Fb, int K, bool swap,
+                    bool sample_major, int flags) {
+    return !swap && sample_major && !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) &&
+           ((((uintptr_t)stack | (uintptr_t)T | (uintptr_t)part) & 15) == 0) &&
+           cg_dw_thin_supported((long long)N * g->M, Fa, Fb, K, g->sm_count, g->smem_optin);
 }
 
 static int run_dw(const cg_graph *g, const float *stack, const float *T, float *dW, int N, int Fa, int Fb, int K,
                   bool swap, bool sample_major, float *part, int flags, cudaStream_t s) {
+    if (thin_ok(g, stack, T, part, N, Fa, Fb, K, swap, sample_major, flags))
+        return cg_run_dw_thin(stack, T, dW, (long long)N * g->M, Fb, K, part, g->sm_count, g->smem_optin, s);
     const bool tc = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) &&
                     cg_dw_umma_supported(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin) &&
                     ((((uintptr_t)stack | (uintptr_t)T | (uintptr_t)part) & 15) == 0);

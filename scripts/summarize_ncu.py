@@ -16,7 +16,7 @@ COLS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__shared_mem_per_block_dynamic']
 # profile-scope names of bench.py (cg_profile_*) for the kernels whose DRAM traffic the roofline line quotes
-SCOPE = {'k_cheb_fused': 'fused_fwd', 'k_cheb_clenshaw': 'clenshaw_dx', 'k_dw_planes': 'dw_umma', 'k_dw_umma': 'dw_umma',
+SCOPE = {'k_cheb_fused': 'fused_fwd', 'k_cheb_clenshaw': 'clenshaw_dx', 'k_dw_planes': 'dw_umma', 'k_dw_umma': 'dw_umma', 'k_dw_thin': 'dw_thin',
          'k_contract_umma': 'contract_umma', 'k_gemm_pipe': 'gemm_umma', 'k_basis_onchip': 'basis_onchip'}
 
 
