@@ -310,3 +310,51 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
     }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Contractions over a caller-owned Chebyshev stack (row-partitioned filter of config C5: the stack is the
+// [K][nloc + nhalo][F] buffer of cnn_graph_b200/partition.py, so the slab stride is not R * F).
+// ---------------------------------------------------------------------------------------------------------
+extern "C" size_t cg_cheb_contract_workspace_bytes(int64_t R, int Fin, int Fout, int K) {
+    if (R <= 0 || R >= (int64_t)INT32_MAX || Fin <= 0 || Fout <= 0 || K < 1) return 0;
+    const size_t a = cg_gemm_workspace((int)R, Fout, K * Fin), b = cg_gemm_workspace((int)R, Fin, K * Fout);
+    const size_t c = cg_gemm_workspace(Fin, Fout, (int)R);
+    return std::max(a, std::max(b, c));
+}
+
+extern "C" int cg_cheb_contract(const float *stack, int64_t slab_stride, const float *W, float *y, int64_t R, int Fin,
+                                int Fout, int K, int transposed, void *workspace, size_t workspace_bytes, void *stream) {
+    CG_REQUIRE(R >= 0 && R < (int64_t)INT32_MAX && Fin > 0 && Fout > 0 && K >= 1, "cg_cheb_contract: bad dims");
+    if (R == 0) return CG_OK;
+    CG_REQUIRE(stack && W && y, "cg_cheb_contract: NULL tensor");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!transposed) {
+        // y[r, fo] = sum_{k,f} stack_k[r, f] W[f*K + k, fo]: q = k*Fin + f  <->  W row f*K + k
+        CG_REQUIRE(slab_stride >= R * Fin, "cg_cheb_contract: slab stride smaller than a slab");
+        return cg_run_gemm(stack, W, y, (int)R, Fout, K * Fin, 0, 0, Fin, Fout, Fout, nullptr, 0, Fin, slab_stride, Fin, 1, K,
+                           workspace, workspace_bytes, s);
+    }
+    // y[r, f] = sum_{k,fo} stack_k[r, fo] W[f*K + k, fo]: B = W read as [f][k*Fout + fo]
+    CG_REQUIRE(slab_stride >= R * Fout, "cg_cheb_contract: slab stride smaller than a slab");
+    return cg_run_gemm(stack, W, y, (int)R, Fin, K * Fout, 0, 1, Fout, K * Fout, Fin, nullptr, 0, Fout, slab_stride, 0, 0, 0,
+                       workspace, workspace_bytes, s);
+}
+
+extern "C" int cg_cheb_contract_dw(const float *stack, int64_t slab_stride, const float *gy, float *dW, int64_t R, int Fin,
+                                   int Fout, int K, void *workspace, size_t workspace_bytes, void *stream) {
+    CG_REQUIRE(R >= 0 && R < (int64_t)INT32_MAX && Fin > 0 && Fout > 0 && K >= 1, "cg_cheb_contract_dw: bad dims");
+    CG_REQUIRE(dW != nullptr, "cg_cheb_contract_dw: dW is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (R == 0) {
+        CG_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Fin * K * Fout, s));
+        return CG_OK;
+    }
+    CG_REQUIRE(stack && gy && slab_stride >= R * Fin, "cg_cheb_contract_dw: bad stack");
+    // dW[f*K + k, fo] = sum_r stack_k[r, f] gy[r, fo]: one GEMM per k into rows k, K + k, ... of dW
+    for (int k = 0; k < K; ++k) {
+        const int rc = cg_run_gemm(stack + (size_t)k * slab_stride, gy, dW + (size_t)k * Fout, Fin, Fout, (int)R, 1, 0, Fin,
+                                   Fout, K * Fout, nullptr, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes, s);
+        if (rc != CG_OK) return rc;
+    }
+    return CG_OK;
+}

@@ -2,7 +2,9 @@
 SURVEY.md 8(e)(2)): the M rows of L~ and of every X_k are split into `world` contiguous blocks (after a
 locality ordering); one recurrence step needs the rows of X_{k-1} referenced by off-block columns -- the halo --
 which the ranks exchange point to point (NCCL all-to-all over NVLink on the B200 box, gloo in CPU tests).
-The contraction with W is row-local, so the forward needs no other communication.
+The contraction with W is row-local, so the forward needs no other communication.  The backward pass
+(`PartitionedFilter.backward`) runs the same exchange pattern on L~^T for the input gradient and sums the weight
+gradient over the ranks with one all-reduce.
 
 Every rank holds the whole (host) operator and derives all send / receive lists from it without talking to
 anyone: rank r needs the sorted distinct columns of its row block that fall outside the block; rank p sends, to
@@ -97,6 +99,10 @@ class PartitionedBasis:
     def basis(self, x_loc, K):
         """x_loc [nloc, C] (this rank's rows of X) -> [K, nloc, C] (a view of the [K, nloc + nhalo, C] buffer whose
         tail rows hold the halo of every X_k: each step writes its block in place, no staging copies)."""
+        return self.basis_ext(x_loc, K)[:, :self.part.nloc]
+
+    def basis_ext(self, x_loc, K):
+        """The whole [K, nloc + nhalo, C] buffer (rows [0, nloc) of every slab are this rank's rows)."""
         part = self.part
         C = x_loc.shape[1]
         ext = torch.empty((K, part.n_ext, C), dtype=torch.float32, device=x_loc.device)
@@ -109,4 +115,82 @@ class PartitionedBasis:
                 ext[k, :part.nloc] = self._step_fn(ext[k - 1], x0, alpha)
             else:
                 self._native_step(ext[k - 1], x0, alpha, ext[k, :part.nloc])
-        return ext[:, :part.nloc]
+        return ext
+
+
+class PartitionedFilter:
+    """Chebyshev filter of one signal on a row-partitioned graph (config C5: N = 1, x [M, Fin], W [Fin*K, Fout] with
+    row fin*K + k as in lib/models.py:222), forward and backward, for the rows of this rank:
+
+        forward    X_k = T_k(L~) x (halo exchange per step)         y_loc  = sum_k X_k[loc] W_k
+        backward   Z_k = T_k(L~^T) gy (same pattern on L~^T)        dx_loc = sum_k Z_k[loc] W_k^T
+                   dW  = sum over ranks of sum_k X_k[loc]^T gy_loc  (one all-reduce)
+
+    L~ is symmetric only to rounding and not at all for directed graphs, so the backward uses its own partition
+    of the true transpose.  `step_fn` / `contract_fn` / `dw_fn` replace the native CUDA
+    pieces (cg_cheb_step, cg_cheb_contract, cg_cheb_contract_dw) in host-side tests."""
+
+    def __init__(self, L_rescaled, K, rank=None, world=None, device=None, step_fn=None, step_fn_t=None,
+                 contract_fn=None, dw_fn=None, group=None):
+        L_rescaled = scipy.sparse.csr_matrix(L_rescaled, dtype=np.float32)
+        self.K = int(K)
+        self.group = group
+        self.fwd = PartitionedBasis(L_rescaled, rank, world, device, step_fn)
+        self.bwd = PartitionedBasis(scipy.sparse.csr_matrix(L_rescaled.T), rank, world, device, step_fn_t)
+        self.part = self.fwd.part
+        self._contract_fn, self._dw_fn = contract_fn, dw_fn
+        self._saved = None
+
+    # stack: [K, n_ext, F] buffer whose first nloc rows per slab are this rank's rows
+    def _contract(self, ext, W, transposed):
+        K, n_ext, F = ext.shape
+        nloc = self.part.nloc
+        Fin, Fout = (W.shape[0] // K, W.shape[1])
+        if self._contract_fn is not None:
+            return self._contract_fn(ext[:, :nloc], W, transposed)
+        lib = _native.lib()
+        out = torch.empty((nloc, Fin if transposed else Fout), dtype=torch.float32, device=ext.device)
+        nbytes = lib.cg_cheb_contract_workspace_bytes(nloc, Fin, Fout, K)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=ext.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _native.check(lib.cg_cheb_contract(ext.data_ptr(), n_ext * F, W.data_ptr(), out.data_ptr(), nloc, Fin, Fout, K,
+                                           int(transposed), ws.data_ptr(), nbytes, stream), 'cg_cheb_contract')
+        return out
+
+    def _dw(self, ext, gy, Fout):
+        K, n_ext, Fin = ext.shape
+        nloc = self.part.nloc
+        if self._dw_fn is not None:
+            return self._dw_fn(ext[:, :nloc], gy)
+        lib = _native.lib()
+        dW = torch.empty((Fin * K, Fout), dtype=torch.float32, device=ext.device)
+        nbytes = lib.cg_cheb_contract_workspace_bytes(nloc, Fin, Fout, K)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=ext.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _native.check(lib.cg_cheb_contract_dw(ext.data_ptr(), n_ext * Fin, gy.data_ptr(), dW.data_ptr(), nloc, Fin, Fout,
+                                              K, ws.data_ptr(), nbytes, stream), 'cg_cheb_contract_dw')
+        return dW
+
+    def forward(self, x_loc, W):
+        """x_loc [nloc, Fin] (this rank's rows), W [Fin*K, Fout] (replicated) -> y_loc [nloc, Fout]."""
+        if W.shape[0] != x_loc.shape[1] * self.K:
+            raise ValueError('W must be [Fin*K, Fout] = [%d, *], got %r' % (x_loc.shape[1] * self.K, tuple(W.shape)))
+        ext = self.fwd.basis_ext(x_loc.contiguous(), self.K)
+        self._saved = (ext, W)
+        return self._contract(ext, W.contiguous(), False)
+
+    def backward(self, gy_loc, need_dx=True):
+        """gy_loc [nloc, Fout] -> (dx_loc [nloc, Fin] or None, dW [Fin*K, Fout] summed over all ranks)."""
+        if self._saved is None:
+            raise RuntimeError('PartitionedFilter.backward called before forward')
+        ext, W = self._saved
+        self._saved = None
+        gy_loc = gy_loc.contiguous()
+        dW = self._dw(ext, gy_loc, W.shape[1])
+        if self.part.world > 1:
+            dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=self.group)
+        dx = None
+        if need_dx:
+            zext = self.bwd.basis_ext(gy_loc, self.K)
+            dx = self._contract(zext, W.contiguous(), True)
+        return dx, dW

@@ -158,6 +158,20 @@ int cg_bias_act_pool_bwd(const float *dev_gy, const float *dev_y, const uint8_t 
                          float *dev_dbias, int N, int M, int F, int p, int bias_kind, int act, int kind,
                          void *stream);
 
+/* ---- contractions over a caller-owned stack (row-partitioned filter, config C5) ------------------------- */
+/* lib/models.py:218-223 on a basis the caller built slab by slab (cg_cheb_step + halo exchange): dev_stack holds K
+ * slabs [R][F] that are slab_stride ELEMENTS apart (>= R*F; the partition keeps halo rows behind every slab).
+ *   cg_cheb_contract, transposed == 0:  y[r, fo] = sum_{k,f}  stack_k[r, f]  W[f*K + k, fo]   (slabs of Fin columns)
+ *   cg_cheb_contract, transposed != 0:  y[r, f]  = sum_{k,fo} stack_k[r, fo] W[f*K + k, fo]   (slabs of Fout columns:
+ *                                        the input gradient from Z_k = T_k(L~^T) gy)
+ *   cg_cheb_contract_dw:                dW[f*K + k, fo] = sum_r stack_k[r, f] gy[r, fo]
+ * Tensor-core GEMMs (bf16 hi+mid split, fp32 accumulation); scratch from cg_cheb_contract_workspace_bytes.        */
+size_t cg_cheb_contract_workspace_bytes(int64_t R, int Fin, int Fout, int K);
+int cg_cheb_contract(const float *dev_stack, int64_t slab_stride, const float *dev_W, float *dev_y, int64_t R, int Fin,
+                     int Fout, int K, int transposed, void *workspace, size_t workspace_bytes, void *stream);
+int cg_cheb_contract_dw(const float *dev_stack, int64_t slab_stride, const float *dev_gy, float *dev_dW, int64_t R,
+                        int Fin, int Fout, int K, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- dense head -------------------------------------------------------- */
 /* fc layers of cgcnn (lib/models.py:268-274: relu(x W + b)) and their gradients: a general fp32 GEMM on the
  * tensor cores, C[M x N] = op(A)[M x K] . op(B)[K x N] (+ bias[N]) (relu), all matrices row-major;

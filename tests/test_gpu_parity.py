@@ -780,3 +780,25 @@ def test_pipelined_trainer_matches_direct_steps(ops, c2, use_graph):
     assert len(got) == len(want)
     np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-6)
     assert tr.h2d_bytes_per_step == 16 * 784 * 4 + 16 * 8
+
+
+# --------------------------------------------------------------------------- row-partitioned filter (config C5)
+@pytest.mark.parametrize('Fin,Fout,K', [(64, 64, 5), (8, 16, 4), (3, 5, 3)])
+def test_partitioned_filter_single_rank_vs_oracle(ops, tf_ref, directed, Fin, Fout, K):
+    """PartitionedFilter at world 1 (no halo): cg_cheb_step recurrences on L~ and L~^T, cg_cheb_contract and
+    cg_cheb_contract_dw over the strided stack -- against the oracle on a directed operator (N = 1)."""
+    from cnn_graph_b200 import partition
+    L = csr_from(directed, 'L')
+    M = L.shape[0]
+    Lr = ops.rescale_csr(L, 3.5)
+    rng = np.random.RandomState(17)
+    x = rng.standard_normal((M, Fin)).astype(np.float32)
+    W = (0.2 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((M, Fout)).astype(np.float32)
+    pf = partition.PartitionedFilter(Lr, K, rank=0, world=1)
+    y = pf.forward(dev(x), dev(W))
+    dx, dW = pf.backward(dev(gy))
+    close(y, tf_ref.chebyshev5(x[None], L, W, K, lmax=3.5)[0])
+    rdx, rdW = tf_ref.chebyshev5_backward(x[None], L, W, K, gy[None], lmax=3.5)
+    close(dx, rdx[0])
+    close(dW, rdW)
