@@ -48,8 +48,10 @@ template <>
 __device__ __forceinline__ float zero_v<float>() { return 0.f; }
 
 // block = 256 threads = (256 / lpr) rows x lpr lanes; lane handles VEC columns.
-template <int VEC>
-__global__ void __launch_bounds__(256)
+// U gathers in flight per thread, at least B resident blocks per SM (the step is bound by load latency: ncu shows
+// long-scoreboard stalls and 65 % occupancy at U = 4 without a register cap)
+template <int VEC, int U, int B>
+__global__ void __launch_bounds__(256, B)
 k_spmm_step(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
             const float *__restrict__ X1, const float *__restrict__ X0, float *__restrict__ out, int M,
             int64_t C, float alpha, int lpr) {
@@ -62,17 +64,19 @@ k_spmm_step(const int *__restrict__ rowptr, const int *__restrict__ col, const f
     const int beg = rowptr[m], end = rowptr[m + 1];
     V acc = zero_v<V>();
     int e = beg;
-    for (; e + 3 < end; e += 4) {
-        const int c0 = col[e], c1 = col[e + 1], c2 = col[e + 2], c3 = col[e + 3];
-        const float v0 = val[e], v1 = val[e + 1], v2 = val[e + 2], v3 = val[e + 3];
-        const V x0 = *reinterpret_cast<const V *>(X1 + (int64_t)c0 * C + c);
-        const V x1 = *reinterpret_cast<const V *>(X1 + (int64_t)c1 * C + c);
-        const V x2 = *reinterpret_cast<const V *>(X1 + (int64_t)c2 * C + c);
-        const V x3 = *reinterpret_cast<const V *>(X1 + (int64_t)c3 * C + c);
-        fma_acc(acc, v0, x0);
-        fma_acc(acc, v1, x1);
-        fma_acc(acc, v2, x2);
-        fma_acc(acc, v3, x3);
+    for (; e + U - 1 < end; e += U) {
+        int cc[U];
+        float vv[U];
+        V xx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cc[u] = col[e + u];
+            vv[u] = val[e + u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xx[u] = *reinterpret_cast<const V *>(X1 + (int64_t)cc[u] * C + c);
+#pragma unroll
+        for (int u = 0; u < U; ++u) fma_acc(acc, vv[u], xx[u]);
     }
     for (; e < end; ++e) {
         const V x = *reinterpret_cast<const V *>(X1 + (int64_t)col[e] * C + c);
@@ -99,10 +103,12 @@ static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, 
     dim3 grid((unsigned)cg_ceil_div(M, rows_per_block), (unsigned)cg_ceil_div(lanes_needed, lpr));
     CG_REQUIRE(grid.y <= 65535, "spmm_step: too many columns (C=%lld)", (long long)C);
     CgProfScope prof("spmm_step", s);
+    // measured at C5 (2^20 vertices, 18.6 M entries, C = 64): U = 4 gathers in flight at full occupancy (register cap 32)
+    // 0.339 ms; without the cap (39 registers, 6 blocks) 0.378; U = 8 0.374 (6 blocks) / 0.465 (4); U = 2 at 8 blocks 0.351
     if (vec4)
-        k_spmm_step<4><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
+        k_spmm_step<4, 4, 8><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
     else
-        k_spmm_step<1><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
+        k_spmm_step<1, 4, 6><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
