@@ -88,7 +88,9 @@ def step_work(L, N):
         # weight gradients: stream the basis (K N M Fin x 4 bytes: fp32, or bf16 hi + mid planes) and gy (N M Fout fp32) once;
         # layer 2 on the tensor cores from the forward kernel's operand planes, layer 1 (Fin = 1) on the FFMA pipe
         'dw_umma': {'bound': 'hbm', 'launches': [(dw_bytes(M2, F[0], F[1], K[1]), g2)]},
-        'dw_thin': {'bound': 'hbm', 'launches': [(dw_bytes(M1, 1, F[0], K[0]), g1)]},
+        # (fused first layer: the kernel reads the fp32 basis and, per POOLED value, the gradient, the output and the
+        #  argmax byte -- 9 bytes per 4 vertices and filter -- instead of the 4x larger gy)
+        'dw_thin': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * K[0] + 9.0 * N * (M1 // P[0]) * F[0], g1)]},
         # layer 1 (Fin = 1): unfused recurrence (forward, and again for dW) and FFMA contraction
         'basis_onchip': {'bound': 'hbm', 'launches': [(b_stream(M1, z1, N, K[0]), spmm_flops(M1, z1, N, K[0]))] * 2},
         'contract': {'bound': 'tensor', 'launches': [(0, g1)]},

@@ -136,6 +136,12 @@ size_t cg_dw_thin_workspace(long long R, int Fa, int Fb, int K, int sm_count, si
 int cg_run_dw_thin(const float *stack, const float *T, float *dW, long long R, int Fb, int K, float *workspace, int sm_count,
                    size_t smem_limit, cudaStream_t s);
 
+// ... and its variant for a first layer followed by bias + relu + max pooling of 4: takes the gradient of the POOLED output
+bool cg_dw_thin_pooled_supported(long long R, int Fb, int K, int sm_count, size_t smem_limit);
+size_t cg_dw_thin_pooled_workspace(long long R, int Fb, int K, int sm_count, size_t smem_limit);
+int cg_run_dw_thin_pooled(const float *stack, const float *gp, const float *yp, const unsigned char *aux, float *dW, float *db,
+                          long long R, int Fb, int K, float *workspace, int sm_count, size_t smem_limit, cudaStream_t s);
+
 // Weight gradient straight from that plane image (cg_dw_planes.cu): no conversion on the stack side.
 bool cg_dw_planes_supported(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
 size_t cg_dw_planes_workspace(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);

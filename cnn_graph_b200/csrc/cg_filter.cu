@@ -358,3 +358,34 @@ extern "C" int cg_cheb_contract_dw(const float *stack, int64_t slab_stride, cons
     }
     return CG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// First-layer fusion (Fin = 1): gradients of  pool_max4(relu(filter(x; W) + b))  from the gradient of the POOLED
+// output (lib/models.py:226-257 behind lib/models.py:192-224; TF autodiff through lib/graph_model.py:296).
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int cg_cheb_dw_pooled_supported(const cg_graph_t *g, int N, int Fout, int K, int p, int act, int kind,
+                                           int bias_kind) {
+    if (!g || N <= 0 || g->M % 4 != 0 || p != 4 || act != 1 || kind != 1 || bias_kind < 0 || bias_kind > 1) return 0;
+    if (cg_cheb_filter_stack_bytes(g, N, 1, Fout, K, 0) == 0) return 0;          // needs the fp32 basis [K][N][M]
+    return cg_dw_thin_pooled_supported((long long)N * g->M, Fout, K, g->sm_count, g->smem_optin) ? 1 : 0;
+}
+
+extern "C" size_t cg_cheb_dw_pooled_workspace_bytes(const cg_graph_t *g, int N, int Fout, int K) {
+    if (!g || N <= 0) return 0;
+    return cg_dw_thin_pooled_workspace((long long)N * g->M, Fout, K, g->sm_count, g->smem_optin);
+}
+
+extern "C" int cg_cheb_dw_pooled(const cg_graph_t *g, const float *stack, const float *g_pooled, const float *y_pooled,
+                                 const uint8_t *aux, float *dW, float *db, int N, int Fout, int K, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+    CG_REQUIRE(g != nullptr && N > 0 && Fout > 0 && K >= 1, "cg_cheb_dw_pooled: bad arguments");
+    CG_REQUIRE(stack && g_pooled && y_pooled && aux && dW, "cg_cheb_dw_pooled: NULL tensor");
+    const size_t need = cg_cheb_dw_pooled_workspace_bytes(g, N, Fout, K);
+    CG_REQUIRE(need > 0, "cg_cheb_dw_pooled: shape not supported (cg_cheb_dw_pooled_supported returned 0)");
+    if (workspace == nullptr || workspace_bytes < need) {
+        cg_set_error("cg_cheb_dw_pooled: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return CG_ERR_WORKSPACE;
+    }
+    return cg_run_dw_thin_pooled(stack, g_pooled, y_pooled, aux, dW, db, (long long)N * g->M, Fout, K,
+                                 reinterpret_cast<float *>(workspace), g->sm_count, g->smem_optin, (cudaStream_t)stream);
+}

@@ -227,6 +227,11 @@ class cgcnn(GraphConvOps, GraphModel):
             x = x.unsqueeze(2)                                   # N x M x F=1  (lib/models.py:318)
         for i in range(len(self.p)):
             with self.variable_scope('conv{}'.format(i + 1)):
+                fused_layer = self._fused_first_layer(x, i)          # declares the same variables in the same scopes
+                if fused_layer is not None:
+                    x = fused_layer
+                    self.nets['conv{}/pooling'.format(i + 1)] = x
+                    continue
                 with self.variable_scope('filter'):
                     x = self.filter(x, self.L[i], self.F[i], self.K[i])
                 with self.variable_scope('bias_relu'):
@@ -248,6 +253,24 @@ class cgcnn(GraphConvOps, GraphModel):
         with self.variable_scope('logits'):
             x = self.fc(x, self.M[-1], relu=False)
         return x
+
+    def _fused_first_layer(self, x, i):
+        """filter -> b1relu -> mpool1(4) of a scalar-input layer as one autograd node (ops.first_layer), or None when the
+        layer is not that (user-bound filter / brelu / pool, other pool sizes, an input that needs a gradient, ...)."""
+        if x.is_meta or not self.fuse_brelu_pool:
+            return None
+        stock = (getattr(self.filter, '__func__', None) in (GraphConvOps.chebyshev5, GraphConvOps.chebyshev2) and
+                 getattr(self.brelu, '__func__', None) is GraphConvOps.b1relu and
+                 getattr(self.pool, '__func__', None) is GraphConvOps.mpool1)
+        if not stock or self.p[i] != 4 or int(x.shape[2]) != 1:
+            return None
+        with self.variable_scope('filter'):
+            W = self._weight_variable([self.K[i], self.F[i]], regularization=False)       # [Fin*K, Fout], Fin = 1
+        with self.variable_scope('bias_relu'):
+            b = self._bias_variable([1, 1, self.F[i]], regularization=False) if self.b1relu_has_bias else None
+        if not ops.first_layer_supported(x, W, b, self.L[i], self.K[i], 'relu', 4, 'max'):
+            return None
+        return ops.first_layer(x, W, b, self.L[i], self.K[i])
 
     def prediction(self, logits):
         return torch.argmax(logits, dim=1)

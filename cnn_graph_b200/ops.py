@@ -373,6 +373,87 @@ class BiasActPoolFn(torch.autograd.Function):
         return gx, db, None, None, None
 
 
+class FirstLayerFn(torch.autograd.Function):
+    """pool_max4(relu(chebyshev5(x; W) + b)) for a scalar-input first layer (x [N, M, 1], no gradient to x) as ONE
+    autograd node: the forward is the usual filter + fused bias/relu/pool pair, the backward goes from the gradient
+    of the pooled output straight to dW and db (cg_cheb_dw_pooled) -- no pooling-backward pass, no [N, M, Fout]
+    gradient tensor.  Same values as bias_act_pool(cheb_filter(x, W), b) and its gradients."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, handle, K):
+        _require_cuda(x, W, bias)
+        x, W = _f32c(x), _f32c(W)
+        N, M, _ = x.shape
+        Fout = W.shape[1]
+        lib = _native.lib()
+        y = torch.empty((N, M, Fout), dtype=torch.float32, device=x.device)
+        nbytes = lib.cg_cheb_filter_fwd_workspace_bytes(handle.handle, N, 1, Fout, K, 0)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
+        stack = torch.empty((K, N, M, 1), dtype=torch.float32, device=x.device)
+        check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, 1, Fout, K, ptr(ws), nbytes, 0,
+                                        _stream()), 'cg_cheb_filter_fwd_ex')
+        bkind = 0
+        if bias is not None:
+            bias = _f32c(bias)
+            if bias.numel() != Fout:
+                raise ValueError('bias must have Fout=%d entries, got %d' % (Fout, bias.numel()))
+            bkind = 1
+        yp = torch.empty((N, M // 4, Fout), dtype=torch.float32, device=x.device)
+        aux = torch.empty((N, M // 4, Fout), dtype=torch.uint8, device=x.device)
+        check(lib.cg_bias_act_pool_fwd(ptr(y), ptr(bias), ptr(yp), ptr(aux), N, M, Fout, 4, bkind, ACT['relu'], 1, _stream()),
+              'cg_bias_act_pool_fwd')
+        ctx.save_for_backward(yp, aux)
+        ctx.stack, ctx.handle, ctx.K = stack, handle, K
+        ctx.w_shape, ctx.bias_shape = tuple(W.shape), None if bias is None else tuple(bias.shape)
+        return yp
+
+    @staticmethod
+    def backward(ctx, g):
+        yp, aux = ctx.saved_tensors
+        g = _f32c(g)
+        N, Mp, Fout = yp.shape
+        K, handle = ctx.K, ctx.handle
+        lib = _native.lib()
+        dW = torch.empty(ctx.w_shape, dtype=torch.float32, device=yp.device)
+        db = None
+        if ctx.bias_shape is not None and ctx.needs_input_grad[2]:
+            db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=yp.device)
+        nbytes = lib.cg_cheb_dw_pooled_workspace_bytes(handle.handle, N, Fout, K)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=yp.device)
+        check(lib.cg_cheb_dw_pooled(handle.handle, ptr(ctx.stack), ptr(g), ptr(yp), ptr(aux), ptr(dW), ptr(db), N, Fout, K,
+                                    ptr(ws), nbytes, _stream()), 'cg_cheb_dw_pooled')
+        ctx.stack = None
+        return None, dW, db, None, None
+
+
+_first_layer_fusion = True
+
+
+def set_first_layer_fusion(flag):
+    """Allow (default) or forbid the fused first-layer node (tests compare both paths)."""
+    global _first_layer_fusion
+    _first_layer_fusion = bool(flag)
+
+
+def first_layer_supported(x, W, bias, L, K, act, p, kind, lmax=2):
+    """True when pool(brelu(cheb_filter(x, W))) can run as the fused first-layer node: scalar input signal that needs
+    no gradient, relu, max pooling of 4, one bias per filter (or none), a shape the streaming dW kernel takes."""
+    if not _first_layer_fusion or x.is_meta or x.dim() != 3 or x.shape[2] != 1 or x.requires_grad or not save_stack_enabled():
+        return False
+    if bias is not None and bias.numel() != W.shape[1]:
+        return False
+    act = ACT[act] if isinstance(act, str) else int(act)
+    kind = 1 if kind in (1, 'max') else 2
+    handle = get_handle(L, lmax)
+    return bool(_native.lib().cg_cheb_dw_pooled_supported(handle.handle, int(x.shape[0]), int(W.shape[1]), int(K), int(p), act,
+                                                          kind, 0 if bias is None else 1))
+
+
+def first_layer(x, W, bias, L, K, lmax=2):
+    """pool_max4(relu(cheb_filter(x, W) + bias)); check first_layer_supported first."""
+    return FirstLayerFn.apply(x, W, bias, get_handle(L, lmax), int(K))
+
+
 def bias_act_pool_supported(act, p, kind):
     act = ACT[act] if isinstance(act, str) else int(act)
     kind = 1 if kind in (1, 'max') else 2

@@ -158,6 +158,19 @@ int cg_bias_act_pool_bwd(const float *dev_gy, const float *dev_y, const uint8_t 
                          float *dev_dbias, int N, int M, int F, int p, int bias_kind, int act, int kind,
                          void *stream);
 
+/* ---- first-layer fusion ------------------------------------------------------------------------------------ */
+/* Scalar-input layer (Fin = 1) followed by bias (per filter or none) + relu + max pooling of 4 (lib/models.py:226-257
+ * after :192-224): weight and bias gradient straight from the gradient of the POOLED output -- the pooling-backward
+ * pass and the 4x larger filter-output gradient are never formed.  dev_stack: the fp32 basis [K][N][M] that
+ * cg_cheb_filter_fwd_ex left behind (no CG_FILTER_STACK_PLANES); dev_g_pooled / dev_y_pooled / dev_aux [N][M/4][Fout]:
+ * gradient of the pooled output, pooled output and argmax bytes of cg_bias_act_pool_fwd; dev_dW [K][Fout]; dev_db
+ * [Fout] or NULL.  No input gradient (first layer).                                                                 */
+int cg_cheb_dw_pooled_supported(const cg_graph_t *g, int N, int Fout, int K, int p, int act, int kind, int bias_kind);
+size_t cg_cheb_dw_pooled_workspace_bytes(const cg_graph_t *g, int N, int Fout, int K);
+int cg_cheb_dw_pooled(const cg_graph_t *g, const float *dev_stack, const float *dev_g_pooled, const float *dev_y_pooled,
+                      const uint8_t *dev_aux, float *dev_dW, float *dev_db, int N, int Fout, int K, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
 /* ---- contractions over a caller-owned stack (row-partitioned filter, config C5) ------------------------- */
 /* lib/models.py:218-223 on a basis the caller built slab by slab (cg_cheb_step + halo exchange): dev_stack holds K
  * slabs [R][F] that are slab_stride ELEMENTS apart (>= R*F; the partition keeps halo rows behind every slab).

@@ -802,3 +802,51 @@ def test_partitioned_filter_single_rank_vs_oracle(ops, tf_ref, directed, Fin, Fo
     rdx, rdW = tf_ref.chebyshev5_backward(x[None], L, W, K, gy[None], lmax=3.5)
     close(dx, rdx[0])
     close(dW, rdW)
+
+
+# --------------------------------------------------------------------------- fused first layer
+@pytest.mark.parametrize('level,N,Fout,K,with_bias', [(0, 8, 32, 25, True), (1, 16, 64, 5, True), (2, 8, 32, 7, False),
+                                                     (0, 64, 32, 20, True)])
+def test_first_layer_fused_node_vs_separate_ops_and_oracle(ops, tf_ref, c2, level, N, Fout, K, with_bias):
+    """ops.first_layer (filter + bias/relu/max-pool-4 as one node; backward from the POOLED gradient straight to dW
+    and db) against the three separate ops (pooled values bit-equal) and against the oracle's gradients."""
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(31 + level + K)
+    x = rng.standard_normal((N, M, 1)).astype(np.float32)
+    W = (0.3 * rng.standard_normal((K, Fout))).astype(np.float32)
+    b = (0.2 * rng.standard_normal(Fout)).astype(np.float32) if with_bias else None
+    g = rng.standard_normal((N, M // 4, Fout)).astype(np.float32)
+    Wt = dev(W).requires_grad_(True)
+    bt = dev(b).requires_grad_(True) if with_bias else None
+    assert ops.first_layer_supported(dev(x), Wt, bt, L, K, 'relu', 4, 'max')
+    yp = ops.first_layer(dev(x), Wt, bt, L, K)
+    ypn, aux = (t.detach().cpu().numpy() for t in yp.grad_fn.saved_tensors)       # pooled output, argmax bytes
+    yp.backward(dev(g))
+    W2 = dev(W).requires_grad_(True)
+    b2 = dev(b).requires_grad_(True) if with_bias else None
+    ref = ops.bias_act_pool(ops.cheb_filter(dev(x), W2, L, K, grad_x=False), b2, 'relu', 4, 'max')
+    ref.backward(dev(g))
+    assert torch.equal(yp, ref)
+    close(Wt.grad, W2.grad.cpu().numpy())
+    # oracle.  The gradient is routed by the argmax of every pool group; among ~10^5..10^6 groups a near-tie or two
+    # resolves differently in the oracle's forward pass, so the routing uses the decisions the GPU made (its argmax
+    # bytes, checked to point at a maximal element of the oracle's own activations)
+    a = tf_ref.chebyshev5(x, L, W, K)
+    r = tf_ref.b1relu(a, b) if with_bias else np.maximum(a, 0)
+    close(yp, tf_ref.mpool1(r, 4))
+    rg = r.reshape(N, M // 4, 4, Fout)
+    picked = np.take_along_axis(rg, aux[:, :, None, :].astype(np.int64), axis=2)[:, :, 0, :]
+    assert np.abs(picked - rg.max(axis=2)).max() <= 1e-4 * np.abs(r).max()
+    ga = np.zeros((N, M // 4, 4, Fout), np.float32)
+    np.put_along_axis(ga, aux[:, :, None, :].astype(np.int64), (g * (ypn > 0))[:, :, None, :], axis=2)
+    ga = ga.reshape(N, M, Fout)
+    _, dW = tf_ref.chebyshev5_backward(x, L, W, K, ga)
+    close(Wt.grad, dW)
+    if with_bias:
+        close(bt.grad, ga.sum(axis=(0, 1)))
+        close(bt.grad, b2.grad.cpu().numpy())
+    # an input that needs a gradient, other pool sizes: not this node
+    assert not ops.first_layer_supported(dev(x).requires_grad_(True), Wt, bt, L, K, 'relu', 4, 'max')
+    assert not ops.first_layer_supported(dev(x), Wt, bt, L, K, 'relu', 2, 'max')
+    assert not ops.first_layer_supported(dev(x), Wt, bt, L, K, 'tanh', 4, 'max')
