@@ -162,6 +162,25 @@ class GraphConvOps(object):
         return kept
 
 
+class _L2LossSum(torch.autograd.Function):
+    """sum_i tf.nn.l2_loss(w_i) = sum_i 0.5 * ||w_i||^2 (upstream cgcnn regulariser) as one autograd node: two
+    multi-tensor kernels forward, one backward, instead of a pow / sum / mul / add chain per variable."""
+
+    @staticmethod
+    def forward(ctx, *ws):
+        ctx.save_for_backward(*ws)
+        norms = torch._foreach_norm(list(ws), 2)
+        return 0.5 * torch.stack(norms).square().sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(torch._foreach_mul(list(ctx.saved_tensors), g))
+
+
+def l2_loss_sum(ws):
+    return _L2LossSum.apply(*ws)
+
+
 class cgcnn(GraphConvOps, GraphModel):
     """Graph CNN with Chebyshev filters.
 
@@ -278,8 +297,8 @@ class cgcnn(GraphConvOps, GraphModel):
     def loss(self, logits, labels, regularization):
         """softmax cross-entropy + L2 on the regularised variables (upstream cgcnn loss)."""
         ce = torch.nn.functional.cross_entropy(logits, labels)
-        if regularization:
-            ce = ce + regularization * sum(0.5 * (w ** 2).sum() for w in self.regularizers)
+        if regularization and self.regularizers:
+            ce = ce + regularization * l2_loss_sum(self.regularizers)
         return ce
 
     def evaluate(self, data, labels, sess=None):
