@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
             nlen[i] = p.rowptr[m + 1] - p.rowptr[m];
             a_g[i] = 4u * (uint32_t)(s * M * Fin + 4 * l);
             a_soff[i] = 4u * (uint32_t)(r * Fin + 4 * l);
-            a_stoff[i] = (uint32_t)((l >> 1) * (int)p.lbo_a + (r >> 3) * 128 + (r & 7) * 16 + (l & 1) * 8);
+            // the even lane of a pair stores the 16-byte hi octet (its 4 features and its partner's), the odd lane the
+            // mid octet: with LBO = 32 and plane = 16 (mod 128) the 8 lanes of a row fill exactly one 128-byte wavefront
+            a_stoff[i] = (uint32_t)((l >> 1) * (int)p.lbo_a + r * 16) + ((l & 1) ? p.plane_bytes : 0u);
         }
     }
 #pragma unroll
@@ -311,12 +313,20 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 }
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
-                    if (a_soff[i] < limb) {
-                        uint2 hi, mid;
-                        split4(res[i], hi, mid);
-                        sts64(st0 + a_stoff[i], hi);
-                        sts64(st0 + p.plane_bytes + a_stoff[i], mid);
-                    }
+                    uint2 hi, mid;
+                    split4(res[i], hi, mid);
+                    // lanes l and l ^ 1 hold the two halves of one feature octet of the same row (absent rows too:
+                    // the exchange runs on every lane, only the store is predicated)
+                    const bool odd = tid & 1;
+                    const uint2 send = odd ? hi : mid;
+                    uint2 recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                    const uint4 v = odd ? make_uint4(recv.x, recv.y, mid.x, mid.y) : make_uint4(hi.x, hi.y, recv.x, recv.y);
+                    if (a_soff[i] < limb)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st0 + a_stoff[i]), "r"(v.x), "r"(v.y),
+                                     "r"(v.z), "r"(v.w)
+                                     : "memory");
                 }
                 umma::fence_proxy_async();
                 if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
@@ -407,8 +417,9 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
         if (need > 8) break;        // res[] + item constants must stay in registers
         const int ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
         const uint32_t Rp = (uint32_t)tiles * 128u;
-        const uint32_t lbo_a = Rp * 16u + 64u;
-        const uint32_t plane = (uint32_t)(Fin / 8) * lbo_a;
+        // strides chosen for conflict-free staging stores (see a_stoff): LBO = 32, plane = 16 (mod 128)
+        const uint32_t lbo_a = Rp * 16u + 32u;
+        const uint32_t plane = (uint32_t)cg_align_up((size_t)(Fin / 8) * lbo_a, 128) + 16u;
         const uint32_t wplane = (uint32_t)Fin * Fout * 2u;
         const uint32_t slab = (uint32_t)cg_align_up((size_t)R * Fin * 4, 128);
         const int estride = std::max(2, (width + 1) & ~1);      // even: 16-byte aligned entry pairs
