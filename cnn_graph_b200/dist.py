@@ -20,6 +20,8 @@ def init_from_env(backend=None):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1 and not dist.is_initialized():
+        # NCCL writes its banner / debug log to stdout by default; keep stdout for the caller's own output
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29500')
         if backend is None:
