@@ -8,6 +8,7 @@ sum of the weight gradients, done here as ONE all-reduce over a single flat fp32
 (launch-latency bound at ~8 MB for the MNIST-shaped model, so one bucket, not many).
 """
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -20,8 +21,6 @@ def init_from_env(backend=None):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1 and not dist.is_initialized():
-        # NCCL writes its banner / debug log to stdout by default; keep stdout for the caller's own output
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29500')
         if backend is None:
@@ -29,6 +28,20 @@ def init_from_env(backend=None):
         if backend == 'nccl':
             torch.cuda.set_device(local_rank)
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        if backend == 'nccl':
+            # NCCL printf()s its version banner to stdout when the communicator is created (NCCL_DEBUG=WARN / VERSION).
+            # Create it now, with file descriptor 1 pointed at stderr, so that stdout stays the caller's (bench.py
+            # prints exactly one JSON line there).
+            sys.stdout.flush()
+            saved = os.dup(1)
+            try:
+                os.dup2(2, 1)
+                t = torch.zeros(1, device=torch.device('cuda', local_rank))
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
     return rank, world, local_rank
 
 
