@@ -83,6 +83,53 @@ class GradAllReducer:
             offset += g.numel()
 
 
+class OverlappedGradAllReducer:
+    """Gradient averaging that overlaps with the backward pass.
+
+    Parameters with at least `min_numel` elements (for cgcnn: the 3968 x 512 fc weight, 97 % of the bytes, whose
+    gradient is ready first) are all-reduced IN PLACE from a post-accumulate-grad hook, asynchronously, while autograd
+    keeps running the graph-conv backward kernels; the remaining small gradients go through one flat bucket after
+    the backward pass, and the step waits for the outstanding work before the optimiser runs.  NCCL averages in
+    the collective (ReduceOp.AVG); other backends sum and divide."""
+
+    def __init__(self, params, average=True, min_numel=1 << 16):
+        self.average = average
+        self.params = list(params)
+        self.big = [p for p in self.params if p.numel() >= min_numel]
+        big_ids = {id(p) for p in self.big}
+        self.small = [p for p in self.params if id(p) not in big_ids]
+        self._works = []
+        self._flat = GradAllReducer(average=average)
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.big]
+
+    def _active(self):
+        return dist.is_initialized() and dist.get_world_size() > 1
+
+    def _avg_in_collective(self):
+        return self.average and dist.get_backend() == 'nccl'
+
+    def _on_grad(self, p):
+        if not self._active() or p.grad is None:
+            return
+        op = dist.ReduceOp.AVG if self._avg_in_collective() else dist.ReduceOp.SUM
+        self._works.append((dist.all_reduce(p.grad, op=op, async_op=True), p))
+
+    def __call__(self, params=None):
+        if not self._active():
+            return
+        self._flat(self.small)
+        for work, p in self._works:
+            work.wait()
+            if self.average and not self._avg_in_collective():
+                p.grad.div_(dist.get_world_size())
+        self._works = []
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def max_over_ranks(value, device):
     """Max of a python float over all ranks (device-side all-reduce)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -39,6 +39,43 @@ def _worker(rank, world, port, out):
     torch.distributed.destroy_process_group()
 
 
+def _overlap_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    from cnn_graph_b200 import dist as cgdist
+    cgdist.init_from_env('gloo')
+    torch.manual_seed(0)
+    big = torch.nn.Parameter(torch.randn(40, 50))          # >= min_numel: all-reduced from the autograd hook
+    small = torch.nn.Parameter(torch.randn(7))             # flat bucket after the backward pass
+    unused = torch.nn.Parameter(torch.randn(3))
+    red = cgdist.OverlappedGradAllReducer([big, small, unused], average=True, min_numel=1000)
+    ok = True
+    for step in range(2):                                   # twice: the hooks and the bucket are reusable
+        for q in (big, small, unused):
+            q.grad = None
+        x = torch.full((50,), float(rank + 1 + step))
+        loss = (big @ x).sum() * (rank + 1) + (small * (rank + 2)).sum()
+        loss.backward()
+        red()
+        # d/d big = (rank+1) * x broadcast over rows; averaged over ranks 0, 1
+        want_big = sum((r + 1) * float(r + 1 + step) for r in range(world)) / world
+        want_small = sum(r + 2 for r in range(world)) / world
+        ok = ok and torch.allclose(big.grad, torch.full((40, 50), want_big)) and \
+            torch.allclose(small.grad, torch.full((7,), want_small)) and unused.grad is None
+    red.remove()
+    out[rank] = bool(ok)
+    torch.distributed.destroy_process_group()
+
+
+def test_overlapped_grad_allreduce_world2_gloo():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_overlap_worker, args=(2, port, out), nprocs=2, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
 def test_grad_allreduce_world2_gloo():
     port = _free_port()
     with mp.Manager() as mgr:
