@@ -130,6 +130,13 @@ size_t cg_fused_workspace(int Fin, int Fout, int K);
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
                  int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s, bool stack_planes = false);
 
+// One adjoint (Clenshaw) step on sample-major tensors with per-tensor row strides, batched over the samples, and the
+// regrouping of the weight rows by k that the product G = gy W^T needs (cg_spmm.cu).
+bool cg_clenshaw_step_supported(int F);
+int cg_run_clenshaw_step(const cg_graph *g, int transpose, const float *G, int64_t sg, const float *X1, int64_t s1,
+                         const float *X0, int64_t s0, float *out, int64_t so, int N, int F, float alpha, cudaStream_t s);
+int cg_run_regroup_w(const float *W, float *Wp, int Fin, int Fout, int K, cudaStream_t s);
+
 // Weight gradient of a first layer (Fa = 1) on the FFMA pipe, HBM-bound streaming (cg_dw_thin.cu).
 bool cg_dw_thin_supported(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);
 size_t cg_dw_thin_workspace(long long R, int Fa, int Fb, int K, int sm_count, size_t smem_limit);

@@ -88,8 +88,20 @@ extern "C" size_t cg_cheb_filter_bwd_workspace_bytes(const cg_graph_t *g, int N,
     const size_t part_b = dw_workspace(g, N, Fin, Fout, K);
     (void)need_dx;
     const int64_t R = (int64_t)N * g->M;
-    const size_t gdx = R > 0 && R < (int64_t)INT32_MAX ? cg_gemm_workspace((int)R, Fin, K * Fout) : 0;
+    size_t gdx = R > 0 && R < (int64_t)INT32_MAX ? cg_gemm_workspace((int)R, Fin, K * Fout) : 0;
+    if (R > 0 && R < (int64_t)INT32_MAX) gdx = std::max(gdx, cg_gemm_workspace((int)R, K * Fin, Fout));      // G = gy W^T
     return wide + cg_align_up(std::max(gdx, std::max(part_a, part_b)), 256) + cg_fused_workspace(Fin, Fout, K);
+}
+
+// Unfused adjoint recurrence for dx (see cg_cheb_filter_bwd_ex): pays off when dx is narrower than gy; needs
+// room for G, two step buffers and the regrouped weights inside the stack region of the workspace.
+static bool unfused_clenshaw_ok(const cg_graph *g, int N, int Fin, int Fout, int K, int flags, const void *gy, const void *dx) {
+    if (flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING | CG_FILTER_NO_CLENSHAW)) return false;
+    const int64_t R = (int64_t)N * g->M;
+    if (K < 2 || Fin >= Fout || R >= (int64_t)INT32_MAX || N > 65535 || !cg_clenshaw_step_supported(Fin)) return false;
+    if (((((uintptr_t)gy) | ((uintptr_t)dx)) & 15) != 0 || Fout % 4 != 0) return false;
+    const size_t need = sizeof(float) * ((size_t)(K + 2) * R * Fin + (size_t)K * Fin * Fout);
+    return need <= sizeof(float) * (size_t)K * R * Fout;      // the stack region holds K slabs of width max(Fin, Fout)
 }
 
 static bool aligned16(const void *a, const void *b, const void *c) {
@@ -270,6 +282,33 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
         } else if (fused) {
             // dx by the fused kernel on L~^T (Z_k never materialised)
             rc = cg_run_fused(g, 1, gy, W, dx, nullptr, N, Fout, Fin, K, true, wpack, s);
+            if (rc != CG_OK) return rc;
+        } else if (have_dW && unfused_clenshaw_ok(g, N, Fin, Fout, K, flags, gy, dx)) {
+            // adjoint recurrence without the fused kernel (wide gy, e.g. the 4H gates of the gconv-LSTM):
+            //   G = gy [W_0^T .. W_{K-1}^T]  (one GEMM, [R, K*Fin]),   b_k = G_k + 2 L~^T b_{k+1} - b_{k+2},
+            //   dx = G_0 + L~^T b_1 - b_2  -- K-1 sparse steps at the width of dx instead of the width of gy
+            const int64_t R = (int64_t)N * M;
+            float *G = stack, *buf0 = G + R * K * Fin, *buf1 = buf0 + R * Fin, *Wp = buf1 + R * Fin;
+            float *part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + stack_bytes(g, N, Fout > Fin ? Fout : Fin, K));
+            rc = cg_run_regroup_w(W, Wp, Fin, Fout, K, s);
+            if (rc == CG_OK)        // G[r, k*Fin + f] = sum_fo gy[r, fo] Wp[k*Fin + f, fo]
+                rc = cg_run_gemm(gy, Wp, G, (int)R, K * Fin, Fout, 0, 1, Fout, Fout, K * Fin, nullptr, 0, 0, 0, 0, 0, 0, part,
+                                 cg_gemm_workspace((int)R, K * Fin, Fout), s);
+            const float *b1 = G + (size_t)(K - 1) * Fin, *b2 = nullptr;       // b_{K-1} = G_{K-1}, b_K = 0
+            int64_t s1 = (int64_t)K * Fin, s2 = 0;
+            float *bufs[2] = {buf0, buf1};
+            int nb = 0;
+            for (int k = K - 2; k >= 1 && rc == CG_OK; --k) {
+                // out may alias b2 (read and written element-wise by the same thread); a G view is never overwritten
+                float *out = (b2 == buf0 || b2 == buf1) ? const_cast<float *>(b2) : bufs[nb++ & 1];
+                if (out == b1) out = bufs[nb++ & 1];
+                rc = cg_run_clenshaw_step(g, 1, G + (size_t)k * Fin, (int64_t)K * Fin, b1, s1, b2, s2, out, Fin, N, Fin, 2.0f, s);
+                b2 = b1;
+                s2 = s1;
+                b1 = out;
+                s1 = Fin;
+            }
+            if (rc == CG_OK) rc = cg_run_clenshaw_step(g, 1, G, (int64_t)K * Fin, b1, s1, b2, s2, dx, Fin, N, Fin, 1.0f, s);
             if (rc != CG_OK) return rc;
         } else {
             // Z_k = T_k(L~^T) gy materialised: dx = Z W^T, and dW = x^T Z_k if still missing

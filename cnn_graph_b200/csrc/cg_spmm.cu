@@ -9,6 +9,8 @@
 //                      HBM traffic = read X once + write the K-1 new slabs.
 //   k_spmm_step     -- one step per launch for operators too large for SMEM
 //                      (CSR from HBM/L2, 128-bit gathers along the column axis).
+#include <algorithm>
+
 #include "cg_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -109,6 +111,90 @@ static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, 
         k_spmm_step<4, 4, 8><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
     else
         k_spmm_step<1, 4, 6><<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, X1, X0, out, M, C, alpha, lpr);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// adjoint (Clenshaw) step on sample-major data, batched over the samples:
+//   out[n, m, :] = G[n, m, :] + alpha * sum_j L[m, j] X1[n, j, :] - X0[n, m, :]        (X0 may be null)
+// Every tensor has its own row stride (elements between consecutive (n, m) rows), so that G_k can be a column block
+// of the [N*M, K*F] product gy W^T and X1 the previous block.  block = 256 threads = (256 / lpr) rows x lpr lanes,
+// a lane owns 4 columns; blockIdx.y = sample.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 8)
+k_clenshaw_step(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
+                const float *__restrict__ G, int64_t sg, const float *__restrict__ X1, int64_t s1,
+                const float *__restrict__ X0, int64_t s0, float *__restrict__ out, int64_t so, int M, int F, float alpha,
+                int lpr) {
+    const int lane = threadIdx.x % lpr;
+    const int m = blockIdx.x * (256 / lpr) + threadIdx.x / lpr;
+    const int c = lane * 4;
+    if (m >= M || c >= F) return;
+    const int64_t row0 = (int64_t)blockIdx.y * M;          // first row of the sample
+    const int beg = rowptr[m], end = rowptr[m + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *x1 = X1 + row0 * s1 + c;
+    int e = beg;
+    for (; e + 3 < end; e += 4) {
+        int cc[4];
+        float vv[4];
+        float4 xx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            cc[u] = col[e + u];
+            vv[u] = val[e + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xx[u] = *reinterpret_cast<const float4 *>(x1 + (int64_t)cc[u] * s1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fma_acc(acc, vv[u], xx[u]);
+    }
+    for (; e < end; ++e) fma_acc(acc, val[e], *reinterpret_cast<const float4 *>(x1 + (int64_t)col[e] * s1));
+    const int64_t r = row0 + m;
+    const float4 g = *reinterpret_cast<const float4 *>(G + r * sg + c);
+    float4 o = make_float4(fmaf(alpha, acc.x, g.x), fmaf(alpha, acc.y, g.y), fmaf(alpha, acc.z, g.z), fmaf(alpha, acc.w, g.w));
+    if (X0 != nullptr) {
+        const float4 b = *reinterpret_cast<const float4 *>(X0 + r * s0 + c);
+        o.x -= b.x; o.y -= b.y; o.z -= b.z; o.w -= b.w;
+    }
+    *reinterpret_cast<float4 *>(out + r * so + c) = o;
+}
+
+// F % 4 == 0, F <= 128 * ... (one lane per 4 columns, at most 32 lanes per row: F <= 128); 16-byte aligned tensors and
+// strides that are multiples of 4
+bool cg_clenshaw_step_supported(int F) { return F % 4 == 0 && F >= 4 && F <= 128; }
+
+int cg_run_clenshaw_step(const cg_graph *g, int transpose, const float *G, int64_t sg, const float *X1, int64_t s1,
+                         const float *X0, int64_t s0, float *out, int64_t so, int N, int F, float alpha, cudaStream_t s) {
+    CG_REQUIRE(cg_clenshaw_step_supported(F) && sg % 4 == 0 && s1 % 4 == 0 && so % 4 == 0 && (X0 == nullptr || s0 % 4 == 0),
+               "clenshaw_step: unsupported width / strides (F=%d)", F);
+    CG_REQUIRE(((((uintptr_t)G) | ((uintptr_t)X1) | ((uintptr_t)X0) | ((uintptr_t)out)) & 15) == 0, "clenshaw_step: unaligned tensor");
+    CG_REQUIRE(N <= 65535, "clenshaw_step: too many samples for one launch (N=%d)", N);
+    const CgCsr &L = cg_side(g, transpose);
+    int lpr = 32;
+    while (lpr > 1 && lpr / 2 >= F / 4) lpr /= 2;
+    dim3 grid((unsigned)cg_ceil_div(g->M, 256 / lpr), (unsigned)N);
+    CgProfScope prof("clenshaw_step", s);
+    k_clenshaw_step<<<grid, 256, 0, s>>>(L.rowptr, L.col, L.val, G, sg, X1, s1, X0, s0, out, so, g->M, F, alpha, lpr);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// Wp[k*Fin + f][:] = W[f*K + k][:]   (rows of the filter weights regrouped by k)
+__global__ void __launch_bounds__(256) k_regroup_w(const float *__restrict__ W, float *__restrict__ Wp, int Fin, int Fout, int K) {
+    const int64_t total = (int64_t)Fin * K * Fout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / Fout;
+        const int fo = (int)(i - row * Fout);
+        const int k = (int)(row / Fin), f = (int)(row - (int64_t)k * Fin);
+        Wp[i] = W[((int64_t)f * K + k) * Fout + fo];
+    }
+}
+
+int cg_run_regroup_w(const float *W, float *Wp, int Fin, int Fout, int K, cudaStream_t s) {
+    const int64_t total = (int64_t)Fin * K * Fout;
+    k_regroup_w<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1184), 256, 0, s>>>(W, Wp, Fin, Fout, K);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

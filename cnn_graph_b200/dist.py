@@ -70,17 +70,18 @@ class GradAllReducer:
         if self._flat is None or self._flat.numel() != total or self._flat.device != grads[0].device:
             self._flat = torch.empty(total, dtype=torch.float32, device=grads[0].device)
         flat = self._flat
-        offset = 0
+        views, offset = [], 0
         for g in grads:
-            flat[offset:offset + g.numel()].copy_(g.reshape(-1))
+            views.append(flat[offset:offset + g.numel()].view_as(g))
             offset += g.numel()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        if self.average:
-            flat.div_(dist.get_world_size())
-        offset = 0
-        for g in grads:
-            g.copy_(flat[offset:offset + g.numel()].view_as(g))
-            offset += g.numel()
+        torch._foreach_copy_(views, grads)                       # one multi-tensor kernel each way
+        if self.average and dist.get_backend() == 'nccl':
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if self.average:
+                flat.div_(dist.get_world_size())
+        torch._foreach_copy_(grads, views)
 
 
 class OverlappedGradAllReducer:

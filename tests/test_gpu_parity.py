@@ -850,3 +850,29 @@ def test_first_layer_fused_node_vs_separate_ops_and_oracle(ops, tf_ref, c2, leve
     assert not ops.first_layer_supported(dev(x).requires_grad_(True), Wt, bt, L, K, 'relu', 4, 'max')
     assert not ops.first_layer_supported(dev(x), Wt, bt, L, K, 'relu', 2, 'max')
     assert not ops.first_layer_supported(dev(x), Wt, bt, L, K, 'tanh', 4, 'max')
+
+
+# --------------------------------------------------------------------------- unfused adjoint recurrence (wide gy)
+@pytest.mark.parametrize('N,Fin,Fout,K', [(2, 32, 128, 2), (3, 32, 128, 4), (2, 32, 160, 5), (2, 64, 256, 3)])
+def test_unfused_clenshaw_input_gradient(ops, tf_ref, N, Fin, Fout, K):
+    """dx when neither fused kernel takes the shape (32x32 grid, M = 1024: the slabs do not fit shared memory) and gy
+    is wider than dx: G = gy W^T by one GEMM, then K-1 batched adjoint steps at the width of dx -- against the oracle,
+    and against the forward-form path (CG_FILTER_NO_CLENSHAW) on the same inputs."""
+    from oracle import graph_ref
+    A = graph_ref.adjacency(*graph_ref.distance_sklearn_metrics(graph_ref.grid(32), k=8, metric='euclidean'))
+    L = graph_ref.laplacian(A, normalized=True)
+    M = L.shape[0]
+    rng = np.random.RandomState(7 * K + Fin)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    got = []
+    for flags in (ops.FILTER_DEFAULT, ops.FILTER_NO_CLENSHAW):
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, K, flags=flags)
+        y.backward(dev(gy))
+        close(xt.grad, dx)
+        close(Wt.grad, dW)
+        got.append(xt.grad.cpu().numpy())
+    close(got[0], got[1], 2e-5)
