@@ -10,10 +10,11 @@
 //   16 converter warps  per K stage (BK = 32) every warp loads 8 rows x 128 bytes (K-contiguous operand) or
 //                       8 k x 128 bytes (row-contiguous operand) with two 16-byte copies per lane, each warp-wide copy covering
 //                       four FULL 128-byte lines (a lane-per-row pattern costs one L1 wavefront per 32-byte sector
-//                       and saturates the L1 data pipe -- measured).  Lane pairs then swap halves by shuffle so that
-//                       every thread owns one whole 8-element octet, splits it and stores the 16-byte bf16 octets
-//                       into the hi and mid planes of the canonical UMMA layout; the strides between core-matrix
-//                       groups are padded by 16 bytes, which makes those stores bank-conflict free.  The loads are
+//                       and saturates the L1 data pipe -- measured).  Every lane splits its own 4-element pieces and
+//                       stores the 8-byte bf16 half octets into the hi and mid planes of the canonical UMMA layout;
+//                       the strides between core-matrix groups are padded by 32 bytes, which makes those 64-bit
+//                       stores bank-conflict free (a lane-pair exchange to full 16-byte octets cost 16 more
+//                       instructions per slot on the pipe that bounds the kernel: instruction issue).  The loads are
 //                       cp.async copies into raw fp32 rings (A two stages ahead, B one) laid out line by line; a
 //                       thread reads back only the 16-byte pieces it copied itself, so the rings need no barriers.
 //   1 issue warp        waits for "full", issues 3 x 2 MMAs of 128 x BN x 16 (elect.sync), commits to "empty";
@@ -37,11 +38,11 @@ constexpr int BK = 32;
 constexpr int MAX_STAGES = 6;
 constexpr int RAW_A = 3, RAW_B = 2;        // raw fp32 rings: A (streamed from HBM) is fetched two stages ahead of the
                                         // conversion, B (L2-resident for most callers) one stage ahead
-constexpr uint32_t MN_SBO = BK * 16 + 16;           // row-contiguous operand: stride between 8-row groups (padded)
+constexpr uint32_t MN_SBO = BK * 16 + 32;           // row-contiguous operand: stride between 8-row groups (padded)
 constexpr uint32_t EP_ROW = 80;                     // epilogue staging: 16 floats + 16 bytes of padding per row
 constexpr uint32_t EP_BYTES = 32 * EP_ROW;          // per epilogue warp
 
-__host__ __device__ constexpr uint32_t kc_lbo(int rows) { return (uint32_t)rows * 16u + 16u; }   // between k octets (padded)
+__host__ __device__ constexpr uint32_t kc_lbo(int rows) { return (uint32_t)rows * 16u + 32u; }   // between k octets (padded)
 __host__ __device__ constexpr uint32_t plane_bytes(int rows) {
     return (uint32_t)(rows / 8) * MN_SBO > 4u * kc_lbo(rows) ? (uint32_t)(rows / 8) * MN_SBO : 4u * kc_lbo(rows);
 }
@@ -106,9 +107,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 //                               the stage's 32 k
 //   MN (row contiguous source)  lines = k rows 8*(we&3) + (lane>>3) [load 0] and + 4 [load 1], row elements
 //                               32*(we>>2) + 4*(lane&7) .. + 3
-// After the pair exchange (lane ^ 1) the thread owns one octet:
-//   KC  row 8*we + (lane>>3) + 4*(lane&1), k octet (lane&7)>>1      MN  k 8*(we&3) + (lane>>3) + 4*(lane&1),
-//                                                                       row octet 4*(we>>2) + ((lane&7)>>1)
+// Each 4-element piece is half an octet of the operand layout: octet (lane&7)>>1 (along k for KC, along the rows
+// for MN), half lane&1, of row (KC) / k (MN) 8*we' + (lane>>3) (+ 4 for load 1).
 struct Slot {
     uint32_t off;       // element offset from the operand base: KC row (load 0) * ld; MN first row element
     int nv;             // KC: bit 0 / bit 1 = row of load 0 / load 1 inside the matrix; MN: valid row elements (0..4)
@@ -146,34 +146,26 @@ __device__ __forceinline__ void slot_fetch(const Slot &s, const float *src, int 
         cp_async16(raw + 512u, g1 < k_lim ? p1 : src, g1 < k_lim ? nb : 0u);
     }
 }
-// byte offset of the thread's octet (hi plane) inside the operand tile
+// byte offset (hi plane) of the 8-byte half octet that load 0 of the thread produces; load 1 lands 64 bytes further
+// (4 rows resp. 4 k down inside the same core matrix).  With the strides padded to 32 (mod 128) the 16 lanes of a
+// half-warp hit 16 different 8-byte bank pairs: the 64-bit stores are conflict-free.
 template <bool KC>
 __device__ __forceinline__ uint32_t slot_dst(int we, int lane, int rows) {
-    const uint32_t i = (uint32_t)((lane >> 3) + 4 * (lane & 1)), o = (uint32_t)((lane & 7) >> 1);
-    if (KC)             // K-major: (k/8) * LBO + (r/8) * 128 + (r%8) * 16
-        return o * kc_lbo(rows) + (uint32_t)we * 128u + i * 16u;
-    // MN-major: (r/8) * SBO + (k/8) * 128 + (k%8) * 16
-    return ((uint32_t)(we >> 2) * 4u + o) * MN_SBO + (uint32_t)(we & 3) * 128u + i * 16u;
+    const uint32_t i = (uint32_t)(lane >> 3), o = (uint32_t)((lane & 7) >> 1), half = (uint32_t)(lane & 1) * 8u;
+    if (KC)             // K-major: (k/8) * LBO + (r/8) * 128 + (r%8) * 16 + (k%8) * 2
+        return o * kc_lbo(rows) + (uint32_t)we * 128u + i * 16u + half;
+    // MN-major: (r/8) * SBO + (k/8) * 128 + (k%8) * 16 + (r%8) * 2
+    return ((uint32_t)(we >> 2) * 4u + o) * MN_SBO + (uint32_t)(we & 3) * 128u + i * 16u + half;
 }
-// pair exchange, split, store: even lanes keep load 0 and take the partner's load 0 as second half; odd lanes keep
-// load 1 as second half and take the partner's load 1 as first half
-__device__ __forceinline__ void slot_store(uint32_t hi_addr, uint32_t plane, const float4 v0, const float4 v1, int lane) {
-    const bool odd = lane & 1;
-    const float4 send = odd ? v0 : v1;
-    float4 recv;
-    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
-    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
-    recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
-    const float4 lo = odd ? recv : v0, hi4 = odd ? v1 : recv;
+// split the two 4-float pieces of the thread and store their bf16 hi / mid halves (8 bytes each)
+__device__ __forceinline__ void slot_store(uint32_t hi_addr, uint32_t plane, const float4 v0, const float4 v1) {
     uint2 h0, m0, h1, m1;
-    split4(lo, h0, m0);
-    split4(hi4, h1, m1);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(h0.x), "r"(h0.y), "r"(h1.x), "r"(h1.y)
-                 : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + plane), "r"(m0.x), "r"(m0.y), "r"(m1.x),
-                 "r"(m1.y)
-                 : "memory");
+    split4(v0, h0, m0);
+    split4(v1, h1, m1);
+    sts64(hi_addr, h0);
+    sts64(hi_addr + plane, m0);
+    sts64(hi_addr + 64u, h1);
+    sts64(hi_addr + plane + 64u, m1);
 }
 
 // TA / TB: the operand is stored with its row index (m resp. n) contiguous -> MN-major; otherwise K contiguous
@@ -302,7 +294,7 @@ __global__ void __launch_bounds__(PT, 1) k_gemm_pipe(const PipeParams p) {
             if (tr) p.trace[(gc - 8) * 8 + 0] = clock64();
             if (use > 0) mbar_wait_warp<0>(empty + slot, (use - 1) & 1, lane);
             if (tr) p.trace[(gc - 8) * 8 + 1] = clock64();
-            // all read-backs first (their latencies overlap), then exchange / split / store slot by slot
+            // all read-backs first (their latencies overlap), then split / store slot by slot
             const float4 a0 = lds128(raw_a + roa), a1 = lds128(raw_a + roa + 512u);
             float4 b00, b01, b10, b11;
             if (b0_on) {
@@ -313,9 +305,9 @@ __global__ void __launch_bounds__(PT, 1) k_gemm_pipe(const PipeParams p) {
                 b10 = lds128(raw_b1 + rob);
                 b11 = lds128(raw_b1 + rob + 512u);
             }
-            slot_store(sb + da, p.a_plane, a0, a1, lane);
-            if (b0_on) slot_store(sb + db0, p.b_plane, b00, b01, lane);
-            if (b1_on) slot_store(sb + db1, p.b_plane, b10, b11, lane);
+            slot_store(sb + da, p.a_plane, a0, a1);
+            if (b0_on) slot_store(sb + db0, p.b_plane, b00, b01);
+            if (b1_on) slot_store(sb + db1, p.b_plane, b10, b11);
             if (tr) p.trace[(gc - 8) * 8 + 2] = clock64();
             umma::fence_proxy_async();
             __syncwarp();
