@@ -167,14 +167,22 @@ size_t cg_gemm_workspace(int M, int N, int K);
 int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda, int ldb,
                 int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi, int b_slo,
                 void *workspace, size_t workspace_bytes, cudaStream_t s);
+//   a_mblk > 0 (transA only): row m of op(A) starts at element (m / a_mblk) * a_mbs + m % a_mblk -- all k slabs of a
+//   Chebyshev stack as one transposed operand.  Only the pipelined kernel implements it: check cg_gemm_mblocked_ok.
+bool cg_gemm_mblocked_ok(const float *A, const float *B, int M, int N, int K, int lda, int ldb, int a_mblk, long long a_mbs);
+int cg_run_gemm_mblocked(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int ldc, int a_mblk,
+                         long long a_mbs, void *workspace, size_t workspace_bytes, cudaStream_t s);
+// dW[f*K + k][:] = T[k*Fin + f][:]  (rows of a stacked gradient back into the order of the filter weights)
+int cg_run_regroup_dw(const float *T, float *dW, int Fin, int Fout, int K, cudaStream_t s);
 
 // Pipelined fast path of the same GEMM (cg_gemm_pipe.cu): 16-byte aligned operands, power-of-two K blocks
 bool cg_gemm_pipe_eligible(const float *A, const float *B, int M, int N, int K, int lda, int ldb, int transA, int transB,
-                           int a_kblk, long long a_kbs, int b_kblk);
+                           int a_kblk, long long a_kbs, int b_kblk, int a_mblk = 0, long long a_mbs = 0);
 size_t cg_gemm_pipe_workspace(int M, int N, int K, int sm_count);
 int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda,
                      int ldb, int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi,
-                     int b_slo, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s);
+                     int b_slo, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s, int a_mblk = 0,
+                     long long a_mbs = 0);
 int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s);
 
 // Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).

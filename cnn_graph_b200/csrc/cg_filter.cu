@@ -23,6 +23,27 @@ extern "C" size_t cg_cheb_filter_fwd_workspace_bytes(const cg_graph_t *g, int N,
     return (K > 1 ? stack_bytes(g, N, Fin, K) : 0) + gws + cg_fused_workspace(Fin, Fout, K);
 }
 
+// dW = stack^T T for all k in ONE tensor-core GEMM: the K slabs [R][Fa] form a transposed operand whose rows
+// m = k*Fa + a are blocked by Fa (cg_run_gemm_mblocked); the [K*Fa][Fb] result is regrouped into W's row order.
+// `scratch` holds K*Fa*Fb floats followed by the GEMM's split-K partials.
+static size_t dw_allk_workspace(int64_t R, int Fa, int Fb, int K) {
+    if (R <= 0 || R >= (int64_t)INT32_MAX) return 0;
+    return cg_align_up(sizeof(float) * (size_t)K * Fa * Fb, 256) + cg_gemm_workspace(K * Fa, Fb, (int)R);
+}
+static bool dw_allk_ok(const float *stack, int64_t slab_stride, const float *T, int64_t R, int Fa, int Fb, int K) {
+    if (R <= 0 || R >= (int64_t)INT32_MAX || (Fa & (Fa - 1)) != 0) return false;
+    return cg_gemm_mblocked_ok(stack, T, K * Fa, Fb, (int)R, Fa, Fb, Fa, slab_stride);
+}
+static int run_dw_allk(const float *stack, int64_t slab_stride, const float *T, float *dW, int64_t R, int Fa, int Fb, int K,
+                       void *scratch, cudaStream_t s) {
+    float *tmp = reinterpret_cast<float *>(scratch);
+    void *gws = reinterpret_cast<char *>(scratch) + cg_align_up(sizeof(float) * (size_t)K * Fa * Fb, 256);
+    int rc = cg_run_gemm_mblocked(stack, T, tmp, K * Fa, Fb, (int)R, Fa, Fb, Fb, Fa, slab_stride, gws,
+                                  cg_gemm_workspace(K * Fa, Fb, (int)R), s);
+    if (rc == CG_OK) rc = cg_run_regroup_dw(tmp, dW, Fa, Fb, K, s);
+    return rc;
+}
+
 // stack^T x plain: tensor-core kernel when the shape allows it, FFMA kernel otherwise
 static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const size_t a = cg_stack_t_plain_workspace(N, g->M, Fa, Fb, K, g->sm_count);
@@ -31,7 +52,8 @@ static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const size_t c = R < (int64_t)INT32_MAX ? cg_gemm_workspace(Fa, Fb, (int)R) : 0;       // per-k GEMM, split over R
     const size_t d = cg_dw_planes_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
     const size_t e = cg_dw_thin_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
-    return std::max(std::max(a, std::max(d, e)), std::max(b, c));
+    const size_t f = std::max(dw_allk_workspace(R, Fa, Fb, K), dw_allk_workspace(R, Fb, Fa, K));
+    return std::max(std::max(a, std::max(d, std::max(e, f))), std::max(b, c));
 }
 
 // stack^T x plain for a scalar-signal stack (first layers): streaming FFMA kernel
@@ -53,7 +75,9 @@ static int run_dw(const cg_graph *g, const float *stack, const float *T, float *
         return cg_run_dw_umma(stack, T, dW, N, g->M, Fa, Fb, K, swap, sample_major, part, g->sm_count, g->smem_optin, s);
     const int64_t R = (int64_t)N * g->M;
     if (sample_major && !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) && R < (int64_t)INT32_MAX) {
-        // shapes the TMEM-resident kernel does not take (Fb > 256, ...): one tensor-core GEMM per k,
+        // shapes the TMEM-resident kernel does not take (Fb > 256, ...)
+        if (!swap && dw_allk_ok(stack, R * Fa, T, R, Fa, Fb, K)) return run_dw_allk(stack, R * Fa, T, dW, R, Fa, Fb, K, part, s);
+        // ... or one tensor-core GEMM per k,
         //   dW_k = stack_k^T T   (rows a*K + k)        or, swapped,   dW_k = T^T stack_k   (rows b*K + k)
         const size_t ws = cg_gemm_workspace(swap ? Fb : Fa, swap ? Fa : Fb, (int)R);
         for (int k = 0; k < K; ++k) {
@@ -357,7 +381,7 @@ extern "C" int cg_cheb_filter_bwd_ex(const cg_graph_t *g, const float *x, const 
 extern "C" size_t cg_cheb_contract_workspace_bytes(int64_t R, int Fin, int Fout, int K) {
     if (R <= 0 || R >= (int64_t)INT32_MAX || Fin <= 0 || Fout <= 0 || K < 1) return 0;
     const size_t a = cg_gemm_workspace((int)R, Fout, K * Fin), b = cg_gemm_workspace((int)R, Fin, K * Fout);
-    const size_t c = cg_gemm_workspace(Fin, Fout, (int)R);
+    const size_t c = std::max(cg_gemm_workspace(Fin, Fout, (int)R), dw_allk_workspace(R, Fin, Fout, K));
     return std::max(a, std::max(b, c));
 }
 
@@ -389,6 +413,8 @@ extern "C" int cg_cheb_contract_dw(const float *stack, int64_t slab_stride, cons
         return CG_OK;
     }
     CG_REQUIRE(stack && gy && slab_stride >= R * Fin, "cg_cheb_contract_dw: bad stack");
+    if (dw_allk_ok(stack, slab_stride, gy, R, Fin, Fout, K) && workspace_bytes >= dw_allk_workspace(R, Fin, Fout, K))
+        return run_dw_allk(stack, slab_stride, gy, dW, R, Fin, Fout, K, workspace, s);
     // dW[f*K + k, fo] = sum_r stack_k[r, f] gy[r, fo]: one GEMM per k into rows k, K + k, ... of dW
     for (int k = 0; k < K; ++k) {
         const int rc = cg_run_gemm(stack + (size_t)k * slab_stride, gy, dW + (size_t)k * Fout, Fin, Fout, (int)R, 1, 0, Fin,

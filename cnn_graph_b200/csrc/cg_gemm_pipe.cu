@@ -55,6 +55,9 @@ struct PipeParams {
     // K blocking (see cg_common.cuh): block index = k >> sh, index inside = k & mask (sh = 31: not blocked)
     int a_sh, a_mask, b_sh, b_mask, b_shi, b_slo;
     long long a_kbs;
+    // M blocking of a row-contiguous A (TA): element offset of row m = (m >> a_msh) * a_mbs + (m & a_mmask)
+    int a_msh, a_mmask;
+    long long a_mbs;
     uint32_t a_plane, b_plane, off_b, stage_bytes, off_raw_a, off_raw_b, raw_b_bytes, off_ep, off_bar, tmem_cols;
 };
 
@@ -115,7 +118,8 @@ struct Slot {
 };
 
 template <bool KC>
-__device__ __forceinline__ void slot_bind(Slot &s, int we, int lane, int ld, int r0, int r_lim) {
+__device__ __forceinline__ void slot_bind(Slot &s, int we, int lane, int ld, int r0, int r_lim, int msh = 31, int mmask = 0x7fffffff,
+                                          long long mbs = 0) {
     if (KC) {
         const int r = r0 + 8 * we + (lane >> 3);
         s.nv = (r < r_lim ? 1 : 0) | (r + 4 < r_lim ? 2 : 0);
@@ -123,7 +127,7 @@ __device__ __forceinline__ void slot_bind(Slot &s, int we, int lane, int ld, int
     } else {
         const int c = r0 + 32 * (we >> 2) + 4 * (lane & 7);
         s.nv = max(0, min(4, r_lim - c));
-        s.off = (uint32_t)(s.nv > 0 ? c : 0);
+        s.off = s.nv > 0 ? (uint32_t)((long long)(c >> msh) * mbs + (c & mmask)) : 0u;
     }
 }
 // KC: blocked element address  base + (k >> sh) * kbs + (k & mask);   MN: source row (k >> sh) * shi + (k & mask) * slo
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(PT, 1) k_gemm_pipe(const PipeParams p) {
             int m0, n0, sp;
             item(ca.wi, m0, n0, ca.kbeg, ca.kend, sp);
             ca.nst = (ca.kend - ca.kbeg + BK - 1) / BK;
-            slot_bind<!TA>(sa, warp, lane, p.lda, m0, p.M);
+            slot_bind<!TA>(sa, warp, lane, p.lda, m0, p.M, p.a_msh, p.a_mmask, p.a_mbs);
         };
         auto bind_b = [&]() {
             int m0, n0, sp;
@@ -500,12 +504,15 @@ extern "C" int cg_debug_gemm_trace(long long *dev_buf) {
 size_t cg_gemm_pipe_workspace(int M, int N, int K, int sm_count) { return pipe_plan(M, N, K, sm_count).ws; }
 
 bool cg_gemm_pipe_eligible(const float *A, const float *B, int M, int N, int K, int lda, int ldb, int transA, int transB,
-                           int a_kblk, long long a_kbs, int b_kblk) {
+                           int a_kblk, long long a_kbs, int b_kblk, int a_mblk, long long a_mbs) {
+    if (a_mblk > 0 && (!transA || pow2_shift(a_mblk) < 2 || (a_mbs & 3) != 0 ||
+                       (long long)cg_ceil_div(M, a_mblk) * a_mbs >= (1LL << 32)))
+        return false;
     // row offsets are kept as 32-bit element counts
     if ((long long)(transA ? 1 : M) * lda >= (1LL << 32) || (long long)(transB ? N : 1) * ldb >= (1LL << 32)) return false;
     (void)K;
     if (((((uintptr_t)A) | ((uintptr_t)B)) & 15) != 0 || (lda & 3) != 0 || (ldb & 3) != 0) return false;
-    if (a_kblk > 0 && (pow2_shift(a_kblk) < 3 || (a_kbs & 3) != 0)) return false;
+    if (a_kblk > 0 && (pow2_shift(a_kblk) < 2 || (a_kbs & 3) != 0)) return false;      // 16-byte pieces never straddle a block
     if (b_kblk > 0 && pow2_shift(b_kblk) < 0) return false;
     return true;
 }
@@ -513,7 +520,8 @@ bool cg_gemm_pipe_eligible(const float *A, const float *B, int M, int N, int K, 
 // same contract as cg_run_gemm (cg_gemm_umma.cu); the caller has checked cg_gemm_pipe_eligible
 int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda,
                      int ldb, int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi,
-                     int b_slo, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s) {
+                     int b_slo, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s, int a_mblk,
+                     long long a_mbs) {
     PipePlan pl = pipe_plan(M, N, K, sm_count);
     CG_REQUIRE(pl.ws == 0 || (workspace && workspace_bytes >= pl.ws), "cg_gemm_f32: workspace too small (%zu < %zu bytes)",
                workspace_bytes, pl.ws);
@@ -542,6 +550,9 @@ int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int
     pp.b_mask = b_kblk > 0 ? b_kblk - 1 : 0x7fffffff;
     pp.b_shi = b_kblk > 0 ? b_shi : 0;
     pp.b_slo = b_kblk > 0 ? b_slo : 1;
+    pp.a_msh = a_mblk > 0 ? pow2_shift(a_mblk) : 31;
+    pp.a_mmask = a_mblk > 0 ? a_mblk - 1 : 0x7fffffff;
+    pp.a_mbs = a_mblk > 0 ? a_mbs : 0;
     const unsigned grid = (unsigned)std::min(pp.n_work, sm_count);
     {
         CgProfScope prof("gemm_umma", s);

@@ -347,3 +347,17 @@ extern "C" int cg_gemm_f32(const float *A, const float *B, float *C, int M, int 
     return cg_run_gemm(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, 0, 0, 0, 0, 0, workspace,
                        workspace_bytes, (cudaStream_t)stream);
 }
+
+bool cg_gemm_mblocked_ok(const float *A, const float *B, int M, int N, int K, int lda, int ldb, int a_mblk, long long a_mbs) {
+    return a_mblk > 0 && cg_gemm_pipe_eligible(A, B, M, N, K, lda, ldb, 1, 0, 0, 0, 0, a_mblk, a_mbs);
+}
+
+int cg_run_gemm_mblocked(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int ldc, int a_mblk,
+                         long long a_mbs, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+    CG_REQUIRE(cg_gemm_mblocked_ok(A, B, M, N, K, lda, ldb, a_mblk, a_mbs), "cg_run_gemm_mblocked: operands not eligible");
+    int dev = 0, sms = 148;
+    CG_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return cg_run_gemm_pipe(A, B, C, M, N, K, 1, 0, lda, ldb, ldc, nullptr, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes, sms, s,
+                            a_mblk, a_mbs);
+}

@@ -192,6 +192,24 @@ __global__ void __launch_bounds__(256) k_regroup_w(const float *__restrict__ W, 
     }
 }
 
+// dW[f*K + k][:] = T[k*Fin + f][:]
+__global__ void __launch_bounds__(256) k_regroup_dw(const float *__restrict__ T, float *__restrict__ dW, int Fin, int Fout, int K) {
+    const int64_t total = (int64_t)Fin * K * Fout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / Fout;
+        const int fo = (int)(i - row * Fout);
+        const int k = (int)(row / Fin), f = (int)(row - (int64_t)k * Fin);
+        dW[((int64_t)f * K + k) * Fout + fo] = T[i];
+    }
+}
+
+int cg_run_regroup_dw(const float *T, float *dW, int Fin, int Fout, int K, cudaStream_t s) {
+    const int64_t total = (int64_t)Fin * K * Fout;
+    k_regroup_dw<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1184), 256, 0, s>>>(T, dW, Fin, Fout, K);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
 int cg_run_regroup_w(const float *W, float *Wp, int Fin, int Fout, int K, cudaStream_t s) {
     const int64_t total = (int64_t)Fin * K * Fout;
     k_regroup_w<<<(unsigned)std::min<int64_t>(cg_ceil_div(total, 256), 1184), 256, 0, s>>>(W, Wp, Fin, Fout, K);

@@ -242,6 +242,14 @@ def cheb_filter(x, W, L, K, lmax=2, grad_x=True, flags=FILTER_DEFAULT):
     """Functional Chebyshev filter; ``L`` is a scipy Laplacian (rescaled here) or a GraphHandle."""
     if x.is_meta:     # shape tracing while a model declares its variables (no device work)
         return x.new_empty((x.shape[0], x.shape[1], W.shape[1]))
+    Fin = int(x.shape[2])
+    if Fin > 1 and Fin % 4 != 0 and W.shape[1] > 128 and W.shape[0] == Fin * K:
+        # narrow inputs under wide outputs (the x path of the gconv-LSTM: Fin = 2, Fout = 4H): zero features up to a
+        # multiple of 4 keep every operand 16-byte aligned for the pipelined tensor-core GEMM.  W rows are f*K + k, so
+        # the rows of the extra features are appended; autograd slices the gradients back.
+        pad = 4 - Fin % 4
+        x = torch.cat([x, x.new_zeros((x.shape[0], x.shape[1], pad))], dim=2)
+        W = torch.cat([W, W.new_zeros((pad * K, W.shape[1]))], dim=0)
     return ChebFilterFn.apply(x, W, get_handle(L, lmax), int(K), bool(grad_x), int(flags))
 
 
