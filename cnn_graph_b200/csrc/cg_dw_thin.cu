@@ -14,8 +14,8 @@
 // POOLED variant (first layer followed by bias + relu + max pooling of 4, lib/models.py:226-257): the kernel takes
 // the gradient of the POOLED output instead of gy.  Pool groups are 4 consecutive rows, so per group and feature
 // gy has at most one non-zero, at the argmax row, equal to the pooled gradient where the pooled output is positive:
-// the weights g[j] = (argmax == j) ? gp * [yp > 0] : 0 feed the unchanged FMA loop, the bias gradient is the sum of
-// those gp, and neither the pooling-backward kernel nor the 4x larger gy ever exist.
+// each lane reads the basis value of its argmax row and does one FMA per k with gp * [yp > 0]; the bias gradient is the
+// sum of those weights, and neither the pooling-backward kernel nor the 4x larger gy ever exist.
 #include <algorithm>
 
 #include "cg_common.cuh"
@@ -109,25 +109,31 @@ __global__ void __launch_bounds__(TT, 1) k_dw_thin(const ThinParams p) {
             const float *xs = reinterpret_cast<const float *>(smem + (size_t)s * p.stage_bytes);
             const float *gs = reinterpret_cast<const float *>(smem + (size_t)s * p.stage_bytes + p.off_g);
             for (int r = 4 * warp; r < rows; r += 4 * TW) {         // rows % 4 == 0 (R % 4 == 0 is required)
-                float g[4][NF];
-                if (!POOLED) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) g[j][f] = gs[(r + j) * Fb + lane + 32 * f];
-                } else {
+                if (POOLED) {
+                    // one non-zero per group and feature: read the basis value of the argmax row directly (the lanes'
+                    // addresses differ by at most 12 bytes: one wavefront) and do a single FMA per k
                     const float *ys = reinterpret_cast<const float *>(smem + (size_t)s * p.stage_bytes + p.off_y);
                     const unsigned char *as = smem + (size_t)s * p.stage_bytes + p.off_a;
+                    float gv[NF];
+                    const float *xa[NF];
 #pragma unroll
                     for (int f = 0; f < NF; ++f) {
                         const int i = (r >> 2) * Fb + lane + 32 * f;
-                        const float gv = ys[i] > 0.f ? gs[i] : 0.f;         // relu'(pooled output) * pooled gradient
-                        const int a = as[i];
-                        accb[f] += gv;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) g[j][f] = a == j ? gv : 0.f;
+                        gv[f] = ys[i] > 0.f ? gs[i] : 0.f;                  // relu'(pooled output) * pooled gradient
+                        xa[f] = xs + r + as[i];
+                        accb[f] += gv[f];
                     }
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) acc[k][f] = fmaf(xa[f][k * RC], gv[f], acc[k][f]);
+                    continue;
                 }
+                float g[4][NF];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) g[j][f] = gs[(r + j) * Fb + lane + 32 * f];
 #pragma unroll
                 for (int k = 0; k < KT; ++k) {
                     const float4 x = *reinterpret_cast<const float4 *>(xs + k * RC + r);
