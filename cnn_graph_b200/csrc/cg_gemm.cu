@@ -299,27 +299,49 @@ k_stack_t_plain(const float *__restrict__ stack, const float *__restrict__ T, fl
 
 // dW[...] = sum_split part[split][q][b];  q = k*Fa + a
 //   direct: dW[(a*K + k) * Fb + b]      swap: dW[(b*K + k) * Fa + a]
+// A block owns 32 consecutive outputs; its 8 warps each sum every 8th partial (one coalesced 128-byte read per
+// partial) and the 8 group sums are added in a fixed order: deterministic, and enough loads in flight for the
+// 30 MB of partials the plane-streaming dW kernel leaves behind (a thread per output summing 148 values one after
+// the other took 25 us for them).
 __global__ void __launch_bounds__(256)
 k_reduce_partials(const float *__restrict__ part, float *__restrict__ dW, int splits, int Fa, int Fb, int K, int swap) {
+    __shared__ float red[8][32];
     const int64_t total = (int64_t)K * Fa * Fb;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * total + i];
-        const int b = (int)(i % Fb);
-        const int q = (int)(i / Fb);
-        const int k = q / Fa, a = q - k * Fa;
-        if (swap)
-            dW[((int64_t)b * K + k) * Fa + a] = s;
-        else
-            dW[((int64_t)a * K + k) * Fb + b] = s;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+        const int64_t i = base + lane;
+        float s0 = 0.f, s1 = 0.f;
+        if (i < total) {
+            int sp = grp;
+            for (; sp + 8 < splits; sp += 16) {
+                s0 += part[(int64_t)sp * total + i];
+                s1 += part[(int64_t)(sp + 8) * total + i];
+            }
+            if (sp < splits) s0 += part[(int64_t)sp * total + i];
+        }
+        red[grp][lane] = s0 + s1;
+        __syncthreads();
+        if (grp == 0 && i < total) {
+            float s = red[0][lane];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) s += red[g][lane];
+            const int b = (int)(i % Fb);
+            const int q = (int)(i / Fb);
+            const int k = q / Fa, a = q - k * Fa;
+            if (swap)
+                dW[((int64_t)b * K + k) * Fa + a] = s;
+            else
+                dW[((int64_t)a * K + k) * Fb + b] = s;
+        }
+        __syncthreads();
     }
 }
 
 int cg_reduce_partials(const float *part, float *dW, int splits, int Fa, int Fb, int K, bool swap, cudaStream_t s) {
     CgProfScope prof("reduce_partials", s);
     const int64_t total = (int64_t)K * Fa * Fb;
-    int64_t blocks = cg_ceil_div(total, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int64_t blocks = cg_ceil_div(total, 32);
+    if (blocks > 148 * 16) blocks = 148 * 16;
     k_reduce_partials<<<(unsigned)blocks, 256, 0, s>>>(part, dW, splits, Fa, Fb, K, swap ? 1 : 0);
     CG_LAUNCH_CHECK();
     return CG_OK;

@@ -223,6 +223,31 @@ __global__ void __launch_bounds__(256)
 k_gemm_reduce(const float *__restrict__ part, const float *__restrict__ bias, float *__restrict__ C, int M, int N, int ldc,
               int split, int relu) {
     const size_t total = (size_t)M * N;
+    if ((N & 3) == 0 && (ldc & 3) == 0 && ((((uintptr_t)part) | ((uintptr_t)C)) & 15) == 0) {
+        // four outputs per thread, two partial sums in flight per thread (same summation order for every output)
+        const size_t total4 = total / 4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            int sp = 0;
+            for (; sp + 1 < split; sp += 2) {
+                const float4 a = reinterpret_cast<const float4 *>(part + (size_t)sp * total)[i];
+                const float4 b = reinterpret_cast<const float4 *>(part + (size_t)(sp + 1) * total)[i];
+                s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+                s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+            }
+            if (sp < split) {
+                const float4 a = reinterpret_cast<const float4 *>(part + (size_t)sp * total)[i];
+                s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            }
+            float4 r = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+            const size_t e = i * 4;
+            const int m = (int)(e / N), n = (int)(e - (size_t)m * N);
+            if (bias) { r.x += bias[n]; r.y += bias[n + 1]; r.z += bias[n + 2]; r.w += bias[n + 3]; }
+            if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+            *reinterpret_cast<float4 *>(C + (size_t)m * ldc + n) = r;
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int sp = 0; sp < split; ++sp) s += part[(size_t)sp * total + i];
