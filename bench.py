@@ -98,7 +98,8 @@ def step_work(L, N):
         # dense head: fc1 (3968 -> 512) and logits (512 -> 10), forward + both gradients, fp32-equivalent flops
         'gemm_umma': {'bound': 'tensor', 'launches': [(0, 2.0 * N * 3968 * 512)] * 3 + [(0, 2.0 * N * 512 * 10)] * 3,
                       'note': 'fp32-equivalent flops (three bf16 MMAs each) against the dense bf16 peak'},
-        'contract_umma': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * (K[0] * 1 + F[0]), g1)]},
+        # (with bias / relu / max-pool 4 in its epilogue it writes the pooled values and argmax bytes, not y)
+        'contract_umma': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * K[0] + 5.0 * N * (M1 // P[0]) * F[0], g1)]},
     }
 
 

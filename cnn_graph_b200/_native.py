@@ -55,6 +55,9 @@ _SIGNATURES = {
     'cg_gemm_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'cg_cheb_dw_pooled_supported': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    'cg_cheb_first_layer_fwd_supported': (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
+    'cg_cheb_first_layer_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_void_p]),
     'cg_cheb_dw_pooled_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'cg_cheb_dw_pooled': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_void_p, c_size_t, c_void_p]),

@@ -157,8 +157,10 @@ int cg_run_dw_planes(const void *planes, const float *T, float *dW, long long R,
 
 // Tensor-core contraction of a sample-major basis that lives in HBM (cg_contract_umma.cu).
 bool cg_contract_umma_supported(int N, int M, int Fa, int J, int K, size_t smem_limit);
+//   yp != NULL: pooled epilogue (relu(y + bias) max-pooled over groups of 4 rows -> yp, aux [N*M/4][J]; y is not written)
 int cg_run_contract_umma(const float *stack, const float *W, float *y, int N, int M, int Fa, int J, int K, int sm_count,
-                         size_t smem_limit, cudaStream_t s);
+                         size_t smem_limit, cudaStream_t s, const float *bias = nullptr, float *yp = nullptr,
+                         unsigned char *aux = nullptr);
 
 // General fp32 GEMM on the tensor cores (cg_gemm_umma.cu) with optional K blocking of the operands:
 //   a_kblk > 0: A element (m, q) at A[(q / a_kblk) * a_kbs + m * lda + q % a_kblk]   (a Chebyshev stack [K][R][F])

@@ -31,9 +31,13 @@ struct CtParams {
     const float *stack;          // [K][R][Fa]
     const float *W;              // [Fa*K][J]  (row = f*K + k)
     float *y;                    // [R][J]
+    // pooled epilogue (first layer, lib/models.py:226-257): relu(y + bias) max-pooled over groups of 4 consecutive rows
+    const float *bias;           // [J] or NULL
+    float *yp;                   // [R/4][J]; non-NULL selects the pooled epilogue (y is not written)
+    unsigned char *aux;          // [R/4][J] first-max index inside the group (format of cg_bias_act_pool_fwd)
     long long R;
     int Fa, J, K, Q, Qp;         // Q = K*Fa, Qp = Q rounded up to 16
-    uint32_t ring_bytes, piece, stage_bytes, a_plane, b_plane, off_ring, off_stage, off_b, off_bar;
+    uint32_t ring_bytes, piece, stage_bytes, a_plane, b_plane, off_ring, off_stage, off_b, off_ep, off_bar;
 };
 
 __global__ void __launch_bounds__(XT, 1) k_contract_umma(const CtParams p) {
@@ -162,6 +166,37 @@ __global__ void __launch_bounds__(XT, 1) k_contract_umma(const CtParams p) {
                 float v[8];
                 umma::tmem_ld8(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)((c & 1) * (ROWS / 128) * J + t * J + c8 * 8), v);
                 umma::tmem_ld_wait();
+                if (p.yp != nullptr) {
+                    // 32 rows x 8 columns of this warp -> [column][row] in a padded tile (36 floats per column: the
+                    // 128-bit reads below hit 8 different bank groups), then one thread per (group of 4 rows, column)
+                    float *tile = reinterpret_cast<float *>(smem + p.off_ep) + (size_t)warp * (8 * 36);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) tile[j * 36 + lane] = v[j];
+                    __syncwarp();
+                    const int colj = lane & 7;
+                    const float b = p.bias != nullptr ? p.bias[c8 * 8 + colj] : 0.f;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int g = (lane >> 3) + 4 * h;
+                        const float4 y4 = *reinterpret_cast<const float4 *>(tile + colj * 36 + 4 * g);
+                        // same order as k_bias_act_pool_fwd: a = relu(y + b), the first maximum wins
+                        const float a0 = fmaxf(y4.x + b, 0.f), a1 = fmaxf(y4.y + b, 0.f), a2 = fmaxf(y4.z + b, 0.f),
+                                    a3 = fmaxf(y4.w + b, 0.f);
+                        float best = a0;
+                        int arg = 0;
+                        if (a1 > best) { best = a1; arg = 1; }
+                        if (a2 > best) { best = a2; arg = 2; }
+                        if (a3 > best) { best = a3; arg = 3; }
+                        const int row0 = t * 128 + 32 * qd + 4 * g;          // rows % 4 == 0: whole groups only
+                        if (row0 < rows) {
+                            const size_t o = (size_t)((rb + row0) >> 2) * J + c8 * 8 + colj;
+                            p.yp[o] = best;
+                            p.aux[o] = (unsigned char)arg;
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (r < rows) {
                     float *dst = p.y + (rb + r) * J + c8 * 8;
                     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -247,6 +282,8 @@ static CtPlan ct_plan(long long R, int Fa, int J, int K, size_t smem_limit) {
     cp.off_b = off;
     cp.b_plane = (uint32_t)(J / 8) * sbo;
     off += 2 * cp.b_plane;
+    cp.off_ep = off;
+    off += (uint32_t)(XC / 32) * 8 * 36 * 4;         // pooled epilogue: one [8][36] fp32 tile per compute warp
     if (off > smem_limit) return pl;
     cp.Q = Q;
     cp.Qp = Qp;
@@ -263,15 +300,20 @@ bool cg_contract_umma_supported(int N, int M, int Fa, int J, int K, size_t smem_
 }
 
 // stack [K][N*M][Fa] sample-major, W [Fa*K][J] (row = f*K + k), y [N*M][J]
+//   yp != NULL: pooled epilogue -- relu(y + bias) max-pooled over groups of 4 rows into yp / aux [N*M/4][J]; y unused
 int cg_run_contract_umma(const float *stack, const float *W, float *y, int N, int M, int Fa, int J, int K, int sm_count,
-                         size_t smem_limit, cudaStream_t s) {
+                         size_t smem_limit, cudaStream_t s, const float *bias, float *yp, unsigned char *aux) {
     CtPlan pl = ct_plan((long long)N * M, Fa, J, K, smem_limit);
     CG_REQUIRE(pl.ok, "cg_run_contract_umma: shape not supported (Fa=%d J=%d K=%d)", Fa, J, K);
     CG_REQUIRE((((uintptr_t)stack | (uintptr_t)y) & 15) == 0, "cg_run_contract_umma: unaligned tensor");
+    CG_REQUIRE(yp == nullptr || (aux != nullptr && M % 4 == 0), "cg_run_contract_umma: pooled epilogue needs aux and M %% 4 == 0");
     CtParams &cp = pl.cp;
     cp.stack = stack;
     cp.W = W;
     cp.y = y;
+    cp.bias = bias;
+    cp.yp = yp;
+    cp.aux = aux;
     cp.R = (long long)N * M;
     cp.Fa = Fa;
     cp.J = J;

@@ -435,6 +435,24 @@ extern "C" int cg_cheb_dw_pooled_supported(const cg_graph_t *g, int N, int Fout,
     return cg_dw_thin_pooled_supported((long long)N * g->M, Fout, K, g->sm_count, g->smem_optin) ? 1 : 0;
 }
 
+// forward of the same layer in two launches: on-chip recurrence (the basis stays for the backward), then the contraction
+// with bias + relu + max pooling of 4 applied in its epilogue -- the [N, M, Fout] filter output is never written
+extern "C" int cg_cheb_first_layer_fwd_supported(const cg_graph_t *g, int N, int Fout, int K, int bias_kind) {
+    if (!cg_cheb_dw_pooled_supported(g, N, Fout, K, 4, 1, 1, bias_kind)) return 0;
+    return cg_basis_samples_supported(g, 0, N, 1) && cg_contract_umma_supported(N, g->M, 1, Fout, K, g->smem_optin) ? 1 : 0;
+}
+
+extern "C" int cg_cheb_first_layer_fwd(const cg_graph_t *g, const float *x, const float *W, const float *bias, float *stack_out,
+                                       float *y_pooled, uint8_t *aux, int N, int Fout, int K, void *stream) {
+    CG_REQUIRE(g != nullptr && x && W && stack_out && y_pooled && aux, "cg_cheb_first_layer_fwd: NULL argument");
+    CG_REQUIRE(cg_cheb_first_layer_fwd_supported(g, N, Fout, K, bias ? 1 : 0), "cg_cheb_first_layer_fwd: shape not supported");
+    CG_REQUIRE(((((uintptr_t)x) | ((uintptr_t)stack_out)) & 15) == 0, "cg_cheb_first_layer_fwd: unaligned tensor");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = cg_run_basis_samples(g, 0, x, stack_out, N, 1, K, s);
+    if (rc != CG_OK) return rc;
+    return cg_run_contract_umma(stack_out, W, nullptr, N, g->M, 1, Fout, K, g->sm_count, g->smem_optin, s, bias, y_pooled, aux);
+}
+
 extern "C" size_t cg_cheb_dw_pooled_workspace_bytes(const cg_graph_t *g, int N, int Fout, int K) {
     if (!g || N <= 0) return 0;
     return cg_dw_thin_pooled_workspace((long long)N * g->M, Fout, K, g->sm_count, g->smem_optin);

@@ -394,22 +394,27 @@ class FirstLayerFn(torch.autograd.Function):
         N, M, _ = x.shape
         Fout = W.shape[1]
         lib = _native.lib()
-        y = torch.empty((N, M, Fout), dtype=torch.float32, device=x.device)
-        nbytes = lib.cg_cheb_filter_fwd_workspace_bytes(handle.handle, N, 1, Fout, K, 0)
-        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
-        stack = torch.empty((K, N, M, 1), dtype=torch.float32, device=x.device)
-        check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, 1, Fout, K, ptr(ws), nbytes, 0,
-                                        _stream()), 'cg_cheb_filter_fwd_ex')
         bkind = 0
         if bias is not None:
             bias = _f32c(bias)
             if bias.numel() != Fout:
                 raise ValueError('bias must have Fout=%d entries, got %d' % (Fout, bias.numel()))
             bkind = 1
+        stack = torch.empty((K, N, M, 1), dtype=torch.float32, device=x.device)
         yp = torch.empty((N, M // 4, Fout), dtype=torch.float32, device=x.device)
         aux = torch.empty((N, M // 4, Fout), dtype=torch.uint8, device=x.device)
-        check(lib.cg_bias_act_pool_fwd(ptr(y), ptr(bias), ptr(yp), ptr(aux), N, M, Fout, 4, bkind, ACT['relu'], 1, _stream()),
-              'cg_bias_act_pool_fwd')
+        if _first_layer_epilogue and lib.cg_cheb_first_layer_fwd_supported(handle.handle, N, Fout, K, bkind):
+            # recurrence + contraction with bias / relu / pool in its epilogue: the [N, M, Fout] output is never written
+            check(lib.cg_cheb_first_layer_fwd(handle.handle, ptr(x), ptr(W), ptr(bias), ptr(stack), ptr(yp), ptr(aux), N, Fout, K,
+                                              _stream()), 'cg_cheb_first_layer_fwd')
+        else:
+            y = torch.empty((N, M, Fout), dtype=torch.float32, device=x.device)
+            nbytes = lib.cg_cheb_filter_fwd_workspace_bytes(handle.handle, N, 1, Fout, K, 0)
+            ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
+            check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, 1, Fout, K, ptr(ws), nbytes, 0,
+                                            _stream()), 'cg_cheb_filter_fwd_ex')
+            check(lib.cg_bias_act_pool_fwd(ptr(y), ptr(bias), ptr(yp), ptr(aux), N, M, Fout, 4, bkind, ACT['relu'], 1, _stream()),
+                  'cg_bias_act_pool_fwd')
         ctx.save_for_backward(yp, aux)
         ctx.stack, ctx.handle, ctx.K = stack, handle, K
         ctx.w_shape, ctx.bias_shape = tuple(W.shape), None if bias is None else tuple(bias.shape)
@@ -435,12 +440,18 @@ class FirstLayerFn(torch.autograd.Function):
 
 
 _first_layer_fusion = True
+_first_layer_epilogue = True      # bias / relu / pool inside the contraction's epilogue (False: separate pooling kernel)
 
 
 def set_first_layer_fusion(flag):
     """Allow (default) or forbid the fused first-layer node (tests compare both paths)."""
     global _first_layer_fusion
     _first_layer_fusion = bool(flag)
+
+
+def set_first_layer_epilogue(flag):
+    global _first_layer_epilogue
+    _first_layer_epilogue = bool(flag)
 
 
 def first_layer_supported(x, W, bias, L, K, act, p, kind, lmax=2):

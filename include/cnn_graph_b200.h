@@ -166,6 +166,12 @@ int cg_bias_act_pool_bwd(const float *dev_gy, const float *dev_y, const uint8_t 
  * gradient of the pooled output, pooled output and argmax bytes of cg_bias_act_pool_fwd; dev_dW [K][Fout]; dev_db
  * [Fout] or NULL.  No input gradient (first layer).                                                                 */
 int cg_cheb_dw_pooled_supported(const cg_graph_t *g, int N, int Fout, int K, int p, int act, int kind, int bias_kind);
+/* Forward of that layer without the [N, M, Fout] filter output: recurrence (the fp32 basis [K][N][M] is left in
+ * dev_stack_out for cg_cheb_dw_pooled), then the contraction with bias + relu + max pooling of 4 in its epilogue.
+ * dev_y_pooled / dev_aux [N][M/4][Fout] as written by cg_bias_act_pool_fwd.  bias_kind: 0 (dev_bias NULL) or 1.  */
+int cg_cheb_first_layer_fwd_supported(const cg_graph_t *g, int N, int Fout, int K, int bias_kind);
+int cg_cheb_first_layer_fwd(const cg_graph_t *g, const float *dev_x, const float *dev_W, const float *dev_bias,
+                            float *dev_stack_out, float *dev_y_pooled, uint8_t *dev_aux, int N, int Fout, int K, void *stream);
 size_t cg_cheb_dw_pooled_workspace_bytes(const cg_graph_t *g, int N, int Fout, int K);
 int cg_cheb_dw_pooled(const cg_graph_t *g, const float *dev_stack, const float *dev_g_pooled, const float *dev_y_pooled,
                       const uint8_t *dev_aux, float *dev_dW, float *dev_db, int N, int Fout, int K, void *workspace,

@@ -829,6 +829,13 @@ def test_first_layer_fused_node_vs_separate_ops_and_oracle(ops, tf_ref, c2, leve
     ref.backward(dev(g))
     assert torch.equal(yp, ref)
     close(Wt.grad, W2.grad.cpu().numpy())
+    # pooling inside the contraction's epilogue (default) and as a separate kernel: same bits
+    ops.set_first_layer_epilogue(False)
+    try:
+        yp_sep = ops.first_layer(dev(x), dev(W), None if b is None else dev(b), L, K)
+    finally:
+        ops.set_first_layer_epilogue(True)
+    assert torch.equal(yp, yp_sep)
     # oracle.  The gradient is routed by the argmax of every pool group; among ~10^5..10^6 groups a near-tie or two
     # resolves differently in the oracle's forward pass, so the routing uses the decisions the GPU made (its argmax
     # bytes, checked to point at a maximal element of the oracle's own activations)
