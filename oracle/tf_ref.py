@@ -1,11 +1,18 @@
 """Oracle restatement of the TensorFlow half of the hot path, in numpy.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED at the
-TF boundary: TensorFlow 1.x (``requirements.txt:7``, no version pin) cannot be
-installed here and the reference holds no golden vector for these ops.  The
-functions below follow the reference's op sequence literally (same layouts,
-same transposes, same order of the recurrence); the arithmetic of each TF op
-is restated from its documented meaning:
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PINNED: TensorFlow 1.x
+(``requirements.txt:7``, no version pin) cannot be installed here and the
+reference holds no golden vector for these ops, so the reference's own source
+files (``lib/filter.py``, ``lib/models.py``, ``lib/gconv_lstm.py``,
+``lib/gconvRNN.py``) were EXECUTED UNMODIFIED in the build container under a
+torch-backed ``tensorflow`` stand-in (``tests/golden/tf_shim.py``; generator
+``tests/golden/make_golden_tf.py``), outputs and autograd gradients stored in
+``tests/golden/tf_*.npz``; ``tests/test_oracle_tf_pinned.py`` checks every
+function below against them.  What remains outside the pin is TensorFlow's own
+kernel arithmetic (summation order inside its SpMM / GEMM), which the 1e-4
+tolerance covers.  The functions follow the reference's op sequence literally
+(same layouts, same transposes, same order of the recurrence); the arithmetic
+of each TF op is restated from its documented meaning:
 
 * ``tf.sparse_tensor_dense_matmul(L, x)`` after ``tf.sparse_reorder``  ->
   row-major CSR x dense, float32 (scipy ``csr_matvecs``; the same kernel the
@@ -76,6 +83,25 @@ def cheby_conv(x, L, lmax, feat_out, K, W):
     """lib/filter.py:45-95 with the weight supplied by the caller."""
     assert W.shape[1] == feat_out
     return chebyshev5(x, L, W, K, lmax)
+
+
+def fourier_conv(x, L, W, U=None):
+    """Dense spectral filter, lib/filter.py:11-42 == lib/models.py:129-157.
+
+    x [N, M, Fin], W [M, Fout, Fin] (one Fout x Fin matrix per graph frequency) ->
+    y [N, M, Fout] = U^T-side transform as the reference writes it: with Ut = U.T (U = eigenvectors of L,
+    ``graph.fourier``), xh = Ut x, yh[m] = W[m] xh[m], y = (yh^T Ut) re-laid out as N x M x Fout.
+    """
+    N, M, Fin = x.shape
+    if U is None:
+        U = graph_ref.fourier(L)[1]
+    Ut = np.asarray(U.T, np.float32)                       # tf.constant(U.T, dtype=tf.float32)
+    xh = np.transpose(x, (1, 2, 0)).reshape(M, Fin * N)     # M x Fin*N
+    xh = np.matmul(Ut, xh).reshape(M, Fin, N)
+    yh = np.matmul(W, xh)                                   # M x Fout x N (batched over the frequency index)
+    yh = np.transpose(yh).reshape(N * W.shape[1], M)        # tf.transpose without perm reverses: N x Fout x M
+    y = np.matmul(yh, Ut).reshape(N, W.shape[1], M)
+    return np.ascontiguousarray(np.transpose(y, (0, 2, 1)))
 
 
 def chebyshev2(x, L, W, K):
