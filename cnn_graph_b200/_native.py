@@ -66,6 +66,8 @@ _SIGNATURES = {
                                  c_void_p]),
     'cg_cheb_contract_dw': (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_size_t,
                                     c_void_p]),
+    'cg_bmm_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_i64, c_i64, c_i64, c_void_p]),
     'cg_perm_data': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     'cg_lstm_gates_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
                                   c_void_p]),

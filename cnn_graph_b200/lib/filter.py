@@ -3,14 +3,15 @@
 ``cheby_conv(x, L, lmax, feat_out, K, W=None)`` (reference lib/filter.py:45-95; copies at
 lib/models.py:416-460 and lib/gconvRNN.py:27-71) keeps its positional order, its weight
 layout ``[K*feat_in, feat_out]`` with row index ``fin*K + k``, and the creation of a
-``weights`` variable in the ambient scope when ``W`` is None.  The op chain behind it
+``weights`` variable in the ambient scope when ``W`` is None; ``fourier_conv`` (:11-42) is the
+dense-eigenbasis filter the fork's recorded runs used.  The op chain behind cheby_conv
 (SparseTensor staging, K-1 SpMM launches, growing concat, stack transpose, matmul) is
 replaced by the native kernels in ``cnn_graph_b200.ops``.
 """
 from .. import ops
 from . import variables
 
-__all__ = ['cheby_conv']
+__all__ = ['cheby_conv', 'fourier_conv']
 
 
 def cheby_conv(x, L, lmax, feat_out, K, W=None):
@@ -25,6 +26,12 @@ def cheby_conv(x, L, lmax, feat_out, K, W=None):
 
 
 def fourier_conv(x, L, lmax, Fout, K, W=None):
-    """The dense-EVD spectral filter of the reference (lib/filter.py:29-42) is outside the
-    Chebyshev hot path and is not provided."""
-    raise NotImplementedError('fourier_conv is out of scope of the B200 Chebyshev hot path')
+    """Dense spectral filter (lib/filter.py:29-42): x [N, M, Fin] -> [N, M, Fout] with one Fout x Fin matrix per graph
+    frequency, W [M, Fout, Fin] (created as ``weights`` in the ambient scope when None).  ``lmax`` and ``K`` are
+    accepted and ignored, as in the reference (K is overwritten by M there, :31)."""
+    N, M, Fin = (int(d) for d in x.shape)
+    if W is None:
+        W = variables.get_variable('weights', [M, Fout, Fin], variables.truncated_normal_initializer(0, 0.1))
+    if tuple(W.shape) != (M, Fout, Fin):
+        raise ValueError('fourier_conv: W must be [M, Fout, Fin] = [%d, %d, %d], got %r' % (M, Fout, Fin, tuple(W.shape)))
+    return ops.fourier_filter(x, W, L)

@@ -141,7 +141,8 @@ class GconvModel(GraphModel):
         self.num_hidden_conv = num_hidden_conv
         self.gate_variant = gate_variant
         self.output_keep_prob = output_keep_prob
-        self.dropout_masks = None          # optional list (per layer, per step) of [N, M, H] masks
+        self.dropout_masks = None          # optional masks [N, M, H]: [layer][step], or flat in DropoutWrapper call order
+        self._mask_cursor = 0
         self.build_graph(self.node_num, int(np.sum(self.feature_num)), self.out_feature_num)
 
     def to_string(self):
@@ -151,45 +152,145 @@ class GconvModel(GraphModel):
             self.infer_func, self.num_hidden_conv)
 
     def _inference(self, x, dropout):
+        self._mask_cursor = 0
         return getattr(self, self.infer_func)(x)
 
     def _filter(self, x, Fout):
         return getattr(filter_module, self.filter)(x, self.laplacian, self.lmax, Fout, self.kernel_num)
 
-    # ---- inference variants ---------------------------------------------------------
-    def _unstack_time(self, x):
+    # ---- inference variants (lib/gconv_lstm.py:264-607), selected by name through ``infer_func`` -------------
+    def _unstack_time(self, x, T=None, transposed=False):
+        """[N, M, C] -> T frames [N, M, C/T]: reshape to [N, M, C/T, T] and unstack the last axis
+        (lib/gconv_lstm.py:274-276); ``transposed`` is the extra (0, 1, 3, 2) transpose of :525-527."""
         N, M, C = (int(d) for d in x.shape)
-        T = self.num_time_steps_closeness
-        x = x.reshape(N, M, C // T, T)                        # lib/gconv_lstm.py:274, 405
+        T = self.num_time_steps_closeness if T is None else T
+        x = x.reshape(N, M, C // T, T)
+        if transposed:
+            x = x.transpose(2, 3)
+            return [x[..., t] for t in range(int(x.shape[3]))]
         return [x[..., t] for t in range(T)]
+
+    def _split_periods(self, x, counts):
+        """Channel blocks of 2*count features each, in order (closeness | period | trend; :327-331, :469-474)."""
+        out, begin = [], 0
+        for c in counts:
+            out.append(x[:, :, begin:begin + 2 * c])
+            begin += 2 * c
+        return out
+
+    def _conv_stack(self, x, nfilter, activation, init_activation=None, suffix=''):
+        """conv_init -> conv_layer_i residual layers -> output_layer (e.g. :298-319)."""
+        with self.variable_scope('conv_init' + suffix):
+            x = self.activation_function(self._filter(x, nfilter), init_activation or activation)
+        for i in range(self.conv_layer_num):
+            with self.variable_scope('conv_layer_{}'.format(i) + suffix):
+                x = self.residual_layer(x, nfilter, activation, 'residual_layer_{0}'.format(i))
+        with self.variable_scope('output_layer' + suffix):
+            return self._filter(x, self.out_feature_num)
+
+    def inference_lstm(self, x, dropout=None):
+        return None                                               # lib/gconv_lstm.py:270-271
 
     def inference_glstm(self, x):
         """gLSTM over the closeness frames, then an output filter (lib/gconv_lstm.py:273-283)."""
         outputs = self.glstm_layer(self._unstack_time(x), self.num_time_steps_closeness, self.lstm_layer_count)
         return self.fc_layer(outputs[-1], self.out_feature_num)
 
-    def inference_gconv(self, x):
-        """Plain residual graph-conv stack (lib/gconv_lstm.py:298-319)."""
-        with self.variable_scope('conv_init'):
-            x = ops.bias_act(self._filter(x, self.num_hidden), None, 'relu')
-        for i in range(self.conv_layer_num):
-            with self.variable_scope('conv_layer_{}'.format(i)):
-                x = self.residual_layer(x, self.num_hidden, 'relu', 'residual_layer_{0}'.format(i))
-        with self.variable_scope('output_layer'):
-            return self._filter(x, self.out_feature_num)
+    def inference_glstm_period_no_expand(self, x):
+        """lib/gconv_lstm.py:285-296.  As shipped this variant cannot run (float division inside tf.reshape, :288) and
+        it returns the LSTM output, not the output filter's; integer division is used here, the return value kept."""
+        assert self.num_time_steps_closeness == self.num_time_steps_period
+        x = self.glstm_layer(self._unstack_time(x), self.num_time_steps_closeness, self.lstm_layer_count)[-1]
+        self.fc_layer(x, self.out_feature_num)
+        return x
 
-    def inference_glstm_gconv_no_expand(self, x):
-        """gLSTM, then conv_init / residual layers / output filter (lib/gconv_lstm.py:402-428)."""
+    def inference_gconv(self, x):
+        """Plain residual graph-conv stack with tanh (lib/gconv_lstm.py:298-319)."""
+        return self._conv_stack(x, self.num_hidden, 'tanh')
+
+    def inference_gconv_period_no_expand(self, x):
+        """Same with relu (lib/gconv_lstm.py:321-342)."""
+        return self._conv_stack(x, self.num_hidden, 'relu')
+
+    def inference_gconv_period_expand(self, x):
+        """One conv stack per closeness / period / trend block, relu, concat, merge filter (lib/gconv_lstm.py:344-382)."""
+        blocks = self._split_periods(x, [self.num_time_steps_closeness, self.num_time_steps_period, self.num_time_steps_trend])
+        outs = []
+        for j, xb in enumerate(blocks):
+            with self.variable_scope('conv_init_{}'.format(j)):
+                y = self.activation_function(self._filter(xb, self.num_hidden), 'tanh')
+            for i in range(self.conv_layer_num):
+                with self.variable_scope('conv_layer_{0}_{1}'.format(i, j)):
+                    y = self.residual_layer(y, self.num_hidden, 'relu', 'residual_layer_{0}'.format(i))
+            with self.variable_scope('output_layer_{}'.format(j)):
+                y = self._filter(y, self.out_feature_num)
+            outs.append(self.activation_function(y, 'relu'))
+        with self.variable_scope('merge_layer'):
+            return self._filter(torch.cat(outs, dim=2), self.out_feature_num)
+
+    def inference_glstm_gconv(self, x):
+        """gLSTM, then conv_init / residual layers / output filter at num_hidden_conv (lib/gconv_lstm.py:384-409)."""
         frames = self._unstack_time(x)
         self.in_feature_num = int(frames[0].shape[2])
         x = self.glstm_layer(frames, self.num_time_steps_closeness, self.lstm_layer_count)[-1]
-        with self.variable_scope('conv_init'):
-            x = ops.bias_act(self._filter(x, self.num_hidden_conv), None, 'relu')
-        for i in range(self.conv_layer_num):
-            with self.variable_scope('conv_layer_{}'.format(i)):
-                x = self.residual_layer(x, self.num_hidden_conv, 'relu', 'residual_layer_{0}'.format(i))
-        with self.variable_scope('output_layer'):
-            return self._filter(x, self.out_feature_num)
+        return self._conv_stack(x, self.num_hidden_conv, 'relu')
+
+    def inference_glstm_gconv_no_expand(self, x):
+        """Identical topology (lib/gconv_lstm.py:411-436)."""
+        return self.inference_glstm_gconv(x)
+
+    def _merged_lstms(self, x, counts, head=None, transposed=False):
+        """merge_i scopes: one gLSTM stack per channel block, last output (optionally through ``head``)."""
+        outs = []
+        for i, xb in enumerate(self._split_periods(x, counts)):
+            with self.variable_scope('merge_{}'.format(i)):
+                frames = self._unstack_time(xb, counts[i], transposed)
+                y = self.glstm_layer(frames, len(frames), self.lstm_layer_count)[-1]
+                outs.append(head(y, i) if head is not None else y)
+        return outs
+
+    def inference_glstm_gconv_split(self, x):
+        """Two gLSTMs over the first two closeness-sized blocks, concat, conv stack (lib/gconv_lstm.py:439-474)."""
+        c = self.num_time_steps_closeness
+        outs = self._merged_lstms(x, [c, c])
+        return self._conv_stack(torch.cat(outs, dim=2), self.num_hidden, 'relu')
+
+    def _period_counts(self):
+        return [self.num_time_steps_closeness, self.num_time_steps_period, self.num_time_steps_trend]
+
+    def _node_weighted_sum(self, outs):
+        """X = sum_i x_i * w_i with one [M, Fout] weight per branch (lib/gconv_lstm.py:495-502)."""
+        total = None
+        for i, y in enumerate(outs):
+            with self.variable_scope('merge_{}'.format(i)):
+                with self.variable_scope('weight_{}'.format(i)):
+                    w = self._weight_variable([int(y.shape[1]), int(y.shape[2])])
+            if not y.is_meta:                                # shape tracing declares the variables only
+                y = y * w
+            total = y if total is None else total + y
+        return total
+
+    def inference_glstm_period_expand(self, x):
+        """Three gLSTMs, each through the output filter, summed with per-vertex weights (lib/gconv_lstm.py:476-505)."""
+        return self._node_weighted_sum(self._merged_lstms(x, self._period_counts(),
+                                                          head=lambda y, i: self.fc_layer(y, self.out_feature_num)))
+
+    def inference_glstm_period_expand_gconv1(self, x):
+        """Same with the branch filter's weights directly in merge_i (lib/gconv_lstm.py:507-537)."""
+        return self._node_weighted_sum(self._merged_lstms(x, self._period_counts(),
+                                                          head=lambda y, i: self._filter(y, self.out_feature_num)))
+
+    def inference_glstm_period_expand_gconv2(self, x):
+        """Branch frames come from the TRANSPOSED reshape (:525-527), concat, one final filter (lib/gconv_lstm.py:539-566)."""
+        outs = self._merged_lstms(x, self._period_counts(), head=lambda y, i: self._filter(y, self.out_feature_num),
+                                  transposed=True)
+        with self.variable_scope('final'):
+            return self._filter(torch.cat(outs, dim=2), self.out_feature_num)
+
+    def inference_glstm_period_expand_gconv3(self, x):
+        """Three gLSTMs, concat, conv stack at num_hidden (lib/gconv_lstm.py:568-607)."""
+        outs = self._merged_lstms(x, self._period_counts())
+        return self._conv_stack(torch.cat(outs, dim=2), self.num_hidden, 'relu')
 
     # ---- layers -----------------------------------------------------------------------
     def _output_dropout(self, y, layer, step):
@@ -197,7 +298,12 @@ class GconvModel(GraphModel):
             return y
         keep = self.output_keep_prob
         if self.dropout_masks is not None:
-            return y * self.dropout_masks[layer][step]
+            masks = self.dropout_masks
+            if masks and isinstance(masks[0], (list, tuple)):
+                return y * masks[layer][step]              # [layer][step] form (one gLSTM stack)
+            mask = masks[self._mask_cursor]                # flat form: DropoutWrapper call order (step-major, layer-minor)
+            self._mask_cursor += 1
+            return y * mask
         if keep >= 1:
             return y
         mask = (torch.rand_like(y) < keep).to(y.dtype) / keep

@@ -36,8 +36,8 @@ class GraphConv(GraphConvOps, GraphModel):
         self.build_graph(M_0, np.sum(self.C_0), 2)              # lib/graph_conv.py:81
 
     def _inference(self, x, dropout):
-        """[N, M, sum(C_0)] -> [N, M, 2] (lib/graph_conv.py:269-303).  Only the single-stack
-        form is provided; the fork's two-branch merge hard-codes 12 + 4 input channels."""
-        if self.stack_num != 1:
-            raise NotImplementedError('_STACK_NUM > 1 (hard-coded 12/4 channel split in the fork) is not provided')
-        return self.residual_network(x)
+        """[N, M, sum(C_0)] -> [N, M, 2] (lib/graph_conv.py:269-303): the residual network, or for
+        ``_STACK_NUM > 1`` the fork's two-branch merge over input channels 0..11 / 12..15."""
+        if self.stack_num == 1:
+            return self.residual_network(x)
+        return self.stacked_inference(x)

@@ -39,6 +39,13 @@ class GraphConvOps(object):
         W = self._weight_variable([Fin * K, Fout], regularization=False)
         return ops.cheb_filter(x, W, L, K, lmax=2, grad_x=False)
 
+    def fourier(self, x, L, Fout, K):
+        """Spectral filter in the eigenbasis of L (lib/models.py:146-157): one Fout x Fin matrix per frequency,
+        ``weights`` [M, Fout, Fin] without L2; K is ignored (the reference overwrites it with M)."""
+        N, M, Fin = (int(d) for d in x.shape)
+        W = self._weight_variable([M, Fout, Fin], regularization=False)
+        return ops.fourier_filter(x, W, L)
+
     # ---- bias + nonlinearity --------------------------------------------------------
     def b1relu(self, x):
         """Bias and ReLU, one bias per filter (lib/models.py:226-235)."""
@@ -148,6 +155,24 @@ class GraphConvOps(object):
             x = self.filter(x, self.L[0], 2, self.K[0])
         return x
 
+    def stacked_inference(self, x):
+        """The fork's two-branch form of ``_inference`` for ``_STACK_NUM > 1`` (lib/graph_conv.py:272-303 ==
+        lib/models.py:319-350): channels 0..11 and 12..15 of the input each go through their own residual network
+        (scopes final_merge/VC_i), relu, and are summed with one [M, 2] weight per branch (final_merge/VC_i/W_i/weights).
+        The 12 / 4 channel split is hard-coded in the reference; more than two branches fail there as well."""
+        branches = [x[:, :, 0:12], x[:, :, 12:16]]
+        total = None
+        with self.variable_scope('final_merge'):
+            for i in range(self.stack_num):
+                with self.variable_scope('VC_{0}'.format(i)):
+                    y = ops.bias_act(self.residual_network(branches[i]), None, 'relu')
+                    with self.variable_scope('W_{0}'.format(i)):
+                        w = self._weight_variable([int(y.shape[1]), int(y.shape[2])])
+                if not y.is_meta:                                # shape tracing declares the variables only
+                    y = y * w
+                total = y if total is None else total + y
+        return total
+
     # ---- constructor checks shared by cgcnn / GraphConv (lib/models.py:72-85) ----------
     def _select_laplacians(self, L, F, K, p):
         assert len(L) >= len(F) == len(K) == len(p)
@@ -251,16 +276,15 @@ class cgcnn(GraphConvOps, GraphModel):
                     x = fused_layer
                     self.nets['conv{}/pooling'.format(i + 1)] = x
                     continue
-                with self.variable_scope('filter'):
-                    x = self.filter(x, self.L[i], self.F[i], self.K[i])
-                with self.variable_scope('bias_relu'):
-                    fused = self._fused_brelu_pool(x, self.p[i])        # bias variable lives in this scope
-                    if fused is None:
-                        x = self.brelu(x)
-                        self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
-                with self.variable_scope('pooling'):
-                    x = fused if fused is not None else self.pool(x, self.p[i])
-                    self.nets['conv{}/pooling'.format(i + 1)] = x
+                # upstream wraps the three blocks in tf.name_scope('filter' / 'bias_relu' / 'pooling'), which does not
+                # prefix variables: they are conv{i}/weights and conv{i}/bias
+                x = self.filter(x, self.L[i], self.F[i], self.K[i])
+                fused = self._fused_brelu_pool(x, self.p[i])
+                if fused is None:
+                    x = self.brelu(x)
+                    self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
+                x = fused if fused is not None else self.pool(x, self.p[i])
+                self.nets['conv{}/pooling'.format(i + 1)] = x
         N, Mv, Fv = (int(d) for d in x.shape)
         x = x.reshape(N, Mv * Fv)
         for i, width in enumerate(self.M[:-1]):
@@ -283,10 +307,8 @@ class cgcnn(GraphConvOps, GraphModel):
                  getattr(self.pool, '__func__', None) is GraphConvOps.mpool1)
         if not stock or self.p[i] != 4 or int(x.shape[2]) != 1:
             return None
-        with self.variable_scope('filter'):
-            W = self._weight_variable([self.K[i], self.F[i]], regularization=False)       # [Fin*K, Fout], Fin = 1
-        with self.variable_scope('bias_relu'):
-            b = self._bias_variable([1, 1, self.F[i]], regularization=False) if self.b1relu_has_bias else None
+        W = self._weight_variable([self.K[i], self.F[i]], regularization=False)           # [Fin*K, Fout], Fin = 1
+        b = self._bias_variable([1, 1, self.F[i]], regularization=False) if self.b1relu_has_bias else None
         if not ops.first_layer_supported(x, W, b, self.L[i], self.K[i], 'relu', 4, 'max'):
             return None
         return ops.first_layer(x, W, b, self.L[i], self.K[i])

@@ -554,6 +554,91 @@ def linear(x, W, b=None, relu=False):
 
 
 # ---------------------------------------------------------------------------------------
+# spectral (Fourier) filter
+# ---------------------------------------------------------------------------------------
+
+def bmm(A, B, transA=False, transB=False):
+    """C[b] = op(A[b]) @ op(B[b]) through cg_bmm_f32; A, B 3-D float32 CUDA tensors."""
+    _require_cuda(A, B)
+    A, B = _f32c(A), _f32c(B)
+    batch = A.shape[0]
+    m, k = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
+    kb, n = (B.shape[2], B.shape[1]) if transB else (B.shape[1], B.shape[2])
+    if k != kb or B.shape[0] != batch:
+        raise ValueError('bmm: incompatible operands %r, %r' % (tuple(A.shape), tuple(B.shape)))
+    C = torch.empty((batch, m, n), dtype=torch.float32, device=A.device)
+    check(_native.lib().cg_bmm_f32(ptr(A), ptr(B), ptr(C), batch, m, n, k, int(transA), int(transB), A.shape[2], B.shape[2], n,
+                                   A.shape[1] * A.shape[2], B.shape[1] * B.shape[2], m * n, _stream()), 'cg_bmm_f32')
+    return C
+
+
+class FourierFilterFn(torch.autograd.Function):
+    """y = U (W_m (U^T x)_m)_m  (lib/filter.py:11-27, lib/models.py:129-144): x [N, M, Fin], W [M, Fout, Fin], U [M, M]
+    (columns = eigenvectors of L) -> y [N, M, Fout].  Two dense transforms on the tensor-core GEMM (cg_gemm_f32) around
+    one batched per-frequency product (cg_bmm_f32); the backward is the same three products transposed."""
+
+    @staticmethod
+    def forward(ctx, x, W, U):
+        _require_cuda(x, W, U)
+        x, W, U = _f32c(x), _f32c(W), _f32c(U)
+        N, M, Fin = x.shape
+        Fout = W.shape[1]
+        if tuple(W.shape) != (M, Fout, Fin) or tuple(U.shape) != (M, M):
+            raise ValueError('fourier filter: W must be [M, Fout, Fin] and U [M, M]; got %r, %r' % (tuple(W.shape), tuple(U.shape)))
+        xm = x.permute(1, 0, 2).reshape(M, N * Fin)                 # vertex-major view of the batch
+        xh = gemm(U, xm, transA=True).view(M, N, Fin)               # U^T x: graph Fourier transform
+        yh = bmm(xh, W, transB=True)                                # per frequency m: [N, Fin] . W[m]^T -> [N, Fout]
+        ym = gemm(U, yh.view(M, N * Fout))                          # back to the vertex domain
+        ctx.save_for_backward(xh, W, U)
+        ctx.dims = (N, M, Fin, Fout)
+        return ym.view(M, N, Fout).permute(1, 0, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, W, U = ctx.saved_tensors
+        N, M, Fin, Fout = ctx.dims
+        gm = _f32c(gy).permute(1, 0, 2).reshape(M, N * Fout)
+        gyh = gemm(U, gm, transA=True).view(M, N, Fout)             # U^T gy
+        dx = dW = None
+        if ctx.needs_input_grad[1]:
+            dW = bmm(gyh, xh, transA=True)                          # [Fout, N] . [N, Fin] per frequency
+        if ctx.needs_input_grad[0]:
+            gxh = bmm(gyh, W)                                       # [N, Fout] . [Fout, Fin]
+            dx = gemm(U, gxh.view(M, N * Fin)).view(M, N, Fin).permute(1, 0, 2).contiguous()
+        return dx, dW, None
+
+
+_fourier_cache = {}
+
+
+def fourier_basis(L):
+    """Device copy of U = eigenvectors of L (graph.fourier, lib/graph.py:148-166: numpy eigh on the host, once per
+    Laplacian object), cached like the packed operators."""
+    dev = torch.cuda.current_device()
+    key = (id(L), dev)
+    hit = _fourier_cache.get(key)
+    if hit is not None and hit[0]() is L:
+        return hit[1]
+    _, U = np.linalg.eigh(L.toarray())
+    Ut = torch.as_tensor(np.ascontiguousarray(U, dtype=np.float32), device=torch.device('cuda', dev))
+    try:
+        ref = weakref.ref(L, lambda _r, k=key: _fourier_cache.pop(k, None))
+    except TypeError:
+        ref = (lambda obj: (lambda: obj))(L)
+    _fourier_cache[key] = (ref, Ut)
+    return Ut
+
+
+def fourier_filter(x, W, L, U=None):
+    """Spectral filter with one Fout x Fin weight matrix per graph frequency; ``U`` overrides the cached eigenbasis."""
+    if x.is_meta:
+        return x.new_empty((x.shape[0], x.shape[1], W.shape[1]))
+    if U is None:
+        U = fourier_basis(L)
+    return FourierFilterFn.apply(x, W, U)
+
+
+# ---------------------------------------------------------------------------------------
 # perm_data on the device
 # ---------------------------------------------------------------------------------------
 

@@ -202,6 +202,16 @@ int cg_gemm_f32(const float *dev_A, const float *dev_B, float *dev_C, int M, int
                 int transB, int lda, int ldb, int ldc, const float *dev_bias, int relu, void *dev_workspace,
                 size_t workspace_bytes, void *stream);
 
+/* ---- batched small GEMM (spectral `fourier` filter) ---------------------- */
+/* lib/filter.py:11-27 == lib/models.py:129-144: between the two dense graph-Fourier transforms the reference applies one
+ * Fout x Fin matrix per graph frequency (tf.matmul(W, x), W [M, Fout, Fin], batched over the M frequencies).
+ * C[b] (m x n) = op(A[b]) (m x k) . op(B[b]) (k x n) for b < batch, all row-major fp32 (FFMA, fp32 accumulate);
+ * transA != 0: A[b] is stored [k][lda >= m]; transB != 0: B[b] is stored [n][ldb >= k]; stride_* in elements between
+ * consecutive batch entries.  The two transforms themselves are cg_gemm_f32 calls against U / U^T.               */
+int cg_bmm_f32(const float *dev_A, const float *dev_B, float *dev_C, int batch, int m, int n, int k, int transA,
+               int transB, int lda, int ldb, int ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+               void *stream);
+
 /* ---- coarsening.perm_data ---------------------------------------------- */
 /* lib/coarsening.py:219-240: out[:, i] = x[:, perm[i]] if perm[i] < M else 0.
  * dev_x [N, M], dev_perm [Mnew] int32, dev_out [N, Mnew] (float32 on device;

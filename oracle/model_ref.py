@@ -18,9 +18,9 @@ def init_params(L, F, K, p, M, seed=0, bias=True):
     params = {}
     Fin = 1
     for i, (Fo, Kk) in enumerate(zip(F, K)):
-        params['conv%d/filter/weights' % (i + 1)] = np.clip(0.1 * rng.standard_normal((Fin * Kk, Fo)), -0.2, 0.2).astype(np.float32)
+        params['conv%d/weights' % (i + 1)] = np.clip(0.1 * rng.standard_normal((Fin * Kk, Fo)), -0.2, 0.2).astype(np.float32)
         if bias:
-            params['conv%d/bias_relu/bias' % (i + 1)] = np.full((1, 1, Fo), 0.1, np.float32)
+            params['conv%d/bias' % (i + 1)] = np.full((1, 1, Fo), 0.1, np.float32)
         Fin = Fo
     width = L[len(F) - 1].shape[0] * F[-1] // p[-1] if len(F) else L[0].shape[0]
     names = ['fc%d' % (i + 1) for i in range(len(M) - 1)] + ['logits']
@@ -38,8 +38,8 @@ def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool=
     acts = []
     h = x[:, :, None].astype(np.float32)
     for i in range(nconv):
-        W = params['conv%d/filter/weights' % (i + 1)]
-        b = params.get('conv%d/bias_relu/bias' % (i + 1))
+        W = params['conv%d/weights' % (i + 1)]
+        b = params.get('conv%d/bias' % (i + 1))
         a = tf_ref.chebyshev5(h, L[i], W, K[i])
         r = tf_ref.b1relu(a, b)
         q = tf_ref.mpool1(r, p[i]) if pool == 'mpool1' else tf_ref.apool1(r, p[i])
@@ -87,11 +87,11 @@ def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool=
         hin, r = acts[i]
         gr = tf_ref.mpool1_backward(r, p[i], g) if pool == 'mpool1' else tf_ref.apool1_backward(r, p[i], g)
         ga = (gr * (r > 0)).astype(np.float32)
-        if 'conv%d/bias_relu/bias' % (i + 1) in params:
-            grads['conv%d/bias_relu/bias' % (i + 1)] = ga.sum(axis=(0, 1)).reshape(1, 1, -1)
-        W = params['conv%d/filter/weights' % (i + 1)]
+        if 'conv%d/bias' % (i + 1) in params:
+            grads['conv%d/bias' % (i + 1)] = ga.sum(axis=(0, 1)).reshape(1, 1, -1)
+        W = params['conv%d/weights' % (i + 1)]
         g, dW = tf_ref.chebyshev5_backward(hin, L[i], W, K[i], ga)
-        grads['conv%d/filter/weights' % (i + 1)] = dW
+        grads['conv%d/weights' % (i + 1)] = dW
     return loss, grads
 
 

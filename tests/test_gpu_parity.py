@@ -418,11 +418,11 @@ def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
     labels = rng.randint(0, 10, N)
     logits = model.inference(dev(x), 1)
     v = {k: p.detach().cpu().numpy() for k, p in model.store.vars.items()}
-    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/filter/weights'], 25)
-    r1 = tf_ref.b1relu(a1, v['conv1/bias_relu/bias'])
+    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/weights'], 25)
+    r1 = tf_ref.b1relu(a1, v['conv1/bias'])
     p1 = tf_ref.mpool1(r1, 4)
-    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/filter/weights'], 25)
-    r2 = tf_ref.b1relu(a2, v['conv2/bias_relu/bias'])
+    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/weights'], 25)
+    r2 = tf_ref.b1relu(a2, v['conv2/bias'])
     p2 = tf_ref.mpool1(r2, 4)
     f1 = tf_ref.fc(p2.reshape(N, -1), v['fc1/weights'], v['fc1/bias'])
     ref_logits = tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False)
@@ -443,19 +443,19 @@ def test_cgcnn_forward_backward_vs_oracle_c2(ops, tf_ref, c2):
     gp2 = (gf1 @ v['fc1/weights'].T).reshape(p2.shape)
     gr2 = tf_ref.mpool1_backward(r2, 4, gp2)
     ga2 = gr2 * (r2 > 0)
-    gp1, dW2 = tf_ref.chebyshev5_backward(p1, L[2], v['conv2/filter/weights'], 25, ga2)
+    gp1, dW2 = tf_ref.chebyshev5_backward(p1, L[2], v['conv2/weights'], 25, ga2)
     gr1 = tf_ref.mpool1_backward(r1, 4, gp1)
     ga1 = gr1 * (r1 > 0)
-    _, dW1 = tf_ref.chebyshev5_backward(x[:, :, None], L[0], v['conv1/filter/weights'], 25, ga1)
-    close(model.store.vars['conv2/filter/weights'].grad, dW2)
-    close(model.store.vars['conv1/filter/weights'].grad, dW1)
-    close(model.store.vars['conv2/bias_relu/bias'].grad.reshape(-1), ga2.sum(axis=(0, 1)))
-    close(model.store.vars['conv1/bias_relu/bias'].grad.reshape(-1), ga1.sum(axis=(0, 1)))
+    _, dW1 = tf_ref.chebyshev5_backward(x[:, :, None], L[0], v['conv1/weights'], 25, ga1)
+    close(model.store.vars['conv2/weights'].grad, dW2)
+    close(model.store.vars['conv1/weights'].grad, dW1)
+    close(model.store.vars['conv2/bias'].grad.reshape(-1), ga2.sum(axis=(0, 1)))
+    close(model.store.vars['conv1/bias'].grad.reshape(-1), ga1.sum(axis=(0, 1)))
     # one optimisation step runs and changes the weights
-    before = v['conv1/filter/weights'].copy()
+    before = v['conv1/weights'].copy()
     loss = model.train_step(dev(x), torch.from_numpy(labels).cuda())
     assert np.isfinite(float(loss))
-    assert not np.array_equal(before, model.get_var('conv1/filter/weights'))
+    assert not np.array_equal(before, model.get_var('conv1/weights'))
 
 
 def test_cgcnn_fused_brelu_pool_matches_unfused_model(ops, c2):
@@ -648,10 +648,10 @@ def test_c1_usage_config_filters_and_model(ops, tf_ref, c1):
     x = rng.standard_normal((N, 104)).astype(np.float32)
     logits = model.inference(dev(x), 1)
     v = {k: p_.detach().cpu().numpy() for k, p_ in model.store.vars.items()}
-    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/filter/weights'], 20)
-    p1 = tf_ref.apool1(tf_ref.b1relu(a1, v['conv1/bias_relu/bias']), 4)
-    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/filter/weights'], 20)
-    p2 = tf_ref.apool1(tf_ref.b1relu(a2, v['conv2/bias_relu/bias']), 2)
+    a1 = tf_ref.chebyshev5(x[:, :, None], L[0], v['conv1/weights'], 20)
+    p1 = tf_ref.apool1(tf_ref.b1relu(a1, v['conv1/bias']), 4)
+    a2 = tf_ref.chebyshev5(p1, L[2], v['conv2/weights'], 20)
+    p2 = tf_ref.apool1(tf_ref.b1relu(a2, v['conv2/bias']), 2)
     f1 = tf_ref.fc(p2.reshape(N, -1), v['fc1/weights'], v['fc1/bias'])
     close(logits, tf_ref.fc(f1, v['logits/weights'], v['logits/bias'], relu=False))
     close(model.nets['conv1/pooling'], p1)
@@ -686,7 +686,7 @@ def test_c3_20news_shaped_config(ops, tf_ref):
     model = models.cgcnn([L], F=[32], K=[5], p=[1], M=[20], batch_size=N, dropout=1)
     logits = model.inference(dev(x), 1)
     v = {k: p_.detach().cpu().numpy() for k, p_ in model.store.vars.items()}
-    r1 = tf_ref.b1relu(tf_ref.chebyshev5(x[:, :, None], L, v['conv1/filter/weights'], 5), v['conv1/bias_relu/bias'])
+    r1 = tf_ref.b1relu(tf_ref.chebyshev5(x[:, :, None], L, v['conv1/weights'], 5), v['conv1/bias'])
     close(logits, tf_ref.fc(r1.reshape(N, -1), v['logits/weights'], v['logits/bias'], relu=False))
 
 

@@ -32,9 +32,9 @@ def test_model_ref_gradients_vs_autograd(c2):
     for i in range(2):
         T = dense_T(L[i], K[i])
         Fin = h.shape[2]
-        W = tp['conv%d/filter/weights' % (i + 1)].reshape(Fin, K[i], F[i])
+        W = tp['conv%d/weights' % (i + 1)].reshape(Fin, K[i], F[i])
         a = torch.einsum('kij,njf,fko->nio', T, h, W)
-        r = torch.relu(a + tp['conv%d/bias_relu/bias' % (i + 1)])
+        r = torch.relu(a + tp['conv%d/bias' % (i + 1)])
         h = torch.nn.functional.max_pool1d(r.permute(0, 2, 1), p[i]).permute(0, 2, 1)
     z = h.reshape(N, -1)
     z = torch.relu(z @ tp['fc1/weights'] + tp['fc1/bias']) * torch.tensor(masks[0], dtype=torch.float64)
