@@ -1,422 +1,44 @@
 #!/usr/bin/env python3
 """Benchmark of the Chebyshev graph-conv hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this framework
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                   # this framework, default config c2
+    python bench.py --impl reference --steps K --warmup W           # the reference's CPU path (oracle port), same config + batch
+    python bench.py --config c1|c2|c3|c4|c5 [--batch B] ...         # the other BASELINE.json configs
 
-Workload (config.workload): BASELINE config C2 -- MNIST-shaped synthetic data on the 28x28
-8-NN grid graph, 4-level Graclus coarsening (M = 992 after fake-node padding), cgcnn
-GC32-P4-GC64-P4-FC512-FC10 with K = 25 Chebyshev terms (nips2016/mnist.ipynb cells 1,3,14,17).
-One "step" = one full training step of that model on one batch: forward, softmax
-cross-entropy + L2, backward, momentum-SGD update (and, for N > 1 GPUs, the all-reduce of the
-weight gradients).  Every graph-conv kernel is native (cnn_graph_b200/csrc); the two dense
-FC layers run on the library's tensor-core GEMM (cg_gemm_f32); the loss and the optimiser are stock PyTorch.  The filter arithmetic is fp32 throughout; the
-tensor-core products split every fp32 operand into bf16 hi + mid (three MMAs, fp32 accumulate in TMEM), which
-stays inside the reference's fp32 tolerance (rtol 1e-4, checked by tests/test_gpu_parity.py).
+Default workload (config.workload): BASELINE config C2 -- MNIST-shaped synthetic data on the 28x28 8-NN grid graph,
+4-level Graclus coarsening (M = 992 after fake-node padding), cgcnn GC32-P4-GC64-P4-FC512-FC10 with K = 25 Chebyshev
+terms (nips2016/mnist.ipynb cells 1,3,14,17), batch 1024 per GPU in BOTH arms (--batch; the reference notebooks' batch 100
+is in `batch_sweep`).  One "step" = one full training step of that model on one batch: forward, softmax cross-entropy +
+L2, backward, momentum-SGD update (and, for N > 1 GPUs, the all-reduce of the weight gradients).  Every graph-conv
+kernel and the dense head are native (cnn_graph_b200/csrc).  The filter arithmetic is fp32 throughout; the tensor-core
+products split every fp32 operand into bf16 hi + mid (three MMAs, fp32 accumulate in TMEM), which stays inside the
+reference's fp32 tolerance (rtol 1e-4, tests/test_gpu_parity.py, tests/test_reference_fixtures.py).
 
-Prints ONE JSON line (rank 0).  `value`: samples/s with the batch resident in HBM;
-`e2e`: the same step driven from pinned HOST buffers (raw 784-pixel images -> H2D -> device
-perm_data -> train step -> loss read back) every step.
+Prints ONE JSON line (rank 0).  `value`: samples/s with the batch resident in HBM; `e2e`: the same step driven from
+pinned HOST buffers (raw signals -> H2D -> device perm_data -> train step -> loss read back) every step.
+The harness lives in benchmarks/ (one module per config family); oracle/ is only used by the CPU legs.
 """
 import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-F, K, P, MFC = [32, 64], [25, 25], [4, 4], [512, 10]
-HYPER = dict(regularization=5e-4, dropout=0.5, learning_rate=0.02, decay_rate=0.95, momentum=0.9)
+from benchmarks import workloads  # noqa: E402  (numpy / scipy only)
+
+WORKLOAD = workloads.CGCNN['c2']['workload']
 
 
 def build_graphs(seed=0):
-    from cnn_graph_b200.lib import coarsening, graph
-    np.random.seed(seed)
-    A = graph.adjacency(*graph.distance_sklearn_metrics(graph.grid(28), k=8, metric='euclidean'))
-    graphs, perm = coarsening.coarsen(A, levels=4, self_connections=False, verbose=False)
-    L = [graph.laplacian(g, normalized=True) for g in graphs]
-    return L, perm
+    """C2 graphs through the product's host library (kept for tests / scripts)."""
+    return workloads.cgcnn_graphs('c2', workloads.host_lib('product'), seed)
 
 
-def peaks():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(path):
-        d = json.load(open(path))
-        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'source': 'measured'}
-    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback'}
-
-
-# ------------------------------------------------------------------------------------------
-# algorithmic work of the native kernels in one training step
-# ------------------------------------------------------------------------------------------
 def step_work(L, N):
-    """Algorithmic work of every native kernel launch in one training step.
-
-    name -> {'bound': 'hbm' | 'tensor', 'launches': [(bytes, flops), ...]}.  SpMM bytes are SURVEY.md 8(d)'s
-    B_stream (what an unfused CSR recurrence has to move: 8 nnz + 4 (M+1) + 12 M C per step), contraction flops
-    are 2 N M Fin K Fout; the dW kernel really streams the saved basis and gy from HBM, so its bytes are those.
-    """
-    from cnn_graph_b200 import ops
-    lay = []
-    for i, Fin, Fout in ((0, 1, F[0]), (2, F[0], F[1])):
-        Lr = ops.rescale_csr(L[i], 2)
-        lay.append((Lr.shape[0], Lr.nnz, Fin, Fout))
-
-    def b_stream(M, nnz, C, Kk):      # sum_{k=1}^{K-1} B_step; first step reads one operand fewer
-        b_step = 8 * nnz + 4 * (M + 1) + 12 * M * C
-        return (Kk - 1) * b_step - 4 * M * C
-
-    def spmm_flops(M, nnz, C, Kk):
-        return (Kk - 1) * 2 * nnz * C + (Kk - 2) * 2 * M * C
-
-    (M1, z1, _, _), (M2, z2, _, _) = lay
-    g1 = 2.0 * N * M1 * 1 * K[0] * F[0]
-    g2 = 2.0 * N * M2 * F[0] * K[1] * F[1]
-    dw_bytes = lambda M, Fa, Fb, Kk: 4.0 * N * M * (Kk * Fa + Fb)
-    return {
-        # layer 2 forward: recurrence at width N*32 and the 800x64 contraction, one kernel
-        'fused_fwd': {'bound': 'hbm', 'launches': [(b_stream(M2, z2, N * F[0], K[1]), spmm_flops(M2, z2, N * F[0], K[1]) + g2)]},
-        # layer 2 input gradient: adjoint recurrence at width N*32 on L~^T and the 64 -> 32 products G_k
-        'clenshaw_dx': {'bound': 'hbm', 'launches': [(b_stream(M2, z2, N * F[0], K[1]), spmm_flops(M2, z2, N * F[0], K[1]) + g2)]},
-        # weight gradients: stream the basis (K N M Fin x 4 bytes: fp32, or bf16 hi + mid planes) and gy (N M Fout fp32) once;
-        # layer 2 on the tensor cores from the forward kernel's operand planes, layer 1 (Fin = 1) on the FFMA pipe
-        'dw_umma': {'bound': 'hbm', 'launches': [(dw_bytes(M2, F[0], F[1], K[1]), g2)]},
-        # (fused first layer: the kernel reads the fp32 basis and, per POOLED value, the gradient, the output and the
-        #  argmax byte -- 9 bytes per 4 vertices and filter -- instead of the 4x larger gy)
-        'dw_thin': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * K[0] + 9.0 * N * (M1 // P[0]) * F[0], g1)]},
-        # layer 1 (Fin = 1): unfused recurrence (forward, and again for dW) and FFMA contraction
-        'basis_onchip': {'bound': 'hbm', 'launches': [(b_stream(M1, z1, N, K[0]), spmm_flops(M1, z1, N, K[0]))] * 2},
-        'contract': {'bound': 'tensor', 'launches': [(0, g1)]},
-        # layer 1 contraction on the tensor cores: reads the basis (K N M fp32) once, writes y (N M 32 fp32)
-        # dense head: fc1 (3968 -> 512) and logits (512 -> 10), forward + both gradients, fp32-equivalent flops
-        'gemm_umma': {'bound': 'tensor', 'launches': [(0, 2.0 * N * 3968 * 512)] * 3 + [(0, 2.0 * N * 512 * 10)] * 3,
-                      'note': 'fp32-equivalent flops (three bf16 MMAs each) against the dense bf16 peak'},
-        # (with bias / relu / max-pool 4 in its epilogue it writes the pooled values and argmax bytes, not y)
-        'contract_umma': {'bound': 'hbm', 'launches': [(4.0 * N * M1 * K[0] + 5.0 * N * (M1 // P[0]) * F[0], g1)]},
-    }
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
-
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[4:8]):
-                if flag.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
-
-
-# ------------------------------------------------------------------------------------------
-# CPU arm: the reference's numpy/scipy path, restated in oracle/
-# ------------------------------------------------------------------------------------------
-def cpu_training_steps(L, batch, steps, warmup, seed=0):
-    from oracle import model_ref
-    rng = np.random.RandomState(seed)
-    Ls = [L[0], L[2]]
-    params = model_ref.init_params(Ls, F, K, P, MFC, seed=seed)
-    velocity = {}
-    x = rng.uniform(0, 1, (batch, L[0].shape[0])).astype(np.float32)
-    labels = rng.randint(0, 10, batch)
-    times = []
-    for it in range(warmup + steps):
-        masks = [(rng.uniform(size=(batch, MFC[0])) < HYPER['dropout']).astype(np.float32) / HYPER['dropout']]
-        t0 = time.perf_counter()
-        loss, grads = model_ref.forward_backward(params, Ls, F, K, P, MFC, x, labels, HYPER['regularization'],
-                                                 'mpool1', masks)
-        model_ref.sgd_momentum_step(params, grads, velocity, HYPER['learning_rate'], HYPER['momentum'])
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return times, float(loss)
-
-
-def run_reference(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    L, _ = build_graphs()
-    batch = args.ref_batch
-    times, _ = cpu_training_steps(L, batch, args.steps, args.warmup)
-    total = float(np.sum(times))
-    value = batch * len(times) / total
-    cores = os.cpu_count()
-    line = {
-        'impl': 'reference', 'metric': 'cheb_graphconv_train_samples_per_sec', 'value': value, 'unit': 'samples/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_step': batch,
-                   'note': 'reference CPU path: TensorFlow is not installable, so the reference\'s own numpy/scipy '
-                           'code path (graph.chebyshev-style scipy CSR SpMM + numpy BLAS), restated in oracle/, is timed'},
-        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d steps of batch %d (full train step: fwd+loss+bwd+update)' % (len(times), batch)},
-        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
-    print(json.dumps(line), flush=True)
-
-
-WORKLOAD = ('C2 MNIST-shaped synthetic: 28x28 8-NN grid graph, 4-level coarsening (M=992), '
-            'cgcnn F=[32,64] K=[25,25] p=[4,4] M=[512,10], full training step')
-
-
-# ------------------------------------------------------------------------------------------
-# GPU arm
-# ------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    from cnn_graph_b200 import _native, dist as cgdist, ops
-    from cnn_graph_b200.lib import models
-
-    rank, world, local_rank = cgdist.init_from_env('nccl')
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device (the hot path has no CPU fallback)')
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    lib = _native.lib()
-    L, perm = build_graphs()
-    B = args.batch
-    torch.manual_seed(1234 + rank)
-    model = models.cgcnn(L, F=F, K=K, p=P, M=MFC, filter='chebyshev5', brelu='b1relu', pool='mpool1',
-                         batch_size=B, decay_steps=600, **HYPER)
-    if world > 1:
-        # identical initial weights on every rank, then one flat all-reduce of the gradients per step
-        for p_ in model.store.parameters():
-            torch.distributed.broadcast(p_.data, src=0)
-        # measured at 2 GPUs: the flat bucket after the backward pass 1.747 ms / step, all-reducing the fc gradient from an
-        # autograd hook under the graph-conv backward kernels 1.783 ms (the NCCL kernel takes SMs from them)
-        model.grad_hook = (cgdist.OverlappedGradAllReducer(model.store.parameters(), average=True) if args.overlap_allreduce
-                           else cgdist.GradAllReducer(average=True))
-
-    # synthetic batch: raw 28x28 "images" U[0,1) on the host (pinned) and their permuted copy in HBM
-    gen = torch.Generator().manual_seed(99 + rank)
-    raw_host = torch.rand((B, 784), generator=gen).pin_memory()
-    labels_host = torch.randint(0, 10, (B,), generator=gen).pin_memory()
-    x_dev = ops.perm_data_device(raw_host.to(device), perm)
-    y_dev = labels_host.to(device)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
-
-    # The step is replayed from a CUDA graph (GraphModel.train_step_graphed: same kernels, one launch); --eager
-    # keeps the kernel-by-kernel launches.  Multi-GPU: the gradient all-reduce is captured with the step; if this
-    # torch/NCCL build refuses, fall back to eager launches and say so.
-    mode = 'eager' if args.eager else 'cuda_graph'
-    if mode == 'cuda_graph':
-        try:
-            model.train_step_graphed(x_dev, y_dev)
-            torch.cuda.synchronize()
-        except Exception as exc:      # noqa: BLE001 -- report and keep measuring
-            sys.stderr.write('bench: CUDA-graph capture failed (%s); eager launches\n' % (exc,))
-            mode = 'eager'
-
-    def step_resident():
-        return model.train_step_graphed(x_dev, y_dev) if mode == 'cuda_graph' else model.train_step(x_dev, y_dev)
-
-    eager0 = lib.cg_launch_count()
-    model.train_step(x_dev, y_dev)
-    native_per_step = int(lib.cg_launch_count() - eager0)      # this library's kernels in one step (eager count)
-
-    # end to end through the public feeder: pinned host batch -> H2D (copy stream) -> perm_data -> step -> loss D2H
-    trainer = model.pipelined_trainer(perm=perm, depth=2, use_graph=(mode == 'cuda_graph'))
-
-    def run_e2e(steps):
-        for _ in range(steps):
-            trainer.submit(raw_host, labels_host)
-        losses = trainer.drain()      # every step's loss has reached the host
-        assert len(losses) == steps and all(np.isfinite(v) for v in losses), losses
-
-    def timed(fn, steps, warmup, sample_clocks=False):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        cgdist.barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start()
-        launches0 = lib.cg_launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for a, b in ev:
-            flush.fill_(0.0)          # evict L2 between timed iterations (outside the timed events)
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        cgdist.barrier()
-        launches = lib.cg_launch_count() - launches0
-        clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        return cgdist.max_over_ranks(ms, device), launches, clocks
-
-    W = max(args.warmup, 3)
-    ms_total, launches, clocks = timed(step_resident, args.steps, W, sample_clocks=True)
-    value = world * B * args.steps / (ms_total * 1e-3)
-    if mode == 'cuda_graph':
-        launches = native_per_step * args.steps      # replays launch the kernels recorded at capture
-    # e2e: K steps back to back inside ONE event pair (copies, perm_data, step, loss read-back all inside; no L2
-    # flush -- every step's inputs arrive from the host and its ~1.3 GB of activations exceed the 126 MB L2)
-    run_e2e(3)
-    torch.cuda.synchronize()
-    cgdist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    cgdist.barrier()
-    ms_e2e = cgdist.max_over_ranks(e0.elapsed_time(e1), device)
-    h2d_bytes = int(trainer.h2d_bytes_per_step)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-
-    # per-kernel device time of the same step, CUDA events on the launch stream (profiling pass)
-    roof, kernel_ms = None, {}
-    # every rank runs the profiling steps (the gradient all-reduce inside the step is a collective); only
-    # rank 0 records
-    prof_steps = min(args.steps, 5)
-    if rank == 0:
-        lib.cg_profile_reset()
-        lib.cg_profile_enable(1)
-    for _ in range(prof_steps):
-        flush.fill_(0.0)
-        model.train_step(x_dev, y_dev)      # eager: the per-kernel events cannot be recorded inside a graph replay
-    torch.cuda.synchronize()
-    cgdist.barrier()
-    if rank == 0:
-        lib.cg_profile_enable(0)
-        import ctypes
-        name = ctypes.create_string_buffer(64)
-        tot, cnt = ctypes.c_double(), ctypes.c_int64()
-        n = lib.cg_profile_query(-1, None, 0, None, None)
-        for i in range(n):
-            lib.cg_profile_query(i, name, 64, ctypes.byref(tot), ctypes.byref(cnt))
-            kernel_ms[name.value.decode()] = {'ms_per_step': tot.value / prof_steps, 'launches_per_step': cnt.value / prof_steps}
-        work = step_work(L, B)
-        pk = peaks()
-        traffic = {}
-        traffic_file = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-        if os.path.exists(traffic_file):
-            traffic = json.load(open(traffic_file))
-        lines = []
-        for kname, w in work.items():
-            if kname not in kernel_ms:
-                continue
-            n_l = max(kernel_ms[kname]['launches_per_step'], 1)
-            avg_s = kernel_ms[kname]['ms_per_step'] * 1e-3 / n_l
-            per_b = sum(b for b, _ in w['launches']) / len(w['launches'])
-            per_f = sum(f for _, f in w['launches']) / len(w['launches'])
-            entry = {'kernel': kname, 'bound': w['bound'], 'ms_per_step': kernel_ms[kname]['ms_per_step'],
-                     'launches_per_step': n_l, 'peak_source': pk['source'],
-                     'traffic': traffic.get(kname)}
-            if w['bound'] == 'hbm':
-                entry.update(achieved=per_b / avg_s / 1e9, peak=pk['hbm_gbs'], unit='GB/s')
-                entry['tensor_TFLOPs'] = per_f / avg_s / 1e12      # executed alongside (fp32-equivalent flops)
-            else:
-                entry.update(achieved=per_f / avg_s / 1e12, peak=pk['bf16_tflops'], unit='TFLOP/s',
-                             note=w.get('note', 'fp32 FFMA contraction measured against the dense bf16 tensor peak'))
-            entry['frac'] = entry['achieved'] / entry['peak']
-            lines.append(entry)
-        if lines:
-            lines.sort(key=lambda e: -e['ms_per_step'])
-            roof = dict(lines[0])                 # the dominant kernel of the step
-            roof['all'] = lines
-            # SpMM line of the metric: the three recurrence kernels together
-            rec = [e for e in lines if e['kernel'] in ('fused_fwd', 'clenshaw_dx', 'basis_onchip')]
-            if rec:
-                tot_b = sum(sum(b for b, _ in work[e['kernel']]['launches']) for e in rec)
-                tot_s = sum(e['ms_per_step'] for e in rec) * 1e-3
-                roof['spmm'] = {'kernels': [e['kernel'] for e in rec], 'algorithmic_GBps': tot_b / tot_s / 1e9,
-                                'frac_of_hbm_peak': tot_b / tot_s / 1e9 / pk['hbm_gbs'],
-                                'ms_per_step': tot_s * 1e3,
-                                'note': 'algorithmic bytes of an unfused CSR recurrence (SURVEY 8d B_stream); the fused '
-                                        'kernels keep the slabs in shared memory, their DRAM traffic is in `traffic`'}
-
-    # captured graphs hold NCCL work: release them before the process group goes away
-    trainer = None
-    model._captured = None
-    import gc
-    gc.collect()
-    torch.cuda.synchronize()
-    cgdist.barrier()
-    if rank != 0:
-        return
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        t0 = time.perf_counter()
-        times, _ = cpu_training_steps(L, args.ref_batch, 3, 1)
-        cpu = {'value': args.ref_batch * len(times) / float(np.sum(times)), 'unit': 'samples/s',
-               'cores': os.cpu_count(), 'kind': 'port',
-               'sample': '3 timed steps of batch %d (1 warm-up), %.1f s of CPU work; oracle/ numpy+scipy port of the '
-                         'reference path (TensorFlow unavailable)' % (args.ref_batch, time.perf_counter() - t0)}
-    line = {
-        'metric': 'cheb_graphconv_train_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': W, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'precision': 'fp32 storage and recurrence; tensor-core products as bf16 hi+mid split x3 with fp32 accumulation (error <= 2^-16 relative, inside rtol 1e-4)', 'global_batch': B * world,
-                   'parallelism': 'dp%d' % world, 'l2': 'flushed between timed iterations (256 MB fill)',
-                   'timing': 'CUDA events per step on the launch stream, summed; max over ranks',
-                   'launch': mode,
-                   'e2e_path': 'GraphModel.pipelined_trainer: pinned host batch -> H2D on a copy stream (2 buffers) -> '
-                               'cg_perm_data -> training step -> loss D2H; K steps in one event pair, no L2 flush '
-                               '(inputs come from the host every step)'},
-        'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
-        'gpu_launches': int(launches),
-        'roofline': roof, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernel_ms,
-    }
-    print(json.dumps(line), flush=True)
-
-
-def _shutdown():
-    """Leave without the blocking NCCL teardown: destroy_process_group() was seen to hang after graph-captured
-    collectives; every rank has passed the final barrier and printed by now."""
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-    except Exception:
-        pass
+    from benchmarks import cgcnn_bench
+    return cgcnn_bench.step_work('c2', L, N)
 
 
 def main():
@@ -428,18 +50,47 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=1024, help='samples per GPU per step')
-    ap.add_argument('--ref-batch', type=int, default=100, help='samples per CPU step (reference batch size)')
+    ap.add_argument('--config', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
+    ap.add_argument('--batch', type=int, default=0, help='samples per GPU per step in BOTH arms (0: the config default; c2: 1024)')
+    ap.add_argument('--ref-batch', type=int, default=0, help='deprecated alias of --batch for the reference arm')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch per GPU; strong: --batch is the GLOBAL batch, split over the GPUs')
+    ap.add_argument('--sweep', type=int, nargs='*', default=None,
+                    help='device-timed batch sweep added to the line as `batch_sweep` (default for c2 at 1 GPU: 100 256 1024 4096)')
+    ap.add_argument('--no-sweep', action='store_true')
+    ap.add_argument('--sustain', type=float, default=0.0, help='also run the resident step for this many seconds (rate under power cap)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--overlap-allreduce', action='store_true', help='all-reduce the large gradients from autograd hooks, '
                     'overlapped with the backward pass (default: one flat all-reduce after it, which measured faster)')
     ap.add_argument('--eager', action='store_true', help='kernel-by-kernel launches instead of CUDA-graph replay')
+    ap.add_argument('--traffic-tag', default='r2', help='profiles/roofline_traffic_<tag>.json: ncu dram bytes per launch')
+    # c4 / c5 knobs
+    ap.add_argument('--T', type=int, default=3, help='c4: unrolled cell steps')
+    ap.add_argument('--H', type=int, default=128, help='c4: hidden features')
+    ap.add_argument('--K', type=int, default=0, help='c4 / c5: Chebyshev terms (0: config default 3 / 20)')
+    ap.add_argument('--log2m', type=int, default=20, help='c5: 2^log2m vertices')
+    ap.add_argument('--order', default='morton', choices=['morton', 'random'], help='c5: vertex order')
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference(args)
+    if args.ref_batch and not args.batch:
+        args.batch = args.ref_batch
+    if args.sweep is None:
+        args.sweep = [100, 256, 1024, 4096] if (args.config == 'c2' and args.impl == 'ours' and not args.no_sweep
+                                                and args.scaling == 'weak') else []
+    if args.no_sweep:
+        args.sweep = []
+
+    if args.config in ('c1', 'c2', 'c3'):
+        from benchmarks import cgcnn_bench as mod
+    elif args.config == 'c4':
+        from benchmarks import glstm_bench as mod
     else:
-        run_ours(args)
-        _shutdown()
+        from benchmarks import rowpart_bench as mod
+    if args.impl == 'reference':
+        mod.run_reference(args, args.config)
+    else:
+        mod.run_ours(args, args.config)
+        from benchmarks import common
+        common.shutdown()
 
 
 if __name__ == '__main__':

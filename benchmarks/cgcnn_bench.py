@@ -1,0 +1,330 @@
+"""bench.py arms for the cgcnn configs (BASELINE.json configs[0..2] = c1, c2, c3): one "step" = one full training
+step of the model on one batch (forward, softmax cross-entropy + L2, backward, momentum-SGD update; for N > 1 GPUs the
+all-reduce of the weight gradients)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import common, workloads
+from .common import METRIC
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's numpy/scipy path restated in oracle/ (never touches cnn_graph_b200)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_training_steps(config, batch, steps, warmup, seed=0, keep_stack=True):
+    from oracle import model_ref
+    cfg = workloads.CGCNN[config]
+    lib = workloads.host_lib('oracle')
+    L, perm = workloads.cgcnn_graphs(config, lib)
+    Ls = workloads.model_laplacians(L, cfg['p'])
+    rng = np.random.RandomState(seed)
+    params = model_ref.init_params(Ls, cfg['F'], cfg['K'], cfg['p'], cfg['M'], seed=seed)
+    velocity = {}
+    raw, labels = workloads.cgcnn_batch(config, L, perm, batch, seed)
+    from oracle import coarsen_ref
+    x = coarsen_ref.perm_data(raw, perm).astype(np.float32) if perm is not None else raw
+    H = workloads.HYPER
+    times = []
+    loss = float('nan')
+    for it in range(warmup + steps):
+        masks = [(rng.uniform(size=(batch, m)) < H['dropout']).astype(np.float32) / H['dropout'] for m in cfg['M'][:-1]]
+        t0 = time.perf_counter()
+        loss, grads = model_ref.forward_backward(params, Ls, cfg['F'], cfg['K'], cfg['p'], cfg['M'], x, labels,
+                                                 H['regularization'], cfg['pool'], masks, keep_stack=keep_stack)
+        model_ref.sgd_momentum_step(params, grads, velocity, H['learning_rate'], H['momentum'])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, float(loss)
+
+
+def cpu_baseline(config, batch, budget_s=20.0):
+    """Bounded sample for the GPU arm's `cpu_baseline` key: as many steps of the SAME batch as fit the budget (>= 1)."""
+    t0 = time.perf_counter()
+    times, _ = cpu_training_steps(config, batch, 1, 1)
+    per = times[0]
+    extra = int(max(0, min(4, (budget_s - (time.perf_counter() - t0)) // max(per, 1e-3))))
+    if extra:
+        more, _ = cpu_training_steps(config, batch, extra, 0)
+        times += more
+    return {'value': batch * len(times) / float(np.sum(times)), 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': '%d timed steps of batch %d after 1 warm-up (full train step: fwd + loss + bwd + update; the forward keeps '
+                      'the restacked Chebyshev operand for the backward, as TF autodiff does), %.1f s of CPU work; oracle/ '
+                      'numpy + scipy port of the reference path (TensorFlow is not installable): scipy CSR x dense SpMM is '
+                      'single-threaded, numpy BLAS uses all cores' % (len(times), batch, time.perf_counter() - t0)}
+
+
+def run_reference(args, config):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    cfg = workloads.CGCNN[config]
+    batch = args.batch or cfg['batch']
+    times, _ = cpu_training_steps(config, batch, args.steps, args.warmup)
+    total = float(np.sum(times))
+    value = batch * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'batch_per_gpu': batch, 'global_batch': batch,
+                   'note': 'reference CPU path: TensorFlow is not installable, so the reference\'s own numpy/scipy code path '
+                           '(graph.chebyshev-style scipy CSR SpMM + numpy BLAS), restated in oracle/ and pinned to outputs of '
+                           'the reference\'s sources, is timed; graphs are built with oracle/ too (no product library is '
+                           'loaded); the backward reuses the forward\'s Chebyshev stack as TF autodiff does'},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': '%d steps of batch %d (full train step: fwd+loss+bwd+update)' % (len(times), batch)},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    import json
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# algorithmic work of the native kernels in one training step
+# ---------------------------------------------------------------------------------------------------------------
+def step_work(config, L, N):
+    """name (the library's profile scope) -> per-launch algorithmic {'bound', 'bytes', 'flops', 'floor_bytes'}.
+    Averages over the launches of that scope in one step when several layers use the same kernel."""
+    from cnn_graph_b200 import ops
+    cfg = workloads.CGCNN[config]
+    Ls = workloads.model_laplacians(L, cfg['p'])
+    layers, Fin = [], 1
+    for i, Fo in enumerate(cfg['F']):
+        Lr = ops.rescale_csr(Ls[i], 2)
+        layers.append(dict(M=Lr.shape[0], nnz=Lr.nnz, Fin=Fin, Fout=Fo, K=cfg['K'][i], p=cfg['p'][i]))
+        Fin = Fo
+    wide = [l for l in layers if l['Fin'] > 1]
+    thin = [l for l in layers if l['Fin'] == 1]
+    mean = lambda xs: float(np.mean(xs)) if xs else 0.0
+    work = {}
+    if wide:
+        bs = mean([common.b_stream(l['M'], l['nnz'], N * l['Fin'], l['K']) for l in wide])
+        fl = mean([common.b_floor(l['M'], l['nnz'], N * l['Fin'], l['K']) for l in wide])
+        fg = mean([common.f_gemm(N, l['M'], l['Fin'], l['K'], l['Fout']) for l in wide])
+        sf = mean([common.spmm_flops(l['M'], l['nnz'], N * l['Fin'], l['K']) for l in wide])
+        # recurrence at width N*Fin fused with the (Fin K) x Fout contraction / its adjoint on L~^T with G_k = gy W_k^T
+        work['fused_fwd'] = {'bound': 'hbm', 'bytes': bs, 'flops': sf + fg, 'floor_bytes': fl}
+        work['clenshaw_dx'] = {'bound': 'hbm', 'bytes': bs, 'flops': sf + fg, 'floor_bytes': fl}
+        # weight gradient: the saved basis (K N M Fin, fp32 or the bf16 hi+mid planes: same bytes) and gy, read once
+        dwb = mean([4.0 * N * l['M'] * (l['K'] * l['Fin'] + l['Fout']) for l in wide])
+        work['dw_planes'] = {'bound': 'hbm', 'bytes': dwb, 'flops': fg}
+        work['dw_umma'] = {'bound': 'hbm', 'bytes': dwb, 'flops': fg}
+        work['spmm_step'] = {'bound': 'hbm', 'bytes': mean([common.b_step(l['M'], l['nnz'], N * l['Fin']) for l in layers]), 'flops': 0}
+    if thin:
+        l = thin[0]
+        g1 = common.f_gemm(N, l['M'], 1, l['K'], l['Fout'])
+        pooled = l['p'] == 4 and cfg['pool'] == 'mpool1'
+        work['basis_onchip'] = {'bound': 'hbm', 'bytes': common.b_stream(l['M'], l['nnz'], N, l['K']),
+                                'flops': common.spmm_flops(l['M'], l['nnz'], N, l['K']),
+                                'floor_bytes': common.b_floor(l['M'], l['nnz'], N, l['K'])}
+        out_b = 5.0 * N * (l['M'] // 4) * l['Fout'] if pooled else 4.0 * N * l['M'] * l['Fout']
+        work['contract_umma'] = {'bound': 'hbm', 'bytes': 4.0 * N * l['M'] * l['K'] + out_b, 'flops': g1}
+        gy_b = 9.0 * N * (l['M'] // 4) * l['Fout'] if pooled else 4.0 * N * l['M'] * l['Fout']
+        work['dw_thin'] = {'bound': 'hbm', 'bytes': 4.0 * N * l['M'] * l['K'] + gy_b, 'flops': g1}
+        if not wide:
+            work['spmm_step'] = {'bound': 'hbm', 'bytes': common.b_step(l['M'], l['nnz'], N), 'flops': 0}
+    # dense head: fc layers forward + both gradients, fp32-equivalent flops against the dense bf16 peak
+    widths = [layers[-1]['M'] // layers[-1]['p'] * layers[-1]['Fout']] + list(cfg['M'])
+    fc = [2.0 * N * a * b for a, b in zip(widths[:-1], widths[1:])]
+    note = 'fp32-equivalent flops (three bf16 MMAs each) against the dense bf16 peak'
+    work['gemm_pipe'] = {'bound': 'tensor', 'bytes': 0, 'flops': mean(fc), 'note': note}
+    work['gemm_umma'] = {'bound': 'tensor', 'bytes': 0, 'flops': mean(fc), 'note': note}
+    return work
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def build_model(config, L, batch, device):
+    from cnn_graph_b200.lib import models
+    cfg = workloads.CGCNN[config]
+    return models.cgcnn(L, F=cfg['F'], K=cfg['K'], p=cfg['p'], M=cfg['M'], filter='chebyshev5', brelu='b1relu',
+                        pool=cfg['pool'], batch_size=batch, decay_steps=600, **workloads.HYPER)
+
+
+def run_ours(args, config):
+    import json
+    import torch
+    from cnn_graph_b200 import _native, dist as cgdist, ops
+
+    cfg = workloads.CGCNN[config]
+    rank, world, local_rank = cgdist.init_from_env('nccl')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the hot path has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    lib = _native.lib()
+    L, perm = workloads.cgcnn_graphs(config, workloads.host_lib('product'))
+    use_perm = perm is not None                                  # c3 has no coarsening levels (20news.ipynb cell 1)
+    timer = common.Timer(device, local_rank)
+    strong = args.scaling == 'strong'
+
+    def make(batch, seed):
+        """model + resident batch + pinned host batch for one per-GPU batch size"""
+        torch.manual_seed(1234)
+        model = build_model(config, L, batch, device)
+        if world > 1:
+            for p_ in model.store.parameters():                   # identical initial weights on every rank
+                torch.distributed.broadcast(p_.data, src=0)
+            model.grad_hook = (cgdist.OverlappedGradAllReducer(model.store.parameters(), average=True)
+                               if args.overlap_allreduce else cgdist.GradAllReducer(average=True))
+        raw, labels = workloads.cgcnn_batch(config, L, perm, batch, 99 + rank + seed)
+        raw_host = torch.from_numpy(raw).pin_memory()
+        labels_host = torch.from_numpy(labels).pin_memory()
+        x_dev = ops.perm_data_device(raw_host.to(device), perm) if use_perm else raw_host.to(device)
+        return model, raw_host, labels_host, x_dev, labels_host.to(device)
+
+    def resident_stepper(model, x_dev, y_dev, mode):
+        if mode == 'cuda_graph':
+            try:
+                model.train_step_graphed(x_dev, y_dev)
+                torch.cuda.synchronize()
+            except Exception as exc:      # noqa: BLE001 -- report and keep measuring
+                sys.stderr.write('bench: CUDA-graph capture failed (%s); eager launches\n' % (exc,))
+                mode = 'eager'
+        fn = (lambda: model.train_step_graphed(x_dev, y_dev)) if mode == 'cuda_graph' else (lambda: model.train_step(x_dev, y_dev))
+        return fn, mode
+
+    B = args.batch or cfg['batch']
+    if strong:
+        assert B % world == 0, 'strong scaling: the global batch must divide by the number of GPUs'
+        B //= world
+    model, raw_host, labels_host, x_dev, y_dev = make(B, 0)
+    step_resident, mode = resident_stepper(model, x_dev, y_dev, 'eager' if args.eager else 'cuda_graph')
+
+    eager0 = lib.cg_launch_count()
+    model.train_step(x_dev, y_dev)
+    native_per_step = int(lib.cg_launch_count() - eager0)       # this library's kernels in one step (eager count)
+
+    W = max(args.warmup, 3)
+    ms_total, clocks, sustained = timer.run(step_resident, args.steps, W, sample_clocks=True, min_seconds=args.sustain)
+    value = world * B * args.steps / (ms_total * 1e-3)
+    launches = native_per_step * args.steps
+
+    # end to end through the public feeder: pinned host batch -> H2D (copy stream) -> perm_data -> step -> loss D2H.
+    # K steps back to back inside ONE event pair (no L2 flush: every step's inputs arrive from the host and its
+    # activations exceed the 126 MB L2 at the default batch)
+    trainer = model.pipelined_trainer(perm=perm if use_perm else None, depth=2, use_graph=(mode == 'cuda_graph'))
+
+    def run_e2e(steps):
+        for _ in range(steps):
+            trainer.submit(raw_host, labels_host)
+        losses = trainer.drain()
+        assert len(losses) == steps and all(np.isfinite(v) for v in losses), losses
+
+    run_e2e(3)
+    torch.cuda.synchronize()
+    cgdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    cgdist.barrier()
+    ms_e2e = cgdist.max_over_ranks(e0.elapsed_time(e1), device)
+    h2d_bytes = int(trainer.h2d_bytes_per_step)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # per-kernel device time of the same step (eager: events cannot be recorded inside a graph replay); every rank
+    # runs the steps (the gradient all-reduce is a collective), rank 0 records
+    prof_steps = min(args.steps, 5)
+    kernel_ms = {}
+    if rank == 0:
+        kernel_ms = common.profile_kernels(lambda: model.train_step(x_dev, y_dev), prof_steps, timer)
+    else:
+        for _ in range(prof_steps):
+            timer.flush()
+            model.train_step(x_dev, y_dev)
+        torch.cuda.synchronize()
+    cgdist.barrier()
+    roof = None
+    if rank == 0:
+        work = step_work(config, L, B)
+        traffic = common.measured_traffic(args.traffic_tag) if (config == 'c2' and B == 1024) else {}
+        lines = common.roofline_entries(work, kernel_ms, traffic)
+        if lines:
+            roof = dict(lines[0])
+            roof['traffic_source'] = (traffic.get('_note') if traffic else None)
+            roof['all'] = lines
+            rec = [e for e in lines if e['kernel'] in ('fused_fwd', 'clenshaw_dx', 'basis_onchip', 'spmm_step')]
+            if rec:
+                tot_b = sum(e['algorithmic_bytes_per_launch'] * e['launches_per_step'] for e in rec)
+                tot_s = sum(e['ms_per_step'] for e in rec) * 1e-3
+                pk = common.peaks()
+                roof['spmm'] = {'kernels': [e['kernel'] for e in rec], 'algorithmic_GBps': tot_b / tot_s / 1e9,
+                                'frac_of_hbm_peak': tot_b / tot_s / 1e9 / pk['hbm_gbs'], 'frac_of_8TBps_nominal': tot_b / tot_s / 8e12,
+                                'ms_per_step': tot_s * 1e3,
+                                'note': 'algorithmic bytes of an unfused CSR recurrence (SURVEY 8d B_stream); the fused kernels '
+                                        'keep the slabs in shared memory -- B_floor/t is `floor_GBps`, DRAM traffic from ncu is '
+                                        '`traffic` / `dram_GBps` in the per-kernel entries'}
+
+    # device-timed batch sweep (100 is the reference notebooks' batch; 256 / 1024 / 4096 the sweep)
+    sweep = None
+    if args.sweep and world == 1:
+        sweep = {}
+        trainer = None
+        model._captured = None
+        for b in args.sweep:
+            if b == B:
+                sweep[str(b)] = {'samples_per_s': value, 'ms_per_step': ms_total / args.steps}
+                continue
+            m2, rh2, lh2, xd2, yd2 = make(b, 1)
+            fn2, _ = resident_stepper(m2, xd2, yd2, mode)
+            ms2, _, _ = timer.run(fn2, args.steps, W)
+            tr2 = m2.pipelined_trainer(perm=perm if use_perm else None, depth=2, use_graph=(mode == 'cuda_graph'))
+            for _ in range(3):
+                tr2.submit(rh2, lh2)
+            tr2.drain()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                tr2.submit(rh2, lh2)
+            tr2.drain()
+            a1.record()
+            torch.cuda.synchronize()
+            sweep[str(b)] = {'samples_per_s': b * args.steps / (ms2 * 1e-3), 'ms_per_step': ms2 / args.steps,
+                             'e2e_samples_per_s': b * args.steps / (a0.elapsed_time(a1) * 1e-3)}
+            tr2 = None
+            m2._captured = None
+            del m2, fn2
+
+    # captured graphs hold NCCL work: release them before the process group goes away
+    trainer = None
+    model._captured = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    cgdist.barrier()
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(config, B)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'name': config, 'batch_per_gpu': B, 'global_batch': B * world,
+                   'precision': 'fp32 storage and recurrence; tensor-core products as bf16 hi+mid split x3 with fp32 '
+                                'accumulation (error <= 2^-16 relative, inside rtol 1e-4)',
+                   'parallelism': 'dp%d' % world, 'l2': 'flushed between timed iterations (256 MB fill)',
+                   'timing': 'CUDA events per step on the launch stream, summed; max over ranks', 'launch': mode,
+                   'e2e_path': 'GraphModel.pipelined_trainer: pinned host batch -> H2D on a copy stream (2 buffers) -> '
+                               'cg_perm_data -> training step -> loss D2H; K steps in one event pair, no L2 flush '
+                               '(inputs come from the host every step)'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches), 'native_launches_per_step': native_per_step,
+        'roofline': roof, 'cpu_baseline': cpu, 'kernels_ms_per_step': kernel_ms,
+    }
+    if sustained:
+        line['sustained'] = sustained
+    if sweep:
+        line['batch_sweep'] = sweep
+    print(json.dumps(line), flush=True)

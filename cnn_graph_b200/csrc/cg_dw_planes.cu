@@ -303,7 +303,7 @@ int cg_run_dw_planes(const void *planes, const float *T, float *dW, long long R,
     dp.Fb = Fb;
     dp.K = K;
     {
-        CgProfScope prof("dw_umma", s);
+        CgProfScope prof("dw_planes", s);
         CG_CHECK_CUDA(cudaFuncSetAttribute(k_dw_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         k_dw_planes<<<(unsigned)pl.ctas, PT, pl.smem, s>>>(dp);
         CG_LAUNCH_CHECK();

@@ -555,7 +555,7 @@ int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int
     pp.a_mbs = a_mblk > 0 ? a_mbs : 0;
     const unsigned grid = (unsigned)std::min(pp.n_work, sm_count);
     {
-        CgProfScope prof("gemm_umma", s);
+        CgProfScope prof("gemm_pipe", s);
 #define CG_PIPE_LAUNCH(TA, TB)                                                                                       \
     do {                                                                                                              \
         CG_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pipe<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \

@@ -75,11 +75,13 @@ class PartitionedBasis:
     """T_k(L~) X for the rows of this rank.  `step_fn(x1_ext, x0_loc_or_None, alpha) -> out_loc` applies the local
     operator; the default is the native CUDA step (cg_cheb_step), tests inject a host function."""
 
-    def __init__(self, L_rescaled, rank=None, world=None, device=None, step_fn=None):
+    def __init__(self, L_rescaled, rank=None, world=None, device=None, step_fn=None, group=None):
+        # rank / world are those of `group` (None = the default process group): the halo exchange runs on it
+        self.group = group
         if rank is None:
-            rank = dist.get_rank() if dist.is_initialized() else 0
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
         if world is None:
-            world = dist.get_world_size() if dist.is_initialized() else 1
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.part = RowPartition(L_rescaled, rank, world)
         self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.send_index = torch.as_tensor(np.concatenate(self.part.send_idx) if world > 0 else np.zeros(0, np.int64),
@@ -108,7 +110,7 @@ class PartitionedBasis:
         ext = torch.empty((K, part.n_ext, C), dtype=torch.float32, device=x_loc.device)
         ext[0, :part.nloc] = x_loc
         for k in range(1, K):
-            _exchange(part, ext[k - 1], self.send_index)
+            _exchange(part, ext[k - 1], self.send_index, group=self.group)
             x0 = ext[k - 2, :part.nloc] if k > 1 else None
             alpha = 2.0 if k > 1 else 1.0
             if self._step_fn is not None:
@@ -135,8 +137,9 @@ class PartitionedFilter:
         L_rescaled = scipy.sparse.csr_matrix(L_rescaled, dtype=np.float32)
         self.K = int(K)
         self.group = group
-        self.fwd = PartitionedBasis(L_rescaled, rank, world, device, step_fn)
-        self.bwd = PartitionedBasis(scipy.sparse.csr_matrix(L_rescaled.T), rank, world, device, step_fn_t)
+        self.fwd = PartitionedBasis(L_rescaled, rank, world, device, step_fn, group=group)
+        self.bwd = PartitionedBasis(scipy.sparse.csr_matrix(L_rescaled.T), rank, world, device, step_fn_t, group=group)
+        self.exchange_kind = 'all_to_all_single (%s)' % (dist.get_backend(group) if dist.is_initialized() else 'single rank')
         self.part = self.fwd.part
         self._contract_fn, self._dw_fn = contract_fn, dw_fn
         self._saved = None

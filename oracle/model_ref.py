@@ -31,8 +31,10 @@ def init_params(L, F, K, p, M, seed=0, bias=True):
     return params
 
 
-def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool='mpool1', dropout_masks=None):
-    """Returns (loss, grads).  x [N, M0] float32, labels [N] int."""
+def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool='mpool1', dropout_masks=None,
+                     keep_stack=True):
+    """Returns (loss, grads).  x [N, M0] float32, labels [N] int.  ``keep_stack``: the forward keeps each layer's
+    restacked Chebyshev operand for the backward (what TF autodiff does, lib/models.py:207-220); False recomputes it."""
     N = x.shape[0]
     nconv = len(F)
     acts = []
@@ -40,10 +42,10 @@ def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool=
     for i in range(nconv):
         W = params['conv%d/weights' % (i + 1)]
         b = params.get('conv%d/bias' % (i + 1))
-        a = tf_ref.chebyshev5(h, L[i], W, K[i])
+        a, kept = tf_ref.chebyshev5(h, L[i], W, K[i], return_stack=True)
         r = tf_ref.b1relu(a, b)
         q = tf_ref.mpool1(r, p[i]) if pool == 'mpool1' else tf_ref.apool1(r, p[i])
-        acts.append((h, r))
+        acts.append((h, r, kept if keep_stack else None))
         h = q
     flat = h.reshape(N, -1)
     names = ['fc%d' % (i + 1) for i in range(len(M) - 1)] + ['logits']
@@ -84,13 +86,13 @@ def forward_backward(params, L, F, K, p, M, x, labels, regularization=0.0, pool=
             grads[n] = grads[n] + regularization * params[n]
     g = g.reshape(h.shape)
     for i in range(nconv - 1, -1, -1):
-        hin, r = acts[i]
+        hin, r, kept = acts[i]
         gr = tf_ref.mpool1_backward(r, p[i], g) if pool == 'mpool1' else tf_ref.apool1_backward(r, p[i], g)
         ga = (gr * (r > 0)).astype(np.float32)
         if 'conv%d/bias' % (i + 1) in params:
             grads['conv%d/bias' % (i + 1)] = ga.sum(axis=(0, 1)).reshape(1, 1, -1)
         W = params['conv%d/weights' % (i + 1)]
-        g, dW = tf_ref.chebyshev5_backward(hin, L[i], W, K[i], ga)
+        g, dW = tf_ref.chebyshev5_backward(hin, L[i], W, K[i], ga, a=kept, need_dx=i > 0)
         grads['conv%d/weights' % (i + 1)] = dW
     return loss, grads
 

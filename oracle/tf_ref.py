@@ -65,10 +65,11 @@ def cheb_basis_tf(x, L, K, lmax=2):
     return stack
 
 
-def chebyshev5(x, L, W, K, lmax=2):
+def chebyshev5(x, L, W, K, lmax=2, return_stack=False):
     """y [N, M, Fout] = chebyshev5(x [N, M, Fin]); W [Fin*K, Fout], row = fin*K + k.
 
-    lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95.
+    lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95.  ``return_stack``: also return the
+    restacked [N*M, Fin*K] matmul operand (lib/models.py:218-220), the tensor TF autodiff keeps for the backward.
     """
     N, M, Fin = x.shape
     Fout = W.shape[1]
@@ -76,7 +77,8 @@ def chebyshev5(x, L, W, K, lmax=2):
     stack = cheb_basis_tf(x.astype(np.float32, copy=False), L, K, lmax)
     a = stack.reshape(K, M, Fin, N)
     a = np.ascontiguousarray(np.transpose(a, (3, 1, 2, 0))).reshape(N * M, Fin * K)
-    return np.matmul(a, W.astype(np.float32, copy=False)).reshape(N, M, Fout)
+    y = np.matmul(a, W.astype(np.float32, copy=False)).reshape(N, M, Fout)
+    return (y, a) if return_stack else y
 
 
 def cheby_conv(x, L, lmax, feat_out, K, W):
@@ -115,8 +117,9 @@ def chebyshev2(x, L, W, K):
     return np.matmul(a, W).reshape(N, M, W.shape[1])
 
 
-def chebyshev5_backward(x, L, W, K, gy, lmax=2):
-    """(dx, dW) for y = chebyshev5(x).  SURVEY.md appendix A.3.
+def chebyshev5_backward(x, L, W, K, gy, lmax=2, a=None, need_dx=True):
+    """(dx, dW) for y = chebyshev5(x).  SURVEY.md appendix A.3.  ``a``: the restacked operand kept by the forward
+    (``chebyshev5(..., return_stack=True)``) -- what TF autodiff does; None recomputes the basis.
 
     dW[fin*K+k, fo] = sum_{n,m} Xk[m, fin*N+n] gy[n,m,fo]
     Gk = gy W_k^T;  for k = K-1..2: G_{k-1} += 2 L~^T G_k, G_{k-2} -= G_k;
@@ -124,10 +127,13 @@ def chebyshev5_backward(x, L, W, K, gy, lmax=2):
     """
     N, M, Fin = x.shape
     Fout = W.shape[1]
-    stack = cheb_basis_tf(x.astype(np.float32, copy=False), L, K, lmax)
-    a = np.transpose(stack.reshape(K, M, Fin, N), (3, 1, 2, 0)).reshape(N * M, Fin * K)
+    if a is None:
+        stack = cheb_basis_tf(x.astype(np.float32, copy=False), L, K, lmax)
+        a = np.transpose(stack.reshape(K, M, Fin, N), (3, 1, 2, 0)).reshape(N * M, Fin * K)
     g2 = gy.reshape(N * M, Fout).astype(np.float32, copy=False)
     dW = np.matmul(a.T, g2)
+    if not need_dx:
+        return None, dW
     ga = np.matmul(g2, W.T)                               # [N*M, Fin*K]
     G = np.transpose(ga.reshape(N, M, Fin, K), (3, 1, 2, 0)).reshape(K, M, Fin * N).copy()
     Lt = _rescaled_csr(L, lmax).T.tocsr()

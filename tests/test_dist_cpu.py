@@ -200,3 +200,72 @@ def test_row_partitioned_filter_forward_backward(world):
         out = mgr.dict()
         mp.spawn(_filter_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {r: (True, True, True) for r in range(world)}
+
+
+def _subgroup_worker(rank, world, port, out):
+    """The filter partitioned over a NON-default subgroup {1, 2} of a 3-rank world: halo exchange and the dW
+    all-reduce must both run on that group with the group's own rank / size."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    import numpy as np
+    import scipy.sparse
+    from cnn_graph_b200 import dist as cgdist, partition
+    from oracle import tf_ref
+    cgdist.init_from_env('gloo')
+    group = torch.distributed.new_group([1, 2])
+    if rank == 0:
+        out[rank] = (True, True, True)
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        return
+    rng = np.random.RandomState(9)
+    M, Fin, Fout, K = 91, 3, 4, 5
+    A = scipy.sparse.random(M, M, density=0.06, random_state=rng, format='csr', dtype=np.float32)
+    Lr = scipy.sparse.csr_matrix(0.1 * A, dtype=np.float32)
+    x = rng.standard_normal((M, Fin)).astype(np.float32)
+    W = (0.3 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((M, Fout)).astype(np.float32)
+    holder = {}
+
+    def make_step(which):
+        def step(x1_ext, x0, alpha):
+            part = getattr(holder['pf'], which).part
+            y = alpha * (part.local @ x1_ext.numpy())[:part.nloc]
+            if x0 is not None:
+                y = y - x0.numpy()
+            return torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        return step
+
+    def contract(stack, Wt, transposed):
+        Wk = Wt.reshape(Fin, K, Fout)
+        return torch.einsum('krf,fko->ro', stack, Wk) if not transposed else torch.einsum('kro,fko->rf', stack, Wk)
+
+    def dw(stack, g):
+        return torch.einsum('krf,ro->fko', stack, g).reshape(Fin * K, Fout)
+
+    pf = partition.PartitionedFilter(Lr, K, device=torch.device('cpu'), step_fn=make_step('fwd'), step_fn_t=make_step('bwd'),
+                                     contract_fn=contract, dw_fn=dw, group=group)
+    holder['pf'] = pf
+    assert (pf.part.rank, pf.part.world) == (rank - 1, 2)
+    r0, r1 = pf.part.r0, pf.part.r1
+    y = pf.forward(torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(W)).numpy()
+    dx, dW = pf.backward(torch.from_numpy(gy[r0:r1].copy()))
+    Lfull = scipy.sparse.csr_matrix(Lr + scipy.sparse.identity(M, dtype=np.float32, format='csr'))
+    ref_y = tf_ref.chebyshev5(x[None], Lfull, W, K)[0]
+    ref_dx, ref_dW = tf_ref.chebyshev5_backward(x[None], Lfull, W, K, gy[None])
+
+    def rel(a, b):
+        return float(np.abs(a - b).max()) / max(float(np.abs(b).max()), 1e-30)
+
+    out[rank] = (rel(y, ref_y[r0:r1]) < 1e-5, rel(dx.numpy(), ref_dx[0][r0:r1]) < 1e-5, rel(dW.numpy(), ref_dW) < 1e-5)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_row_partitioned_filter_on_subgroup():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_subgroup_worker, args=(3, port, out), nprocs=3, join=True)
+        assert dict(out) == {r: (True, True, True) for r in range(3)}

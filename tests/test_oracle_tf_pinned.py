@@ -128,3 +128,33 @@ def test_reference_inference_variants_recorded(tfl):
     assert len(status) == 12
     broken = {k for k, v in status.items() if v != 'ok'}
     assert broken == {'inference_glstm_period_no_expand'}            # float reshape at lib/gconv_lstm.py:288
+
+
+def test_torch_mirror_matches_reference_source(tff, tfl):
+    """oracle/torch_ref.py (the CPU arm of bench.py --config c4|c5) against the same fixtures."""
+    import torch
+    from oracle import torch_ref
+    for name in ('c4', 'directed', 'k1'):
+        L = csr_from(tff, name + '_L')
+        lmax, N, Fin, Fout, K = tff[name + '_meta']
+        x = torch.tensor(tff[name + '_x'], requires_grad=True)
+        W = torch.tensor(tff[name + '_W'], requires_grad=True)
+        y = torch_ref.cheby_conv(x, torch_ref.sparse_operator(L, lmax), int(K), W)
+        y.backward(torch.tensor(tff[name + '_gy']))
+        close(y.detach().numpy(), tff[name + '_y'])
+        close(x.grad.numpy(), tff[name + '_dx'])
+        close(W.grad.numpy(), tff[name + '_dW'])
+    L = csr_from(tfl, 'L')
+    N, Fin, H, K = (int(v) for v in tfl['cell_meta'])
+    Ls = torch_ref.sparse_operator(L, 2)
+    for variant in ('fork', 'standard'):
+        pre = variant + '_'
+        Wx = {g: torch.tensor(tfl[pre + 'W%sxt' % g]) for g in 'zifo'}
+        Wh = {g: torch.tensor(tfl[pre + 'W%sht' % g]) for g in 'zifo'}
+        b = {g: torch.tensor(tfl[pre + 'b%st' % g]) for g in 'zifo'}
+        x = torch.tensor(tfl['cell_x'], requires_grad=True)
+        h, c = torch_ref.lstm_cell(x, torch.tensor(tfl['cell_c']), torch.tensor(tfl['cell_h']), Ls, K, Wx, Wh, b, variant)
+        torch.autograd.backward([h, c], [torch.tensor(tfl['cell_gh']), torch.tensor(tfl['cell_gc'])])
+        close(h.detach().numpy(), tfl[pre + 'new_h'])
+        close(c.detach().numpy(), tfl[pre + 'new_c'])
+        close(x.grad.numpy(), tfl[pre + 'dx'])
