@@ -1,7 +1,11 @@
 // Host-side native loops of the coarsening: the two pure-Python
-// loops of the reference that make large graphs impractical.  Arithmetic is float32 in
-// the reference's order (numpy >= 2 scalar promotion), no fast-math, so cluster ids are
-// bit-identical to lib/coarsening.py on the same inputs.
+// loops of the reference that make large graphs impractical.  The match score
+// vv * (1/w[v] + 1/w[u]) is evaluated in the reference's order, no fast-math, in the dtype numpy
+// gives it: float32 for a float32 adjacency under numpy >= 2 (weak Python scalars; what the pinned
+// fixtures of tests/golden were generated with), float64 for a float64 adjacency, and -- the
+// `_f64` entry fed with widened float32 inputs -- float64 under the legacy value-based promotion of
+// the numpy 1.x the reference was written for.  Parity is against the oracle port and the
+// reference-generated fixtures (tests/test_host_lib.py).
 #include <stdint.h>
 
 #include <vector>
@@ -11,9 +15,9 @@
 void cg_set_error(const char *fmt, ...);
 
 // lib/coarsening.py:119-165
-extern "C" int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int64_t *cc, const float *vv,
-                                       const int64_t *rid, int64_t n_rid, const float *weights,
-                                       int32_t *cluster_id, int64_t *nclusters) {
+template <typename T>
+static int metis_one_level(int64_t nnz, const int64_t *rr, const int64_t *cc, const T *vv, const int64_t *rid,
+                           int64_t n_rid, const T *weights, int32_t *cluster_id, int64_t *nclusters) {
     if (nnz <= 0 || !rr || !cc || !vv || !rid || !weights || !cluster_id || !nclusters) {
         cg_set_error("cg_host_metis_one_level: bad arguments");
         return CG_ERR_ARG;
@@ -50,7 +54,7 @@ extern "C" int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int
         }
         if (marked[(size_t)v]) continue;
         marked[(size_t)v] = 1;
-        float best_w = 0.0f;
+        T best_w = (T)0;
         int64_t best = -1;
         const int64_t base = rowstart[(size_t)v];
         for (int64_t j = 0; j < rowlength[(size_t)v]; ++j) {
@@ -63,13 +67,13 @@ extern "C" int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int
                 cg_set_error("cg_host_metis_one_level: column %lld out of range", (long long)u);
                 return CG_ERR_ARG;
             }
-            float w;
+            T w;
             if (marked[(size_t)u]) {
-                w = 0.0f;
+                w = (T)0;
             } else {
-                const float inv_v = 1.0f / weights[v];
-                const float inv_u = 1.0f / weights[u];
-                const float s = inv_v + inv_u;
+                const T inv_v = (T)1 / weights[v];
+                const T inv_u = (T)1 / weights[u];
+                const T s = inv_v + inv_u;
                 w = vv[base + j] * s;
             }
             if (w > best_w) {
@@ -86,6 +90,18 @@ extern "C" int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int
     }
     *nclusters = count;
     return CG_OK;
+}
+
+extern "C" int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int64_t *cc, const float *vv,
+                                       const int64_t *rid, int64_t n_rid, const float *weights,
+                                       int32_t *cluster_id, int64_t *nclusters) {
+    return metis_one_level<float>(nnz, rr, cc, vv, rid, n_rid, weights, cluster_id, nclusters);
+}
+
+extern "C" int cg_host_metis_one_level_f64(int64_t nnz, const int64_t *rr, const int64_t *cc, const double *vv,
+                                           const int64_t *rid, int64_t n_rid, const double *weights,
+                                           int32_t *cluster_id, int64_t *nclusters) {
+    return metis_one_level<double>(nnz, rr, cc, vv, rid, n_rid, weights, cluster_id, nclusters);
 }
 
 // lib/coarsening.py:179-204, one level

@@ -213,15 +213,16 @@ class ChebFilterFn(torch.autograd.Function):
                     stack = torch.empty((K, N, M, Fin), dtype=torch.float32, device=x.device)
         check(lib.cg_cheb_filter_fwd_ex(handle.handle, ptr(x), ptr(W), ptr(y), ptr(stack), N, Fin, Fout, K, ptr(ws),
                                         nbytes, flags, _stream()), 'cg_cheb_filter_fwd_ex')
-        ctx.stack = stack
         ctx.stack_planes = bool(flags & FILTER_STACK_PLANES)
-        ctx.save_for_backward(x, W)
+        # the saved basis goes through save_for_backward: autograd frees it with the graph and keeps it under
+        # retain_graph=True (a second backward sees the same basis, not a NULL pointer)
+        ctx.save_for_backward(x, W, stack)
         ctx.handle, ctx.K, ctx.grad_x, ctx.flags = handle, K, grad_x, flags
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, W = ctx.saved_tensors
+        x, W, stack = ctx.saved_tensors
         handle, K, flags = ctx.handle, ctx.K, ctx.flags
         gy = _f32c(gy)
         N, M, Fin = x.shape
@@ -232,9 +233,8 @@ class ChebFilterFn(torch.autograd.Function):
         dW = torch.empty_like(W)
         nbytes = lib.cg_cheb_filter_bwd_workspace_bytes(handle.handle, N, Fin, Fout, K, int(need_dx), flags)
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
-        check(lib.cg_cheb_filter_bwd_ex(handle.handle, ptr(x), ptr(W), ptr(gy), ptr(ctx.stack), ptr(dx), ptr(dW), N,
+        check(lib.cg_cheb_filter_bwd_ex(handle.handle, ptr(x), ptr(W), ptr(gy), ptr(stack), ptr(dx), ptr(dW), N,
                                         Fin, Fout, K, ptr(ws), nbytes, flags, _stream()), 'cg_cheb_filter_bwd_ex')
-        ctx.stack = None
         return dx, dW, None, None, None, None
 
 
@@ -391,7 +391,10 @@ class FirstLayerFn(torch.autograd.Function):
     def forward(ctx, x, W, bias, handle, K):
         _require_cuda(x, W, bias)
         x, W = _f32c(x), _f32c(W)
-        N, M, _ = x.shape
+        N, M, Fin = x.shape
+        if Fin != 1 or M % 4 != 0 or M != handle.M or W.shape[0] != K:
+            raise ValueError('FirstLayerFn: needs x [N, M, 1] with M %% 4 == 0 on the graph (M = %d) and W [K, Fout]; got x %r, '
+                             'W %r, K = %d' % (handle.M, tuple(x.shape), tuple(W.shape), K))
         Fout = W.shape[1]
         lib = _native.lib()
         bkind = 0
@@ -415,14 +418,14 @@ class FirstLayerFn(torch.autograd.Function):
                                             _stream()), 'cg_cheb_filter_fwd_ex')
             check(lib.cg_bias_act_pool_fwd(ptr(y), ptr(bias), ptr(yp), ptr(aux), N, M, Fout, 4, bkind, ACT['relu'], 1, _stream()),
                   'cg_bias_act_pool_fwd')
-        ctx.save_for_backward(yp, aux)
-        ctx.stack, ctx.handle, ctx.K = stack, handle, K
+        ctx.save_for_backward(yp, aux, stack)
+        ctx.handle, ctx.K = handle, K
         ctx.w_shape, ctx.bias_shape = tuple(W.shape), None if bias is None else tuple(bias.shape)
         return yp
 
     @staticmethod
     def backward(ctx, g):
-        yp, aux = ctx.saved_tensors
+        yp, aux, stack = ctx.saved_tensors
         g = _f32c(g)
         N, Mp, Fout = yp.shape
         K, handle = ctx.K, ctx.handle
@@ -433,9 +436,8 @@ class FirstLayerFn(torch.autograd.Function):
             db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=yp.device)
         nbytes = lib.cg_cheb_dw_pooled_workspace_bytes(handle.handle, N, Fout, K)
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=yp.device)
-        check(lib.cg_cheb_dw_pooled(handle.handle, ptr(ctx.stack), ptr(g), ptr(yp), ptr(aux), ptr(dW), ptr(db), N, Fout, K,
+        check(lib.cg_cheb_dw_pooled(handle.handle, ptr(stack), ptr(g), ptr(yp), ptr(aux), ptr(dW), ptr(db), N, Fout, K,
                                     ptr(ws), nbytes, _stream()), 'cg_cheb_dw_pooled')
-        ctx.stack = None
         return None, dW, db, None, None
 
 

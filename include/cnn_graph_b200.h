@@ -266,6 +266,12 @@ int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, 
 int cg_host_metis_one_level(int64_t nnz, const int64_t *rr, const int64_t *cc, const float *vv,
                             const int64_t *rid, int64_t n_rid, const float *weights,
                             int32_t *cluster_id, int64_t *nclusters);
+/* Same loop with the match score vv*(1/w[v] + 1/w[u]) in float64: float64 adjacencies, and float32
+ * ones (widened by the caller) under numpy 1.x value-based promotion, where the Python scalar 1.0
+ * makes the reference's score float64 (lib/coarsening.py:150).                              */
+int cg_host_metis_one_level_f64(int64_t nnz, const int64_t *rr, const int64_t *cc, const double *vv,
+                                const int64_t *rid, int64_t n_rid, const double *weights,
+                                int32_t *cluster_id, int64_t *nclusters);
 /* lib/coarsening.py:179-204 (one level of compute_perm): children of the
  * vertices listed in `order` (length n_order) under `parent` (length n_parent),
  * singletons padded with fake ids starting at n_parent.  out has 2*n_order.  */

@@ -533,7 +533,7 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
         try:
             xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
             y = ops.cheb_filter(xt, Wt, L, K)
-            assert (y.grad_fn.stack is not None) == save
+            assert (y.grad_fn.saved_tensors[2] is not None) == save
             y.backward(dev(gy))
             grads.append((xt.grad.cpu().numpy(), Wt.grad.cpu().numpy()))
         finally:
@@ -551,7 +551,7 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
     y = ops.cheb_filter(dev(x).requires_grad_(True), dev(W), L, K)
     assert y.grad_fn.stack_planes
     nch = (N * M + 127) // 128
-    pl = y.grad_fn.stack.reshape(2, K, nch, Fin // 8, 128, 8).float().sum(0)          # [K, chunk, octet, row, 8]
+    pl = y.grad_fn.saved_tensors[2].reshape(2, K, nch, Fin // 8, 128, 8).float().sum(0)          # [K, chunk, octet, row, 8]
     basis = pl.permute(0, 1, 3, 2, 4).reshape(K, nch * 128, Fin)[:, :N * M].reshape(K, N, M, Fin).cpu().numpy()
     close(basis.transpose(0, 2, 1, 3).reshape(K, M, N * Fin), ref, 3e-5)
     # the fp32 format [K, N, M, Fin] on request: same basis, same gradients
@@ -560,7 +560,7 @@ def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
         xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
         y = ops.cheb_filter(xt, Wt, L, K)
         assert not y.grad_fn.stack_planes
-        stack = y.grad_fn.stack.cpu().numpy()
+        stack = y.grad_fn.saved_tensors[2].cpu().numpy()
         y.backward(dev(gy))
     finally:
         ops.set_stack_planes(True)
@@ -821,7 +821,7 @@ def test_first_layer_fused_node_vs_separate_ops_and_oracle(ops, tf_ref, c2, leve
     bt = dev(b).requires_grad_(True) if with_bias else None
     assert ops.first_layer_supported(dev(x), Wt, bt, L, K, 'relu', 4, 'max')
     yp = ops.first_layer(dev(x), Wt, bt, L, K)
-    ypn, aux = (t.detach().cpu().numpy() for t in yp.grad_fn.saved_tensors)       # pooled output, argmax bytes
+    ypn, aux = (t.detach().cpu().numpy() for t in yp.grad_fn.saved_tensors[:2])       # pooled output, argmax bytes
     yp.backward(dev(g))
     W2 = dev(W).requires_grad_(True)
     b2 = dev(b).requires_grad_(True) if with_bias else None
@@ -883,3 +883,36 @@ def test_unfused_clenshaw_input_gradient(ops, tf_ref, N, Fin, Fout, K):
         close(Wt.grad, dW)
         got.append(xt.grad.cpu().numpy())
     close(got[0], got[1], 2e-5)
+
+
+def test_second_backward_through_retained_graph(ops, tf_ref, c2):
+    """retain_graph=True: the saved basis lives in autograd's saved tensors, so a second backward through the same
+    graph gives the same gradients (filter node and fused first-layer node)."""
+    L = csr_from(c2, 'L2')
+    M = L.shape[0]
+    rng = np.random.RandomState(11)
+    N, Fin, Fout, K = 9, 32, 64, 6
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+    y = ops.cheb_filter(xt, Wt, L, K)
+    g1 = torch.autograd.grad(y, (xt, Wt), dev(gy), retain_graph=True)
+    g2 = torch.autograd.grad(y, (xt, Wt), dev(gy))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+    for a, b in zip(g1, g2):
+        assert torch.equal(a, b)
+    close(g2[0], dx)
+    close(g2[1], dW)
+    L0 = csr_from(c2, 'L0')
+    M0 = L0.shape[0]
+    x0 = rng.standard_normal((16, M0, 1)).astype(np.float32)
+    W0 = dev((0.1 * rng.standard_normal((25, 32))).astype(np.float32)).requires_grad_(True)
+    b0 = dev((0.1 * rng.standard_normal(32)).astype(np.float32)).requires_grad_(True)
+    if ops.first_layer_supported(dev(x0), W0, b0, L0, 25, 'relu', 4, 'max'):
+        yp = ops.first_layer(dev(x0), W0, b0, L0, 25)
+        g = dev(rng.standard_normal(tuple(yp.shape)).astype(np.float32))
+        h1 = torch.autograd.grad(yp, (W0, b0), g, retain_graph=True)
+        h2 = torch.autograd.grad(yp, (W0, b0), g)
+        for a, b in zip(h1, h2):
+            assert torch.equal(a, b)
