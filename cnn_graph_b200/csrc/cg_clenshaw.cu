@@ -36,6 +36,8 @@ struct ClenshawParams {
     float *dx;                   // [N][M][Fi]
     int N, M, Fi, Fo, K, S, tiles, tmem_cols, ns, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_gbuf, off_w, wplane_bytes, off_bar;
+    BlkTables bt;                // row-block form of L~^T (k_cheb_clenshaw_b); its tables live at off_ent
+    uint32_t off_wsz;
 };
 
 // LPR lanes per row (Fi = 4 * LPR), IPT items (row, 4-column chunk) per compute thread
@@ -312,20 +314,257 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw(const ClenshawParams p)
     if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
+// The same kernel with the row-block gather of cg_fused_common.cuh (a compute thread owns IPB items of 4 consecutive
+// rows x 4 features); issue warp, TMEM ring and the G dump are unchanged.
+template <int LPR, int IPB>
+__global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *wbar = bars;              // [2] W_k landed
+    uint64_t *gfull = bars + 2;         // [ns] MMAs of the G in this TMEM slot completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + MAX_NS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.M, Fi = p.Fi, Fo = p.Fo, K = p.K, S = p.S, NS = p.ns;
+    const bool is_issuer = warp == CC / 32;
+    constexpr uint32_t SWZ = LPR >= 8 ? 7u : (uint32_t)(LPR - 1);     // chunk swizzle mask of the G buffer
+    const uint32_t rowb = (uint32_t)Fi * 4u;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2 + MAX_NS; ++i) umma::mbar_init(bars + i, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+
+    BlkItems<IPB> it;
+    blk_setup<LPR, IPB, CC>(p.bt, S, rowb, umma::smem_u32(smem + p.off_ent), reinterpret_cast<int *>(smem + p.off_wsz), it);
+    uint32_t a_g[IPB], a_soff[IPB];
+    int r0[IPB], nrow[IPB];
+    const uint32_t lc = (uint32_t)(tid % LPR);
+#pragma unroll
+    for (int i = 0; i < IPB; ++i) {
+        r0[i] = it.samp[i] * M + it.row0[i];
+        a_g[i] = 4u * (uint32_t)(it.samp[i] * M * Fi) + 16u * lc;
+        a_soff[i] = 4u * (uint32_t)(r0[i] * Fi) + 16u * lc;
+        nrow[i] = it.samp[i] < S ? min(4, M - it.row0[i]) : 0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (p.N + S - 1) / S;
+    const uint32_t slab0 = umma::smem_u32(smem + p.off_slab);
+    const uint32_t gbuf0 = umma::smem_u32(smem + p.off_gbuf);
+    const uint32_t wbytes = 2 * p.wplane_bytes;
+    const uint32_t w0 = umma::smem_u32(smem + p.off_w);
+    const uint32_t g_col0 = (uint32_t)(p.tiles * Fo);            // TMEM: A planes first, then the G ring
+    const uint32_t g_slot = (uint32_t)(p.tiles * Fi);
+    uint32_t gpar = 0;
+    uint32_t wpar = 0;
+
+    for (int g = blockIdx.x; g < G; g += gridDim.x) {
+        const int n0 = g * S;
+        const int Sg = min(S, p.N - n0);
+        const int Rg = Sg * M;
+
+        if (is_issuer) {
+            // =========================== issue warp (as k_cheb_clenshaw) ================
+            if (lane == 0) {
+                mbar_expect_tx(wbar, wbytes);
+                bulk_g2s(w0, p.wp + (size_t)(K - 1) * wbytes, wbytes, wbar);
+                if (K > 1) {
+                    mbar_expect_tx(wbar + 1, wbytes);
+                    bulk_g2s(w0 + wbytes, p.wp + (size_t)(K - 2) * wbytes, wbytes, wbar + 1);
+                }
+            }
+            const uint32_t idesc = umma::make_idesc_bf16(128, Fi, 0, 0);
+            const uint32_t lbo_w = (uint32_t)Fi * 16u;
+            const uint32_t d_hi = umma::desc_hi(128u);
+            const int nk16 = Fo / 16;
+            auto issue = [&](int k) {
+                const int slot = (K - 1 - k) % NS, bw = (K - 1 - k) & 1;
+                umma::mbar_wait(wbar + bw, (wpar >> bw) & 1u);
+                wpar ^= 1u << bw;
+                umma::fence_after_sync();
+                const uint32_t b_lo = umma::desc_lo(w0 + (uint32_t)bw * wbytes, lbo_w);
+                const uint32_t b_mid = p.wplane_bytes >> 4, b_k = (2u * lbo_w) >> 4;
+                for (int t = 0; t < p.tiles; ++t) {
+                    const uint32_t acc = tmem + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi);
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        uint32_t a_col = tmem + (uint32_t)(t * Fo) + (pass == 1 ? (uint32_t)(Fo / 2) : 0u);
+                        uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
+                        for (int j = 0; j < nk16; ++j) {
+                            umma::mma_bf16_ts(acc, a_col, umma::desc_join(bl, d_hi), idesc, (pass | j) != 0);
+                            a_col += 8u;
+                            bl += b_k;
+                        }
+                    }
+                }
+                umma::commit(gfull + slot);
+                if (k + 1 < K) {
+                    const int sp = (K - 2 - k) % NS;
+                    umma::mbar_wait(gfull + sp, (gpar >> sp) & 1u);
+                    gpar ^= 1u << sp;
+                    if (k >= 1) {
+                        const int bn = (K - k) & 1;
+                        mbar_expect_tx(wbar + bn, wbytes);
+                        bulk_g2s(w0 + (uint32_t)bn * wbytes, p.wp + (size_t)(k - 1) * wbytes, wbytes, wbar + bn);
+                    }
+                }
+                if (k == 0) {
+                    umma::mbar_wait(gfull + slot, (gpar >> slot) & 1u);
+                    gpar ^= 1u << slot;
+                }
+            };
+            __syncthreads();                         // sync A: gy of this group is in tensor memory
+            if (lane == 0 && umma::elect_lane0())
+                for (int k = K - 1; k >= 0 && k > K - 1 - NS; --k) issue(k);
+            __syncwarp();
+            for (int j = 0; j <= K; ++j) {
+                __syncthreads();                     // sync j: G_{K-1-j} has left its slot
+                const int kn = K - 1 - j - NS;
+                if (kn >= 0 && lane == 0 && umma::elect_lane0()) issue(kn);
+                __syncwarp();
+            }
+        } else {
+            // =========================== compute warps ==================================
+            const int q = warp & 3, sub = warp >> 2;
+            const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+            for (int t = 0; t < p.tiles; ++t) {
+                const int r = t * 128 + 32 * q + lane;
+                const float *src = p.gy + ((size_t)n0 * M + r) * Fo;
+                for (int sl = sub; sl < Fo / 16; sl += 4) {
+                    uint32_t hi[8], mid[8];
+                    if (r < Rg) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float4 v = *reinterpret_cast<const float4 *>(src + sl * 16 + h * 4);
+                            uint2 a, b;
+                            split4(v, a, b);
+                            hi[2 * h] = a.x;
+                            hi[2 * h + 1] = a.y;
+                            mid[2 * h] = b.x;
+                            mid[2 * h + 1] = b.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) hi[h] = mid[h] = 0u;
+                    }
+                    umma::tmem_st8(tmem + lane_base + (uint32_t)(t * Fo + sl * 8), hi);
+                    umma::tmem_st8(tmem + lane_base + (uint32_t)(t * Fo + Fo / 2 + sl * 8), mid);
+                }
+            }
+            umma::tmem_st_wait();
+            umma::fence_before_sync();
+            __syncthreads();                         // sync A
+
+            auto dump = [&](int k) {
+                const int slot = (K - 1 - k) % NS;
+                umma::mbar_wait(gfull + slot, (gpar >> slot) & 1u);
+                gpar ^= 1u << slot;
+                umma::fence_after_sync();
+                const uint32_t gb = gbuf0 + (uint32_t)(k & 1) * p.slab_bytes;
+                const int nc8 = Fi / 8;
+                for (int t = 0; t < p.tiles; ++t) {
+                    const int r = t * 128 + 32 * q + lane;
+                    for (int c = sub; c < nc8; c += 4) {
+                        float v[8];
+                        umma::tmem_ld8(tmem + lane_base + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi + c * 8), v);
+                        umma::tmem_ld_wait();
+                        if (r < Rg) {
+                            const uint32_t row = gb + 4u * (uint32_t)(r * Fi);
+                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)r & SWZ)), make_float4(v[0], v[1], v[2], v[3]));
+                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)r & SWZ)), make_float4(v[4], v[5], v[6], v[7]));
+                        }
+                    }
+                }
+            };
+
+            dump(K - 1);
+            umma::fence_before_sync();
+            __syncthreads();                         // sync 0
+
+            int nr[IPB];
+            constexpr bool OLD_REGS = IPB == 1;      // two items per thread: b_{k+2} is read back from the slab it sits in
+            float4 res[IPB][4], old[OLD_REGS ? IPB : 1][4];
+#pragma unroll
+            for (int i = 0; i < IPB; ++i) {
+                nr[i] = it.samp[i] < Sg ? nrow[i] : 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) res[i][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if constexpr (OLD_REGS) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) old[0][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int s = 0; s < K; ++s) {
+                const int k = K - 1 - s;
+                const uint32_t prev = slab0 + (uint32_t)((s + 1) & 1) * p.slab_bytes;     // b_{k+1}
+                const uint32_t cur = slab0 + (uint32_t)(s & 1) * p.slab_bytes;            // receives b_k (holds b_{k+2})
+                const uint32_t gb = gbuf0 + (uint32_t)(k & 1) * p.slab_bytes;
+                const float c2 = k > 0 ? 2.f : 1.f;
+                char *dxp = reinterpret_cast<char *>(p.dx + (size_t)n0 * M * Fi);
+#pragma unroll
+                for (int i = 0; i < IPB; ++i) {
+                    float4 acc[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s > 0) blk_gather<LPR>(prev + a_g[i], it.tab[i], it.trips[i], acc);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool v = r < nr[i];
+                        const uint32_t rr = (uint32_t)(r0[i] + r);
+                        float4 Gv = make_float4(0.f, 0.f, 0.f, 0.f), o = Gv;
+                        if (v) Gv = lds128(gb + 4u * rr * (uint32_t)Fi + 16u * (lc ^ (rr & SWZ)));
+                        if constexpr (OLD_REGS) {
+                            o = old[i][r];
+                        } else {
+                            if (v && s >= 2) o = lds128(cur + a_soff[i] + (uint32_t)r * rowb);
+                        }
+                        // b_k = G_k + c L^T b_{k+1} - b_{k+2}
+                        acc[r] = make_float4(fmaf(c2, acc[r].x, Gv.x) - o.x, fmaf(c2, acc[r].y, Gv.y) - o.y,
+                                             fmaf(c2, acc[r].z, Gv.z) - o.z, fmaf(c2, acc[r].w, Gv.w) - o.w);
+                        if constexpr (OLD_REGS) old[i][r] = res[i][r];
+                        res[i][r] = acc[r];
+                        if (v) {
+                            if (k > 0)
+                                sts128(cur + a_soff[i] + (uint32_t)r * rowb, acc[r]);
+                            else
+                                *reinterpret_cast<float4 *>(dxp + a_soff[i] + (uint32_t)r * rowb) = acc[r];
+                        }
+                    }
+                }
+                if (k > 0) dump(k - 1);
+                umma::fence_before_sync();
+                __syncthreads();                     // sync s+1
+            }
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
 struct CPlan {
     bool ok = false;
     int S = 0, ipt = 0;
+    bool blocked = false;
     ClenshawParams cp;
     size_t smem = 0;
 };
 
-static CPlan make_cplan(const cg_graph *g, int width, int N, int Fi, int Fo, int K) {
+static CPlan make_cplan(const cg_graph *g, int N, int Fi, int Fo, int K, bool blocked) {
     CPlan best;
     if (Fi % 16 != 0 || Fi > 128 || (Fi & (Fi - 1)) != 0) return best;     // LPR in {4, 8, 16, 32}
     if (Fo % 16 != 0 || Fo < 16 || Fo > 256) return best;
     if (N <= 0 || K < 1) return best;
-    const int M = g->M, LPR = Fi / 4;
-    const double avg = M > 0 ? (double)g->nnz / M : 0.0;
+    const CgCsr &side = g->adj;
+    if (blocked && side.nblk == 0) return best;
+    const int M = g->M, LPR = Fi / 4, width = side.width;
+    const double avg = M > 0 ? (double)(blocked ? 4 * (int64_t)side.blk_total : g->nnz) / M : 0.0;
     const int estride = std::max(2, (width + 1) & ~1);
     double best_cost = 0.0;
     int s_lo = 1, s_hi = 64;
@@ -339,18 +578,28 @@ static CPlan make_cplan(const cg_graph *g, int width, int N, int Fi, int Fo, int
         // TMEM: tiles * Fo columns of gy planes + at least two G slots of tiles * Fi columns
         const int ns = std::min(MAX_NS, (512 - tiles * Fo) / (tiles * Fi));
         if (tiles * Fo > 512 || ns < 2) break;
-        const int need = (int)cg_ceil_div(R * LPR, CC);
-        if (need > 8) break;
-        const int ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+        int need, ipt;
+        if (blocked) {
+            need = (int)cg_ceil_div((int64_t)S * side.nblk * LPR, CC);
+            if (need > 2) break;
+            ipt = need;
+        } else {
+            need = (int)cg_ceil_div(R * LPR, CC);
+            if (need > 8) break;
+            ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+        }
         const uint32_t slab = (uint32_t)cg_align_up((size_t)R * Fi * 4, 128);
         const uint32_t wplane = (uint32_t)Fi * Fo * 2u;
+        const size_t ent_bytes = blocked ? cg_blk_table_bytes(side.blk_len_sorted, S, LPR, ipt, CC) : (size_t)M * estride * 8;
         ClenshawParams cp;
         memset(&cp, 0, sizeof(cp));
         uint32_t off = 0;
         cp.off_bar = off;
         off += 128;
+        cp.off_wsz = off;
+        off += 256;
         cp.off_ent = off;
-        off += (uint32_t)cg_align_up((size_t)M * estride * 8, 128);
+        off += (uint32_t)cg_align_up(ent_bytes, 128);
         cp.off_slab = off;
         off += 2 * slab;
         cp.off_gbuf = off;
@@ -360,13 +609,15 @@ static CPlan make_cplan(const cg_graph *g, int width, int N, int Fi, int Fo, int
         if (off > g->smem_optin) continue;
         const int64_t G = cg_ceil_div(N, S);
         const int64_t rounds = cg_ceil_div(G, g->sm_count);
-        const double step = (double)need * (avg * 7.0 + 60.0) * (need > 4 ? 1.6 : 1.0) + 300.0;
+        const double step = blocked ? (double)need * (avg * 5.5 + 140.0) + 300.0
+                                    : (double)need * (avg * 7.0 + 60.0) * (need > 4 ? 1.6 : 1.0) + 300.0;
         const double cost = (double)rounds * ((double)K * step + 1500.0);
         if (!best.ok || cost < best_cost) {
             best.ok = true;
             best_cost = cost;
             best.S = S;
             best.ipt = ipt;
+            best.blocked = blocked;
             cp.S = S;
             cp.tiles = tiles;
             cp.ns = ns;
@@ -383,6 +634,16 @@ static CPlan make_cplan(const cg_graph *g, int width, int N, int Fi, int Fo, int
     return best;
 }
 
+static CPlan choose_cplan(const cg_graph *g, int N, int Fi, int Fo, int K) {
+    bool blocked = g->adj.nblk > 0 && (int64_t)g->adj.blk_total * 10 <= g->nnz * 8;
+    if (const char *env = getenv("CG_FUSED_BLOCK")) blocked = atoi(env) != 0;
+    if (blocked) {
+        CPlan pb = make_cplan(g, N, Fi, Fo, K, true);
+        if (pb.ok) return pb;
+    }
+    return make_cplan(g, N, Fi, Fo, K, false);
+}
+
 template <int LPR>
 static cudaError_t launch_c(const CPlan &pl, dim3 grid, cudaStream_t s) {
 #define CG_CL_CASE(I)                                                                                              \
@@ -392,6 +653,22 @@ static cudaError_t launch_c(const CPlan &pl, dim3 grid, cudaStream_t s) {
         if (e != cudaSuccess) return e;                                                                            \
         k_cheb_clenshaw<LPR, I><<<grid, CT, pl.smem, s>>>(pl.cp);                                                  \
         return cudaGetLastError();                                                                                 \
+    }
+    if (pl.blocked) {
+#define CG_CL_BCASE(I)                                                                                               \
+    case I: {                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(k_cheb_clenshaw_b<LPR, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)pl.smem);                                                          \
+        if (e != cudaSuccess) return e;                                                                              \
+        k_cheb_clenshaw_b<LPR, I><<<grid, CT, pl.smem, s>>>(pl.cp);                                                  \
+        return cudaGetLastError();                                                                                   \
+    }
+        switch (pl.ipt) {
+            CG_CL_BCASE(1)
+            CG_CL_BCASE(2)
+        }
+#undef CG_CL_BCASE
+        return cudaErrorInvalidValue;
     }
     switch (pl.ipt) {
         CG_CL_CASE(2)
@@ -404,14 +681,16 @@ static cudaError_t launch_c(const CPlan &pl, dim3 grid, cudaStream_t s) {
 
 }  // namespace
 
+extern int g_fused_last_plan[8];
+
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K) {
-    return make_cplan(g, g->adj.width, N, Fin, Fout, K).ok;
+    return choose_cplan(g, N, Fin, Fout, K).ok;
 }
 
 // dx[n,m,fin] = sum_{k,fo} (T_k(L~^T) gy)[n,m,fo] W[fin*K+k, fo];  workspace: cg_fused_workspace(Fin, Fout, K) bytes
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,
                     void *workspace, cudaStream_t s) {
-    CPlan pl = make_cplan(g, g->adj.width, N, Fin, Fout, K);
+    CPlan pl = choose_cplan(g, N, Fin, Fout, K);
     CG_REQUIRE(pl.ok, "cg_run_clenshaw: shape not supported (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
     CG_REQUIRE(workspace != nullptr, "cg_run_clenshaw: workspace is NULL");
     unsigned char *wp = reinterpret_cast<unsigned char *>(workspace);
@@ -422,6 +701,11 @@ int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *d
     cp.col = g->adj.col;
     cp.val = g->adj.val;
     cp.order = g->adj.order;
+    cp.bt.ptr = g->adj.blk_ptr;
+    cp.bt.col = g->adj.blk_col;
+    cp.bt.w = g->adj.blk_w;
+    cp.bt.order = g->adj.blk_order;
+    cp.bt.nblk = g->adj.nblk;
     cp.gy = gy;
     cp.wp = wp;
     cp.dx = dx;
@@ -432,6 +716,10 @@ int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *d
     cp.K = K;
     const int64_t G = cg_ceil_div(N, pl.S);
     dim3 grid((unsigned)std::min<int64_t>(G, g->sm_count));
+    g_fused_last_plan[4] = pl.blocked ? 1 : 0;
+    g_fused_last_plan[5] = pl.S;
+    g_fused_last_plan[6] = pl.ipt;
+    g_fused_last_plan[7] = (int)pl.smem;
     CgProfScope prof("clenshaw_dx", s);
     cudaError_t e;
     switch (Fin / 4) {

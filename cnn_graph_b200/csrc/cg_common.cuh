@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/cnn_graph_b200.h"
 
 // ---------------------------------------------------------------------------
@@ -66,6 +68,17 @@ struct CgCsr {
     float2 *ell = nullptr;   // .x = value, .y = __int_as_float(col)
     int width = 0;           // max row length (ELL width)
     int m_pad = 0;           // rows padded to a multiple of 32
+    // Row-block form for the fused kernels (built with the ELL): block b = rows 4b .. 4b+3; its entries are the UNION of
+    // the four rows' columns, each with the four rows' weights (0 where a row has no such entry).  Neighbouring rows of
+    // a coarsened grid share most of their neighbours, so a thread that owns a block gathers every needed row of the
+    // signal once instead of once per referencing row.
+    int nblk = 0;            // ceil(M / 4)
+    int blk_total = 0;       // sum of union sizes
+    int *blk_ptr = nullptr;  // [nblk + 1]
+    int *blk_col = nullptr;  // [blk_total]
+    float4 *blk_w = nullptr; // [blk_total]  weights of rows 4b .. 4b+3 for that column
+    int *blk_order = nullptr;            // blocks by descending union size (stable)
+    std::vector<int> blk_len_sorted;     // host copy: union sizes in that order (kernel planning)
 };
 
 struct cg_graph {

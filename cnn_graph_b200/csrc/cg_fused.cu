@@ -27,7 +27,8 @@
 namespace {
 
 constexpr int FC = 512;        // compute threads
-constexpr int FT = FC + 32;    // + issue warp
+constexpr int NSTORE = 3;                  // plane store warps (one 128-row chunk of the image each)
+constexpr int FT = FC + 32 + 32 * NSTORE;  // + MMA issue warp + plane store warps = 20 warps: still 96 registers per thread
 
 struct FusedParams {
     const int *rowptr;
@@ -42,10 +43,139 @@ struct FusedParams {
                                  // [2][K][chunks of 128 rows][Fin/8][128 rows][8 features] over the rows n*M + m
                                  // (cg_dw_planes.cu reads them without conversion)
     long long planes_k, planes_pl;      // bytes per k (all chunks) / between the hi and mid halves
-    long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][8]
+    long long *trace;            // optional (debug): clock64 stamps of CTA 0, second group: [K][10]
     int N, M, Fin, Fout, K, S, nnz, tiles, tmem_cols, nslab, nw, estride;
     uint32_t off_ent, off_slab, slab_bytes, off_stage, plane_bytes, lbo_a, off_w, wplane_bytes, off_bar;
+    BlkTables bt;                // row-block form of the operator (k_cheb_fused_b); its tables live at off_ent
+    uint32_t off_wsz;
 };
+
+// ---- the two service warps of both fused kernels --------------------------------------------------------------------
+// A single warp runs its (uniform-datapath) issue code at one dependent instruction per ~5 cycles next to four busy
+// compute warps on its scheduler: the ~25 bulk stores of a step's planes alone took 1200 - 2200 cycles in the MMA issue
+// thread and delayed the MMAs behind them (ncu / clock64 trace, round 2).  So: warp FC/32 issues the loads of x and
+// W_k and the MMAs of a step, warp FC/32 + 1 ships the staged planes; the staging buffer is released when both are
+// done (sbar counts two arrivals when the plane side output is on).
+struct FusedCtl {
+    uint64_t *xbar, *wbar, *mbar, *sbar;
+    uint32_t slab0, w0, stage0, tmem, wbytes;
+};
+
+// MMA issue warp, one group: x / W loads, K steps of MMAs.  NK16 = Fin / 16 MMAs along the reduction per pass.
+template <int NK16>
+__device__ __forceinline__ void fused_issue_group(const FusedParams &p, const FusedCtl &c, int g, int gi, int G, int sP, int sR,
+                                                  uint32_t &wpar, uint32_t &mpar, int lane) {
+    const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
+    const int n0 = g * S;
+    const int Sg = min(S, p.N - n0);
+    const bool prefetch = p.nslab == 3;
+    if (lane == 0) {
+        // weights of steps 0 and 1 (all MMAs of the previous group have completed)
+        mbar_expect_tx(c.wbar, c.wbytes);
+        bulk_g2s(c.w0, p.wp, c.wbytes, c.wbar);
+        if (K > 1 && p.nw > 1) {
+            mbar_expect_tx(c.wbar + 1, c.wbytes);
+            bulk_g2s(c.w0 + c.wbytes, p.wp + c.wbytes, c.wbytes, c.wbar + 1);
+        }
+        const int gn = g + gridDim.x;
+        if (prefetch) {
+            if (gn < G) {       // next group's x into the spare slab
+                const int Sn = min(S, p.N - gn * S);
+                const uint32_t bytes = (uint32_t)Sn * M * Fin * 4u;
+                umma::fence_proxy_async();
+                mbar_expect_tx(c.xbar + ((gi + 1) & 1), bytes);
+                bulk_g2s(c.slab0 + (uint32_t)sR * p.slab_bytes, p.x + (size_t)gn * S * M * Fin, bytes, c.xbar + ((gi + 1) & 1));
+            }
+        } else if (gi > 0) {    // no spare slab: load this group's x now
+            const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
+            umma::fence_proxy_async();
+            mbar_expect_tx(c.xbar + (gi & 1), bytes);
+            bulk_g2s(c.slab0 + (uint32_t)sP * p.slab_bytes, p.x + (size_t)n0 * M * Fin, bytes, c.xbar + (gi & 1));
+        }
+    }
+    const uint32_t idesc = umma::make_idesc_bf16(128, Fout, 0, 0);
+    const uint32_t lbo_w = (uint32_t)Fout * 16u;
+    const uint32_t d_hi = umma::desc_hi(128u);      // SBO = 128 for both operands
+    // descriptors advance by plain adds on the low word (units of 16 bytes)
+    const uint32_t a_lo = umma::desc_lo(c.stage0, p.lbo_a);
+    const uint32_t a_mid = p.plane_bytes >> 4, b_mid = p.wplane_bytes >> 4;
+    const uint32_t a_k = (2u * p.lbo_a) >> 4, b_k = (2u * lbo_w) >> 4;
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();                                  // staging of step k is complete
+        if (lane == 0 && umma::elect_lane0()) {
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
+            if (tr) p.trace[k * 10 + 4] = clock64();
+            const int b = k & (p.nw - 1);
+            umma::mbar_wait(c.wbar + b, (wpar >> b) & 1u);
+            wpar ^= 1u << b;
+            umma::fence_after_sync();
+            if (tr) p.trace[k * 10 + 5] = clock64();
+            const uint32_t wb = c.w0 + (uint32_t)b * c.wbytes;
+            const uint32_t b_lo = umma::desc_lo(wb, lbo_w);
+            uint32_t at = a_lo, acc = c.tmem;
+            for (int t = 0; t < p.tiles; ++t, at += 128u, acc += (uint32_t)Fout) {      // 2048 bytes per 128-row tile
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                    for (int j = 0; j < NK16; ++j) {
+                        const uint32_t al = at + (pass == 1 ? a_mid : 0u) + (uint32_t)j * a_k;
+                        const uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u) + (uint32_t)j * b_k;
+                        umma::mma_bf16(acc, umma::desc_join(al, d_hi), umma::desc_join(bl, d_hi), idesc, (k | pass | j) != 0);
+                    }
+                }
+            }
+            umma::commit(c.mbar);
+            if (tr) p.trace[k * 10 + 6] = clock64();
+            // W_{k+nw} goes where W_k was, once the MMAs of step k have read it; waiting for every
+            // step also guarantees that nothing is in flight when the group ends
+            umma::mbar_wait(c.mbar, mpar);
+            mbar_arrive(c.sbar);                    // compute warps may overwrite the planes (once the store warp agrees)
+            if (tr) p.trace[k * 10 + 7] = clock64();
+            if (k + p.nw < K) {
+                mbar_expect_tx(c.wbar + b, c.wbytes);
+                bulk_g2s(wb, p.wp + (size_t)(k + p.nw) * c.wbytes, c.wbytes, c.wbar + b);
+            }
+        }
+        mpar ^= 1;
+        __syncwarp();
+    }
+}
+
+// plane store warp, one group: after every step's staging, ship the planes as they are.  The staged planes are, per
+// feature octet, one contiguous run over the group's rows in the MN-major core-matrix order the weight-gradient kernel
+// wants (global image: chunks of 128 rows, so that a chunk of one k is one contiguous block).
+__device__ __forceinline__ void fused_store_group(const FusedParams &p, const FusedCtl &c, int g, int gi, int lane, int sw) {
+    const int M = p.M, Fin = p.Fin, K = p.K, S = p.S;
+    const int n0 = g * S;
+    const int Rg = min(S, p.N - n0) * M;
+    const long long g0 = (long long)n0 * M, g1 = g0 + Rg;
+    const uint32_t cs = (uint32_t)(Fin / 8) * 2048u;
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();                                  // staging of step k is complete
+        if (p.planes_out != nullptr && lane == 0 && umma::elect_lane0()) {
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && sw == 0;
+            if (tr) p.trace[k * 10 + 8] = clock64();
+            unsigned char *kbase = p.planes_out + (size_t)k * p.planes_k;
+            for (long long ch = (g0 >> 7) + sw; ch <= (g1 - 1) >> 7; ch += NSTORE) {
+                const long long a = max(g0, ch << 7), b = min(g1, (ch + 1) << 7);
+                const uint32_t run = (uint32_t)(b - a) * 16u, so = (uint32_t)(a - g0) * 16u;
+                unsigned char *dst = kbase + (size_t)ch * cs + (size_t)(a & 127) * 16;
+                uint32_t src = c.stage0 + so;
+                for (int fo = 0; fo < Fin / 8; ++fo) {
+                    bulk_s2g(dst, src, run);
+                    bulk_s2g(dst + p.planes_pl, src + p.plane_bytes, run);
+                    dst += 2048;
+                    src += p.lbo_a;
+                }
+            }
+            bulk_commit();
+            bulk_wait_read();
+            mbar_arrive(c.sbar);
+            if (tr) p.trace[k * 10 + 9] = clock64();
+        }
+        __syncwarp();
+    }
+}
 
 // LPR lanes per row (Fin = 4 * LPR), IPT items (row, 4-column chunk) per compute thread
 template <int LPR, int IPT>
@@ -63,7 +193,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
     const int R = S * M;
-    const bool is_issuer = warp == FC / 32;
+    const bool is_issuer = warp >= FC / 32;      // MMA issue warp or plane store warp
 
     // ---- one-time setup ------------------------------------------------------------
     // operator as fixed-stride rows {weight, byte offset of the neighbour inside its sample's slab}; the tail of
@@ -84,7 +214,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
         for (int i = tid; i < n16; i += FT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
-        for (int i = 0; i < 6; ++i) umma::mbar_init(bars + i, 1);
+        for (int i = 0; i < 6; ++i) umma::mbar_init(bars + i, (i == 5 && p.planes_out != nullptr) ? 1 + NSTORE : 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -133,12 +263,13 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
     const uint32_t slab0 = umma::smem_u32(smem + p.off_slab);
     const uint32_t wbytes = 2 * p.wplane_bytes;
     const uint32_t w0 = umma::smem_u32(smem + p.off_w);
+    const FusedCtl ctl = {xbar, wbar, mbar, sbar, slab0, w0, umma::smem_u32(stage), tmem, wbytes};
     int sP = 0, sQ = 1, sR = 2;           // slab roles: X_0 of this group, second slab, prefetch target
     uint32_t mpar = 0;                    // parity of the next MMA-complete phase to wait for
     uint32_t wpar = 0;                    // issuer: parities of the two W barriers (bit b)
     int gi = 0;                           // groups processed by this CTA
 
-    if (is_issuer && lane == 0 && (int)blockIdx.x < G) {
+    if (warp == FC / 32 && lane == 0 && (int)blockIdx.x < G) {
         const int Sg = min(S, p.N - (int)blockIdx.x * S);
         const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
         mbar_expect_tx(xbar, bytes);
@@ -151,100 +282,10 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
         const int Rg = Sg * M;
         const int lim = Rg * Fin;         // items with i_soff >= lim belong to absent samples
 
-        if (is_issuer) {
-            // =========================== issue warp =====================================
-            if (lane == 0) {
-                // weights of steps 0 and 1 (all MMAs of the previous group have completed)
-                mbar_expect_tx(wbar, wbytes);
-                bulk_g2s(w0, p.wp, wbytes, wbar);
-                if (K > 1 && p.nw > 1) {
-                    mbar_expect_tx(wbar + 1, wbytes);
-                    bulk_g2s(w0 + wbytes, p.wp + wbytes, wbytes, wbar + 1);
-                }
-                const int gn = g + gridDim.x;
-                if (prefetch) {
-                    if (gn < G) {       // next group's x into the spare slab
-                        const int Sn = min(S, p.N - gn * S);
-                        const uint32_t bytes = (uint32_t)Sn * M * Fin * 4u;
-                        umma::fence_proxy_async();
-                        mbar_expect_tx(xbar + ((gi + 1) & 1), bytes);
-                        bulk_g2s(slab0 + (uint32_t)sR * p.slab_bytes, p.x + (size_t)gn * S * M * Fin, bytes,
-                                 xbar + ((gi + 1) & 1));
-                    }
-                } else if (gi > 0) {    // no spare slab: load this group's x now
-                    const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
-                    umma::fence_proxy_async();
-                    mbar_expect_tx(xbar + (gi & 1), bytes);
-                    bulk_g2s(slab0 + (uint32_t)sP * p.slab_bytes, p.x + (size_t)n0 * M * Fin, bytes, xbar + (gi & 1));
-                }
-            }
-            const uint32_t idesc = umma::make_idesc_bf16(128, Fout, 0, 0);
-            const uint32_t a0 = umma::smem_u32(stage);
-            const uint32_t lbo_w = (uint32_t)Fout * 16u;
-            const uint32_t d_hi = umma::desc_hi(128u);      // SBO = 128 for both operands
-            const int nk16 = Fin / 16;
-            for (int k = 0; k < K; ++k) {
-                __syncthreads();                                  // staging of step k is complete
-                if (lane == 0 && umma::elect_lane0()) {
-                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
-                    if (tr) p.trace[k * 8 + 4] = clock64();
-                    const int b = k & (p.nw - 1);
-                    umma::mbar_wait(wbar + b, (wpar >> b) & 1u);
-                    wpar ^= 1u << b;
-                    umma::fence_after_sync();
-                    if (tr) p.trace[k * 8 + 5] = clock64();
-                    if (p.planes_out != nullptr) {
-                        // the staged planes are, per feature octet, one contiguous run over the group's rows in the
-                        // MN-major core-matrix order the weight-gradient kernel wants: ship them as they are
-                        // (global image: chunks of 128 rows, so that a chunk of one k is one contiguous block)
-                        const long long g0 = (long long)n0 * M, g1 = g0 + Rg;
-                        const uint32_t cs = (uint32_t)(Fin / 8) * 2048u;
-                        for (long long c = g0 >> 7; c <= (g1 - 1) >> 7; ++c) {
-                            const long long a = max(g0, c << 7), b = min(g1, (c + 1) << 7);
-                            const uint32_t run = (uint32_t)(b - a) * 16u, so = (uint32_t)(a - g0) * 16u;
-                            unsigned char *dst = p.planes_out + (size_t)k * p.planes_k + (size_t)c * cs + (size_t)(a & 127) * 16;
-                            for (int fo = 0; fo < Fin / 8; ++fo) {
-                                bulk_s2g(dst + fo * 2048, a0 + (uint32_t)fo * p.lbo_a + so, run);
-                                bulk_s2g(dst + p.planes_pl + fo * 2048, a0 + p.plane_bytes + (uint32_t)fo * p.lbo_a + so, run);
-                            }
-                        }
-                        bulk_commit();
-                    }
-                    const uint32_t wb = w0 + (uint32_t)b * wbytes;
-                    // descriptors advance by plain adds on the low word (units of 16 bytes)
-                    const uint32_t a_lo = umma::desc_lo(a0, p.lbo_a), b_lo = umma::desc_lo(wb, lbo_w);
-                    const uint32_t a_mid = p.plane_bytes >> 4, b_mid = p.wplane_bytes >> 4;
-                    const uint32_t a_k = (2u * p.lbo_a) >> 4, b_k = (2u * lbo_w) >> 4;
-                    for (int t = 0; t < p.tiles; ++t) {
-                        const uint32_t at = a_lo + (uint32_t)t * 128u;          // 2048 bytes per 128-row tile
-                        const uint32_t acc = tmem + (uint32_t)(t * Fout);
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            uint32_t al = at + (pass == 1 ? a_mid : 0u), bl = b_lo + (pass == 2 ? b_mid : 0u);
-                            for (int j = 0; j < nk16; ++j) {
-                                umma::mma_bf16(acc, umma::desc_join(al, d_hi), umma::desc_join(bl, d_hi), idesc,
-                                               (k | pass | j) != 0);
-                                al += a_k;
-                                bl += b_k;
-                            }
-                        }
-                    }
-                    umma::commit(mbar);
-                    if (tr) p.trace[k * 8 + 6] = clock64();
-                    // W_{k+nw} goes where W_k was, once the MMAs of step k have read it; waiting for every
-                    // step also guarantees that nothing is in flight when the group ends
-                    umma::mbar_wait(mbar, mpar);
-                    if (p.planes_out != nullptr) bulk_wait_read();
-                    mbar_arrive(sbar);                      // compute warps may overwrite the planes
-                    if (tr) p.trace[k * 8 + 7] = clock64();
-                    if (k + p.nw < K) {
-                        mbar_expect_tx(wbar + b, wbytes);
-                        bulk_g2s(wb, p.wp + (size_t)(k + p.nw) * wbytes, wbytes, wbar + b);
-                    }
-                }
-                mpar ^= 1;
-                __syncwarp();
-            }
+        if (warp == FC / 32) {
+            fused_issue_group<LPR / 4>(p, ctl, g, gi, G, sP, sR, wpar, mpar, lane);
+        } else if (warp > FC / 32) {
+            fused_store_group(p, ctl, g, gi, lane, warp - FC / 32 - 1);
         } else {
             // =========================== compute warps ==================================
             umma::mbar_wait(xbar + (gi & 1), (uint32_t)((gi >> 1) & 1));
@@ -258,7 +299,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 if (a_soff[i] < limb) res[i] = lds128(aP + a_soff[i]);
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && tid == 0;
             for (int k = 0; k < K; ++k) {
-                if (tr) p.trace[k * 8 + 0] = clock64();
+                if (tr) p.trace[k * 10 + 0] = clock64();
                 if (k > 0) {
                     const uint32_t prev = (k & 1) ? aP : aQ;     // X_{k-1}
                     const uint32_t cur = (k & 1) ? aQ : aP;      // X_{k-2} -> X_k
@@ -300,11 +341,11 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                         if (a_soff[i1] < limb) sts128(cur + a_soff[i1], acc1);
                     }
                     // the staging planes are free once the MMAs (and bulk stores) of step k-1 have read them
-                    if (tr) p.trace[k * 8 + 1] = clock64();
+                    if (tr) p.trace[k * 10 + 1] = clock64();
                     umma::mbar_wait(sbar, mpar);
                     mpar ^= 1;
                 }
-                if (tr) p.trace[k * 8 + 2] = clock64();
+                if (tr) p.trace[k * 10 + 2] = clock64();
                 if (p.stack_out != nullptr) {       // side output for the backward pass (coalesced 128-bit stores)
                     char *dst = reinterpret_cast<char *>(p.stack_out + ((size_t)k * p.N + n0) * M * Fin);
 #pragma unroll
@@ -330,7 +371,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 }
                 umma::fence_proxy_async();
                 if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
-                if (tr) p.trace[k * 8 + 3] = clock64();
+                if (tr) p.trace[k * 10 + 3] = clock64();
                 __syncthreads();
             }
             // ---- epilogue: TMEM -> registers -> y
@@ -353,6 +394,200 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
             }
         }
         // rotate the slabs: the prefetched block becomes X_0
+        if (prefetch) {
+            const int t = sP;
+            sP = sR;
+            sR = sQ;
+            sQ = t;
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// The same kernel with the row-block gather of cg_fused_common.cuh: a compute thread owns IPB items of
+// (4 consecutive rows) x (4 features); everything else (slabs, staging planes, issue warp, epilogue) is unchanged.
+template <int LPR, int IPB>
+__global__ void __launch_bounds__(FT, 1) k_cheb_fused_b(const FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *stage = smem + p.off_stage;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *xbar = bars;            // [2] x slab of a group landed
+    uint64_t *wbar = bars + 2;        // [2] W_k landed
+    uint64_t *mbar = bars + 4;        // MMAs of the last issued step completed
+    uint64_t *sbar = bars + 5;        // staging planes free again
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
+    const bool is_issuer = warp >= FC / 32;      // MMA issue warp or plane store warp
+    const uint32_t rowb = (uint32_t)Fin * 4u;
+
+    // ---- one-time setup ------------------------------------------------------------
+    {   // pad rows of the A operand are never written by the steps: clear the staging planes once
+        uint4 *z = reinterpret_cast<uint4 *>(stage);
+        const int n16 = (int)(2 * p.plane_bytes / 16);
+        for (int i = tid; i < n16; i += FT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) umma::mbar_init(bars + i, (i == 5 && p.planes_out != nullptr) ? 1 + NSTORE : 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+
+    BlkItems<IPB> it;
+    blk_setup<LPR, IPB, FC>(p.bt, S, rowb, umma::smem_u32(smem + p.off_ent), reinterpret_cast<int *>(smem + p.off_wsz), it);
+    uint32_t a_g[IPB], a_soff[IPB], a_stoff[IPB];
+    int nrow[IPB];
+    {
+        const int l = tid % LPR;
+#pragma unroll
+        for (int i = 0; i < IPB; ++i) {
+            const int r0 = it.samp[i] * M + it.row0[i];
+            a_g[i] = 4u * (uint32_t)(it.samp[i] * M * Fin + 4 * l);
+            a_soff[i] = 4u * (uint32_t)(r0 * Fin + 4 * l);
+            // even lanes store the 16-byte hi octet (own 4 features + partner's), odd lanes the mid octet (see k_cheb_fused)
+            a_stoff[i] = (uint32_t)((l >> 1) * (int)p.lbo_a + r0 * 16) + ((l & 1) ? p.plane_bytes : 0u);
+            nrow[i] = it.samp[i] < S ? min(4, M - it.row0[i]) : 0;
+        }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (p.N + S - 1) / S;
+    const bool prefetch = p.nslab == 3;
+    const uint32_t slab0 = umma::smem_u32(smem + p.off_slab);
+    const uint32_t wbytes = 2 * p.wplane_bytes;
+    const uint32_t w0 = umma::smem_u32(smem + p.off_w);
+    const FusedCtl ctl = {xbar, wbar, mbar, sbar, slab0, w0, umma::smem_u32(stage), tmem, wbytes};
+    int sP = 0, sQ = 1, sR = 2;
+    uint32_t mpar = 0;
+    uint32_t wpar = 0;
+    int gi = 0;
+
+    if (warp == FC / 32 && lane == 0 && (int)blockIdx.x < G) {
+        const int Sg = min(S, p.N - (int)blockIdx.x * S);
+        const uint32_t bytes = (uint32_t)Sg * M * Fin * 4u;
+        mbar_expect_tx(xbar, bytes);
+        bulk_g2s(slab0, p.x + (size_t)blockIdx.x * S * M * Fin, bytes, xbar);
+    }
+
+    for (int g = blockIdx.x; g < G; g += gridDim.x, ++gi) {
+        const int n0 = g * S;
+        const int Sg = min(S, p.N - n0);
+        const int Rg = Sg * M;
+
+        if (warp == FC / 32) {
+            fused_issue_group<LPR / 4>(p, ctl, g, gi, G, sP, sR, wpar, mpar, lane);
+        } else if (warp > FC / 32) {
+            fused_store_group(p, ctl, g, gi, lane, warp - FC / 32 - 1);
+        } else {
+            // =========================== compute warps ==================================
+            umma::mbar_wait(xbar + (gi & 1), (uint32_t)((gi >> 1) & 1));
+            const uint32_t aP = slab0 + (uint32_t)sP * p.slab_bytes, aQ = slab0 + (uint32_t)sQ * p.slab_bytes;
+            const uint32_t st0 = umma::smem_u32(stage);
+            int nr[IPB];                      // rows of the item that exist in this group
+            // the thread's own X_{k-1} (X_k after the step) and X_{k-2}; with two items per thread X_{k-2} is read back
+            // from the slab position that X_k is about to overwrite instead (96-register cap at 544 threads)
+            constexpr bool OLD_REGS = IPB == 1;
+            float4 res[IPB][4], old[OLD_REGS ? IPB : 1][4];
+#pragma unroll
+            for (int i = 0; i < IPB; ++i) {
+                nr[i] = it.samp[i] < Sg ? nrow[i] : 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    res[i][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nr[i]) res[i][r] = lds128(aP + a_soff[i] + (uint32_t)r * rowb);
+                }
+            }
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && tid == 0;
+            for (int k = 0; k < K; ++k) {
+                if (tr) p.trace[k * 10 + 0] = clock64();
+                if (k > 0) {
+                    const uint32_t prev = (k & 1) ? aP : aQ;     // X_{k-1}
+                    const uint32_t cur = (k & 1) ? aQ : aP;      // X_{k-2} -> X_k
+#pragma unroll
+                    for (int i = 0; i < IPB; ++i) {
+                        float4 acc[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        blk_gather<LPR>(prev + a_g[i], it.tab[i], it.trips[i], acc);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (k > 1) {
+                                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if constexpr (OLD_REGS) {
+                                    o = old[i][r];
+                                } else {
+                                    if (r < nr[i]) o = lds128(cur + a_soff[i] + (uint32_t)r * rowb);
+                                }
+                                acc[r] = make_float4(fmaf(2.f, acc[r].x, -o.x), fmaf(2.f, acc[r].y, -o.y),
+                                                     fmaf(2.f, acc[r].z, -o.z), fmaf(2.f, acc[r].w, -o.w));
+                            }
+                            if constexpr (OLD_REGS) old[i][r] = res[i][r];
+                            res[i][r] = acc[r];
+                            if (r < nr[i]) sts128(cur + a_soff[i] + (uint32_t)r * rowb, acc[r]);
+                        }
+                    }
+                    if (tr) p.trace[k * 10 + 1] = clock64();
+                    umma::mbar_wait(sbar, mpar);
+                    mpar ^= 1;
+                }
+                if (tr) p.trace[k * 10 + 2] = clock64();
+                if (p.stack_out != nullptr) {       // side output for the backward pass (coalesced 128-bit stores)
+                    char *dst = reinterpret_cast<char *>(p.stack_out + ((size_t)k * p.N + n0) * M * Fin);
+#pragma unroll
+                    for (int i = 0; i < IPB; ++i)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (r < nr[i]) *reinterpret_cast<float4 *>(dst + a_soff[i] + (uint32_t)r * rowb) = res[i][r];
+                }
+#pragma unroll
+                for (int i = 0; i < IPB; ++i)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        uint2 hi, mid;
+                        split4(res[i][r], hi, mid);
+                        const bool odd = tid & 1;
+                        const uint2 send = odd ? hi : mid;
+                        uint2 recv;
+                        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                        const uint4 v = odd ? make_uint4(recv.x, recv.y, mid.x, mid.y) : make_uint4(hi.x, hi.y, recv.x, recv.y);
+                        if (r < nr[i])
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st0 + a_stoff[i] + 16u * (uint32_t)r),
+                                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                                         : "memory");
+                    }
+                umma::fence_proxy_async();
+                if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
+                if (tr) p.trace[k * 10 + 3] = clock64();
+                __syncthreads();
+            }
+            // ---- epilogue: TMEM -> registers -> y
+            umma::mbar_wait(sbar, mpar);
+            mpar ^= 1;
+            umma::fence_after_sync();
+            const int q = warp & 3, wq = warp >> 2;
+            const int nc8 = Fout / 8;
+            for (int idx = wq; idx < p.tiles * nc8; idx += 4) {
+                const int t = idx / nc8, c = idx - t * nc8;
+                const int r = t * 128 + 32 * q + lane;
+                float v[8];
+                umma::tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * Fout + c * 8), v);
+                umma::tmem_ld_wait();
+                if (r < Rg) {
+                    float *dst = p.y + ((size_t)n0 * M + r) * Fout + c * 8;
+                    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
         if (prefetch) {
             const int t = sP;
             sP = sR;
@@ -391,17 +626,21 @@ k_pack_w(const float *__restrict__ W, unsigned char *__restrict__ wp, int Q, int
 struct Plan {
     bool ok = false;
     int S = 0, tiles = 0, ipt = 0, nslab = 0, tmem_cols = 0;
+    bool blocked = false;
+    double cost = 0.0;
     FusedParams fp;
     size_t smem = 0;
 };
 
-static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin, int Fout, int K) {
+// blocked: the row-block gather kernel (k_cheb_fused_b); otherwise one row per item (k_cheb_fused)
+static Plan make_plan(const cg_graph *g, const CgCsr &side, int64_t nnz, int N, int Fin, int Fout, int K, bool blocked) {
     Plan best;
     if (Fin % 16 != 0 || Fin > 128 || (Fin & (Fin - 1)) != 0) return best;     // LPR in {4, 8, 16, 32}
     if (Fout % 16 != 0 || Fout < 16 || Fout > 256) return best;
     if (N <= 0 || K < 1) return best;
-    const int M = g->M, LPR = Fin / 4;
-    const double avg = M > 0 ? (double)nnz / M : 0.0;
+    if (blocked && side.nblk == 0) return best;
+    const int M = g->M, LPR = Fin / 4, width = side.width;
+    const double avg = M > 0 ? (double)(blocked ? 4 * (int64_t)side.blk_total : nnz) / M : 0.0;   // gathers per 4 rows x 1/4
     double best_cost = 0.0;
     int s_lo = 1, s_hi = 64;
     if (const char *env = getenv("CG_FUSED_S")) {       // tuning / debugging aid: pin the samples per group
@@ -412,10 +651,16 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
         const int64_t R = (int64_t)S * M;
         const int tiles = (int)cg_ceil_div(R, 128);
         if ((int64_t)tiles * Fout > 512) break;
-        const int64_t items = R * LPR;
-        const int need = (int)cg_ceil_div(items, FC);
-        if (need > 8) break;        // res[] + item constants must stay in registers
-        const int ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+        int need, ipt;
+        if (blocked) {
+            need = (int)cg_ceil_div((int64_t)S * side.nblk * LPR, FC);
+            if (need > 2) break;        // res[] / old[] of 4 rows per item must stay in registers
+            ipt = need;
+        } else {
+            need = (int)cg_ceil_div(R * LPR, FC);
+            if (need > 8) break;        // res[] + item constants must stay in registers
+            ipt = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+        }
         const uint32_t Rp = (uint32_t)tiles * 128u;
         // strides chosen for conflict-free staging stores (see a_stoff): LBO = 32, plane = 16 (mod 128)
         const uint32_t lbo_a = Rp * 16u + 32u;
@@ -423,6 +668,7 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
         const uint32_t wplane = (uint32_t)Fin * Fout * 2u;
         const uint32_t slab = (uint32_t)cg_align_up((size_t)R * Fin * 4, 128);
         const int estride = std::max(2, (width + 1) & ~1);      // even: 16-byte aligned entry pairs
+        const size_t ent_bytes = blocked ? cg_blk_table_bytes(side.blk_len_sorted, S, LPR, ipt, FC) : (size_t)M * estride * 8;
         for (int cfg = 0; cfg < 3; ++cfg) {
             const int nslab = cfg == 0 ? 3 : 2, nw = cfg == 2 ? 1 : 2;
             FusedParams fp;
@@ -430,8 +676,10 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
             uint32_t off = 0;
             fp.off_bar = off;
             off += 128;
+            fp.off_wsz = off;
+            off += 256;                  // blk_setup scratch: (FC / 32) * IPB ints
             fp.off_ent = off;
-            off += (uint32_t)cg_align_up((size_t)M * estride * 8, 128);
+            off += (uint32_t)cg_align_up(ent_bytes, 128);
             fp.off_slab = off;
             off += (uint32_t)nslab * slab;
             fp.off_stage = off;
@@ -441,12 +689,14 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
             if (off > g->smem_optin) continue;
             const int64_t G = cg_ceil_div(N, S);
             const int64_t rounds = cg_ceil_div(G, g->sm_count);
-            const double step = (double)need * (avg * 7.0 + 40.0) * (need > 4 ? 1.6 : 1.0) + 300.0;   // > 4: register spills
+            const double step = blocked ? (double)need * (avg * 5.5 + 120.0) + 300.0
+                                        : (double)need * (avg * 7.0 + 40.0) * (need > 4 ? 1.6 : 1.0) + 300.0;   // > 4: register spills
             const double cost = (double)rounds * ((double)K * step + 600.0 + (double)R * Fout / 64.0) -
                                 (nslab == 3 ? 1.0 : 0.0) - (nw == 2 ? 0.5 : 0.0);
             if (!best.ok || cost < best_cost) {
                 best.ok = true;
                 best_cost = cost;
+                best.cost = cost;
                 best.S = S;
                 best.tiles = tiles;
                 best.ipt = ipt;
@@ -466,11 +716,28 @@ static Plan make_plan(const cg_graph *g, int width, int64_t nnz, int N, int Fin,
                 fp.wplane_bytes = wplane;
                 best.fp = fp;
                 best.smem = off;
+                best.blocked = blocked;
             }
             break;      // 3 slabs fit: no need to look at 2
         }
     }
     return best;
+}
+
+// The row-block gather pays when neighbouring rows share neighbours (union well below the entry count); on operators
+// without that locality it would only add multiplications by zero.  CG_FUSED_BLOCK=0/1 overrides (tests run both).
+static bool want_blocked(const CgCsr &side, int64_t nnz) {
+    if (const char *env = getenv("CG_FUSED_BLOCK")) return atoi(env) != 0;
+    return side.nblk > 0 && (int64_t)side.blk_total * 10 <= nnz * 8;
+}
+
+static Plan choose_plan(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K) {
+    const CgCsr &side = cg_side(g, transpose);
+    if (want_blocked(side, g->nnz)) {
+        Plan pb = make_plan(g, side, g->nnz, N, Fin, Fout, K, true);
+        if (pb.ok) return pb;
+    }
+    return make_plan(g, side, g->nnz, N, Fin, Fout, K, false);
 }
 
 template <int LPR>
@@ -482,6 +749,22 @@ static cudaError_t launch_lpr(const Plan &pl, dim3 grid, cudaStream_t s) {
         if (e != cudaSuccess) return e;                                                                          \
         k_cheb_fused<LPR, I><<<grid, FT, pl.smem, s>>>(pl.fp);                                                   \
         return cudaGetLastError();                                                                               \
+    }
+    if (pl.blocked) {
+#define CG_FUSED_BCASE(I)                                                                                          \
+    case I: {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(k_cheb_fused_b<LPR, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)pl.smem);                                                        \
+        if (e != cudaSuccess) return e;                                                                            \
+        k_cheb_fused_b<LPR, I><<<grid, FT, pl.smem, s>>>(pl.fp);                                                   \
+        return cudaGetLastError();                                                                                 \
+    }
+        switch (pl.ipt) {
+            CG_FUSED_BCASE(1)
+            CG_FUSED_BCASE(2)
+        }
+#undef CG_FUSED_BCASE
+        return cudaErrorInvalidValue;
     }
     switch (pl.ipt) {
         CG_FUSED_CASE(2)
@@ -495,6 +778,13 @@ static cudaError_t launch_lpr(const Plan &pl, dim3 grid, cudaStream_t s) {
 }  // namespace
 
 static long long *g_fused_trace = nullptr;
+int g_fused_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // [0..3] forward kernel, [4..7] Clenshaw kernel: blocked, S, items, smem
+// debug aid: the plan of the most recent fused forward / Clenshaw launch of this process
+extern "C" int cg_debug_fused_plan_info(int *info8) {
+    if (!info8) return CG_ERR_ARG;
+    for (int i = 0; i < 8; ++i) info8[i] = g_fused_last_plan[i];
+    return CG_OK;
+}
 // debug aid (not in the public header): clock64 stamps of CTA 0's second group, [K][8] int64 on the device
 extern "C" int cg_debug_fused_trace(long long *dev_buf) {
     g_fused_trace = dev_buf;
@@ -510,14 +800,14 @@ int cg_pack_w(const float *W, unsigned char *wp, int Q, int Nn, int K, bool tran
 }
 
 bool cg_fused_supported(const cg_graph *g, int transpose, int N, int Fin, int Fout, int K) {
-    return make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K).ok;
+    return choose_plan(g, transpose, N, Fin, Fout, K).ok;
 }
 
 size_t cg_fused_workspace(int Fin, int Fout, int K) { return cg_align_up((size_t)K * Fin * Fout * 4, 256); }
 
 int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *W, float *y, float *stack_out, int N,
                  int Fin, int Fout, int K, bool w_transposed, void *workspace, cudaStream_t s, bool stack_planes) {
-    Plan pl = make_plan(g, cg_side(g, transpose).width, g->nnz, N, Fin, Fout, K);
+    Plan pl = choose_plan(g, transpose, N, Fin, Fout, K);
     CG_REQUIRE(pl.ok, "cg_run_fused: shape not supported by the fused kernel (M=%d Fin=%d Fout=%d)", g->M, Fin, Fout);
     CG_REQUIRE(workspace != nullptr, "cg_run_fused: workspace is NULL");
     const CgCsr &L = cg_side(g, transpose);
@@ -529,6 +819,11 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.col = L.col;
     fp.val = L.val;
     fp.order = L.order;
+    fp.bt.ptr = L.blk_ptr;
+    fp.bt.col = L.blk_col;
+    fp.bt.w = L.blk_w;
+    fp.bt.order = L.blk_order;
+    fp.bt.nblk = L.nblk;
     fp.x = x;
     fp.wp = wp;
     fp.y = y;
@@ -546,6 +841,10 @@ int cg_run_fused(const cg_graph *g, int transpose, const float *x, const float *
     fp.trace = g_fused_trace;
     const int64_t G = cg_ceil_div(N, pl.S);
     dim3 grid((unsigned)std::min<int64_t>(G, g->sm_count));
+    g_fused_last_plan[0] = pl.blocked ? 1 : 0;
+    g_fused_last_plan[1] = pl.S;
+    g_fused_last_plan[2] = pl.ipt;
+    g_fused_last_plan[3] = (int)pl.smem;
     CgProfScope prof(transpose ? "fused_dx" : "fused_fwd", s);
     cudaError_t e;
     switch (Fin / 4) {

@@ -62,6 +62,51 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
         CG_CHECK_CUDA(cudaMalloc(&dst.ell, sizeof(float2) * ell.size()));
         CG_CHECK_CUDA(cudaMemcpy(dst.ell, ell.data(), sizeof(float2) * ell.size(), cudaMemcpyHostToDevice));
     }
+    if (want_ell) {
+        // row-block (4 rows) union form, see CgCsr
+        const int nblk = (M + 3) / 4;
+        std::vector<int> bptr(nblk + 1, 0), bcol;
+        std::vector<float4> bw;
+        for (int b = 0; b < nblk; ++b) {
+            int cur[4], end[4];
+            for (int i = 0; i < 4; ++i) {
+                const int m = 4 * b + i;
+                cur[i] = m < M ? rowptr[m] : 0;
+                end[i] = m < M ? rowptr[m + 1] : 0;
+            }
+            for (;;) {      // 4-way merge of the sorted rows
+                int c = INT32_MAX;
+                for (int i = 0; i < 4; ++i)
+                    if (cur[i] < end[i]) c = std::min(c, col[cur[i]]);
+                if (c == INT32_MAX) break;
+                float w[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < 4; ++i)
+                    if (cur[i] < end[i] && col[cur[i]] == c) w[i] = val[cur[i]++];
+                bcol.push_back(c);
+                bw.push_back(make_float4(w[0], w[1], w[2], w[3]));
+            }
+            bptr[b + 1] = (int)bcol.size();
+        }
+        std::vector<int> border(nblk);
+        for (int b = 0; b < nblk; ++b) border[b] = b;
+        std::stable_sort(border.begin(), border.end(),
+                         [&](int a, int b) { return bptr[a + 1] - bptr[a] > bptr[b + 1] - bptr[b]; });
+        dst.nblk = nblk;
+        dst.blk_total = (int)bcol.size();
+        dst.blk_len_sorted.resize(nblk);
+        for (int i = 0; i < nblk; ++i) dst.blk_len_sorted[i] = bptr[border[i] + 1] - bptr[border[i]];
+        const size_t nt = std::max<size_t>(bcol.size(), 1);
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_order, sizeof(int) * (size_t)nblk));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_col, sizeof(int) * nt));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_w, sizeof(float4) * nt));
+        CG_CHECK_CUDA(cudaMemcpy(dst.blk_ptr, bptr.data(), sizeof(int) * (size_t)(nblk + 1), cudaMemcpyHostToDevice));
+        CG_CHECK_CUDA(cudaMemcpy(dst.blk_order, border.data(), sizeof(int) * (size_t)nblk, cudaMemcpyHostToDevice));
+        if (!bcol.empty()) {
+            CG_CHECK_CUDA(cudaMemcpy(dst.blk_col, bcol.data(), sizeof(int) * bcol.size(), cudaMemcpyHostToDevice));
+            CG_CHECK_CUDA(cudaMemcpy(dst.blk_w, bw.data(), sizeof(float4) * bw.size(), cudaMemcpyHostToDevice));
+        }
+    }
     return CG_OK;
 }
 
@@ -71,6 +116,10 @@ static void free_side(CgCsr &s) {
     cudaFree(s.val);
     cudaFree(s.order);
     cudaFree(s.ell);
+    cudaFree(s.blk_ptr);
+    cudaFree(s.blk_col);
+    cudaFree(s.blk_w);
+    cudaFree(s.blk_order);
     s = CgCsr();
 }
 

@@ -258,6 +258,13 @@ int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, i
 /* A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A operand): dev_A [128][Kd], dev_B [N][Kd]. */
 int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, void *stream);
 
+/* Debug aids of the fused recurrence kernels.  cg_debug_fused_trace: device buffer [K][10] of int64 that receives
+ * clock64 stamps of CTA 0's second group (NULL switches it off).  cg_debug_fused_plan_info: the plan of the most
+ * recent fused forward ([0..3]) and Clenshaw ([4..7]) launch: {row-block gather used, samples per group, items per
+ * thread, dynamic shared-memory bytes}.                                                                        */
+int cg_debug_fused_trace(long long *dev_buf);
+int cg_debug_fused_plan_info(int *info8);
+
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32
  * arithmetic in the reference's order, including the reference's row-table

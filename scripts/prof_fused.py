@@ -57,17 +57,21 @@ if os.environ.get('CG_TRACE'):
     import ctypes
     from cnn_graph_b200 import _native
     lib = _native.lib()
-    buf = torch.zeros(a.K * 8, dtype=torch.int64, device='cuda')
+    buf = torch.zeros(a.K * 10, dtype=torch.int64, device='cuda')
     lib._handle if False else None
     fn = ctypes.CDLL(_native.LIB_PATH).cg_debug_fused_trace
     fn.argtypes = [ctypes.c_void_p]
     fn(buf.data_ptr())
-    y = ops.cheb_filter(x, W, L, a.K, flags=a.flags)
+    if os.environ.get('CG_TRACE_NOGRAD'):      # inference form: no saved basis (no plane side output)
+        with torch.no_grad():
+            y = ops.cheb_filter(x, W, L, a.K, flags=a.flags)
+    else:
+        y = ops.cheb_filter(x, W, L, a.K, flags=a.flags)
     torch.cuda.synchronize()
     fn(None)
-    t = buf.cpu().numpy().reshape(a.K, 8)
+    t = buf.cpu().numpy().reshape(a.K, 10)
     t0 = t[0, 0]
-    names = ['A_start', 'A_end', 'wait_end', 'B_end', 'I_sync', 'I_wbar', 'I_issued', 'I_done']
+    names = ['A_start', 'A_end', 'wait_end', 'B_end', 'I_sync', 'I_wbar', 'I_issued', 'I_done', 'S_start', 'S_done']
     print(' k ' + ' '.join('%9s' % n for n in names))
     for k in range(a.K):
         print('%2d ' % k + ' '.join('%9d' % (v - t0 if v else -1) for v in t[k]))

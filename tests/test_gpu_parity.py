@@ -43,6 +43,17 @@ def tf_ref():
     return t
 
 
+@pytest.fixture(params=['rows', 'blocks'])
+def gather(request):
+    """Both gather forms of the fused recurrence kernels: one row per item (k_cheb_fused / k_cheb_clenshaw) and the
+    4-row union blocks (k_cheb_fused_b / k_cheb_clenshaw_b); the library picks by the operator's locality unless
+    CG_FUSED_BLOCK says otherwise."""
+    import os
+    os.environ['CG_FUSED_BLOCK'] = '1' if request.param == 'blocks' else '0'
+    yield request.param
+    os.environ.pop('CG_FUSED_BLOCK', None)
+
+
 FLAG_SETS = [0, 1, 4]   # default (fused / on-chip when it fits), forced streaming, on-chip without the fused kernel
 
 
@@ -119,7 +130,7 @@ FUSED_SHAPES = [
 
 
 @pytest.mark.parametrize('level,N,Fin,Fout,K', FUSED_SHAPES)
-def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K):
+def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, gather, level, N, Fin, Fout, K):
     L = csr_from(c2, 'L%d' % level)
     M = L.shape[0]
     rng = np.random.RandomState(10 * level + K + N)
@@ -135,7 +146,7 @@ def test_fused_filter_forward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K)
 @pytest.mark.parametrize('level,N,Fin,Fout,K', [(2, 5, 32, 64, 25), (4, 37, 64, 16, 4), (3, 10, 32, 64, 3),
                                                 (3, 9, 16, 16, 1), (3, 5, 64, 64, 25), (4, 130, 16, 32, 3), (2, 301, 32, 64, 5), (4, 700, 16, 16, 4)])
 @pytest.mark.parametrize('dx_kernel', ['clenshaw', 'forward_form'])
-def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K, dx_kernel):
+def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, gather, level, N, Fin, Fout, K, dx_kernel):
     """dx through the adjoint (Clenshaw) kernel or the forward-form fused kernel on L~^T; dW from the basis."""
     L = csr_from(c2, 'L%d' % level)
     M = L.shape[0]
@@ -152,7 +163,7 @@ def test_fused_filter_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K
     close(Wt.grad, dW)
 
 
-def test_fused_filter_directed(ops, tf_ref, directed):
+def test_fused_filter_directed(ops, tf_ref, directed, gather):
     """Non-symmetric operator: the fused dx must use the true transpose."""
     L = csr_from(directed, 'L')
     M = L.shape[0]
@@ -517,7 +528,7 @@ def test_graphconv_and_glstm_models_run(ops, tf_ref, c2):
     assert np.isfinite(float(gm.train_step(dev(x), dev(y))))
 
 
-def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2):
+def test_saved_stack_backward_matches_recompute(ops, tf_ref, c2, gather):
     """The forward pass leaves the basis behind (sample-major) and the backward pass uses it for dW:
     same gradients as the recomputing path and as the oracle."""
     L = csr_from(c2, 'L2')
@@ -916,3 +927,51 @@ def test_second_backward_through_retained_graph(ops, tf_ref, c2):
         h2 = torch.autograd.grad(yp, (W0, b0), g)
         for a, b in zip(h1, h2):
             assert torch.equal(a, b)
+
+
+def _plan_info():
+    import ctypes
+    from cnn_graph_b200 import _native
+    buf = (ctypes.c_int * 8)()
+    _native.check(_native.lib().cg_debug_fused_plan_info(buf), 'cg_debug_fused_plan_info')
+    return list(buf)
+
+
+# (fixture, operator, N, Fin, Fout, K): one and two block items per thread, every lanes-per-row variant, ragged last
+# groups, a vertex count that is not a multiple of 4 (directed57), an operator without locality (c1)
+BLOCK_SHAPES = [('c2', 'L2', 7, 32, 64, 25), ('c2', 'L2', 5, 16, 32, 6), ('c2', 'L2', 3, 64, 64, 5), ('c2', 'L3', 2, 128, 32, 3),
+                ('c2', 'L3', 11, 32, 64, 7), ('c2', 'L3', 9, 16, 16, 4), ('c2', 'L4', 50, 32, 32, 5), ('c2', 'L4', 33, 64, 16, 3),
+                ('directed', 'L', 13, 16, 32, 6), ('directed', 'L', 5, 32, 16, 4), ('c1', 'L2', 100, 32, 64, 20), ('c1', 'L1', 37, 16, 32, 5)]
+
+
+@pytest.mark.parametrize('fix,name,N,Fin,Fout,K', BLOCK_SHAPES)
+def test_row_block_gather_kernels_vs_oracle(ops, tf_ref, request, fix, name, N, Fin, Fout, K):
+    """k_cheb_fused_b / k_cheb_clenshaw_b (4-row union blocks) forced on: y, dx, dW and the saved basis path against the
+    oracle, and bit-equal y / dx between the two gather forms is NOT expected (different summation order) -- both sit
+    inside the fp32 tolerance."""
+    import os
+    npz = request.getfixturevalue(fix)
+    L = csr_from(npz, name)
+    M = L.shape[0]
+    lmax = 3.5 if fix == 'directed' else 2
+    rng = np.random.RandomState(N + Fin + K)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    os.environ['CG_FUSED_BLOCK'] = '1'
+    try:
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, K, lmax=lmax, flags=ops.FILTER_FORCE_FUSED)
+        info_f = _plan_info()
+        y.backward(dev(gy))
+        info_b = _plan_info()
+    finally:
+        os.environ.pop('CG_FUSED_BLOCK', None)
+    # wide layers whose tables + slabs exceed shared memory fall back to the row-per-item kernels (M = 248 with Fin >= 64)
+    if Fin <= 32 or M <= 128:
+        assert info_f[0] == 1, 'forward did not take the row-block kernel: %r' % info_f
+        assert info_b[4] == 1, 'dx did not take the row-block Clenshaw kernel: %r' % info_b
+    close(y, tf_ref.chebyshev5(x, L, W, K, lmax=lmax))
+    dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy, lmax=lmax)
+    close(xt.grad, dx)
+    close(Wt.grad, dW)
