@@ -82,6 +82,7 @@ _SIGNATURES = {
     'cg_debug_umma_gemm_m': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'cg_debug_umma_gemm_ts': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'cg_debug_fused_trace': (c_int, [c_void_p]),
+    'cg_debug_clenshaw_trace': (c_int, [c_void_p]),
     'cg_debug_fused_plan_info': (c_int, [c_void_p]),
     'cg_host_metis_one_level': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                         c_void_p, ctypes.POINTER(c_i64)]),

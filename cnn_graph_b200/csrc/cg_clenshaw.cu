@@ -20,6 +20,20 @@
 #include "cg_umma.cuh"
 #include "cg_fused_common.cuh"
 
+// clock64 stamps for scripts/prof_fused.py: compiled in only with -DCG_TRACE_BUILD (CG_TRACE_BUILD=1 python -m
+// cnn_graph_b200.build --force); even a predicated-off stamp costs issue slots in the hot loops
+#ifdef CG_TRACE_BUILD
+#define CG_STAMP(cond, idx)                    \
+    do {                                       \
+        if (cond) p.trace[idx] = clock64();    \
+    } while (0)
+#else
+#define CG_STAMP(cond, idx) \
+    do {                    \
+        (void)(cond);       \
+    } while (0)
+#endif
+
 namespace {
 
 constexpr int CC = 512;        // compute threads
@@ -38,6 +52,7 @@ struct ClenshawParams {
     uint32_t off_ent, off_slab, slab_bytes, off_gbuf, off_w, wplane_bytes, off_bar;
     BlkTables bt;                // row-block form of L~^T (k_cheb_clenshaw_b); its tables live at off_ent
     uint32_t off_wsz;
+    long long *trace;            // optional (debug): clock64 stamps of CTA 0's second group, [K][10] (k_cheb_clenshaw_b)
 };
 
 // LPR lanes per row (Fi = 4 * LPR), IPT items (row, 4-column chunk) per compute thread
@@ -325,10 +340,11 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + MAX_NS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.M, Fi = p.Fi, Fo = p.Fo, K = p.K, S = p.S, NS = p.ns;
+    constexpr int Fi = 4 * LPR;                  // compile-time row width
+    const int M = p.M, Fo = p.Fo, K = p.K, S = p.S, NS = p.ns;
     const bool is_issuer = warp == CC / 32;
     constexpr uint32_t SWZ = LPR >= 8 ? 7u : (uint32_t)(LPR - 1);     // chunk swizzle mask of the G buffer
-    const uint32_t rowb = (uint32_t)Fi * 4u;
+    constexpr uint32_t rowb = (uint32_t)Fi * 4u;
 
     if (tid == 0) {
         for (int i = 0; i < 2 + MAX_NS; ++i) umma::mbar_init(bars + i, 1);
@@ -338,15 +354,18 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
 
     BlkItems<IPB> it;
     blk_setup<LPR, IPB, CC>(p.bt, S, rowb, umma::smem_u32(smem + p.off_ent), reinterpret_cast<int *>(smem + p.off_wsz), it);
-    uint32_t a_g[IPB], a_soff[IPB];
-    int r0[IPB], nrow[IPB];
+    uint32_t a_g[IPB], a_soff[IPB], a_goff[IPB][4];
+    int nrow[IPB];
     const uint32_t lc = (uint32_t)(tid % LPR);
 #pragma unroll
     for (int i = 0; i < IPB; ++i) {
-        r0[i] = it.samp[i] * M + it.row0[i];
+        const int r0 = it.samp[i] * M + it.row0[i];
         a_g[i] = 4u * (uint32_t)(it.samp[i] * M * Fi) + 16u * lc;
-        a_soff[i] = 4u * (uint32_t)(r0[i] * Fi) + 16u * lc;
+        a_soff[i] = 4u * (uint32_t)(r0 * Fi) + 16u * lc;
         nrow[i] = it.samp[i] < S ? min(4, M - it.row0[i]) : 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)      // position of the thread's chunk of row r0 + r in the swizzled G buffer
+            a_goff[i][r] = 4u * (uint32_t)((r0 + r) * Fi) + 16u * (lc ^ ((uint32_t)(r0 + r) & SWZ));
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -363,8 +382,10 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
     uint32_t gpar = 0;
     uint32_t wpar = 0;
 
-    for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    int gi = 0;
+    for (int g = blockIdx.x; g < G; g += gridDim.x, ++gi) {
         const int n0 = g * S;
+        const bool trg = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
         const int Sg = min(S, p.N - n0);
         const int Rg = Sg * M;
 
@@ -384,6 +405,7 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
             const int nk16 = Fo / 16;
             auto issue = [&](int k) {
                 const int slot = (K - 1 - k) % NS, bw = (K - 1 - k) & 1;
+                CG_STAMP(trg, (K - 1 - k) * 10 + 5);
                 umma::mbar_wait(wbar + bw, (wpar >> bw) & 1u);
                 wpar ^= 1u << bw;
                 umma::fence_after_sync();
@@ -403,6 +425,7 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                     }
                 }
                 umma::commit(gfull + slot);
+                CG_STAMP(trg, (K - 1 - k) * 10 + 6);
                 if (k + 1 < K) {
                     const int sp = (K - 2 - k) % NS;
                     umma::mbar_wait(gfull + sp, (gpar >> sp) & 1u);
@@ -417,6 +440,7 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                     umma::mbar_wait(gfull + slot, (gpar >> slot) & 1u);
                     gpar ^= 1u << slot;
                 }
+                CG_STAMP(trg, (K - 1 - k) * 10 + 7);
             };
             __syncthreads();                         // sync A: gy of this group is in tensor memory
             if (lane == 0 && umma::elect_lane0())
@@ -466,17 +490,25 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                 gpar ^= 1u << slot;
                 umma::fence_after_sync();
                 const uint32_t gb = gbuf0 + (uint32_t)(k & 1) * p.slab_bytes;
-                const int nc8 = Fi / 8;
-                for (int t = 0; t < p.tiles; ++t) {
-                    const int r = t * 128 + 32 * q + lane;
+                constexpr int nc8 = Fi / 8;
+                for (int t = 0; t < p.tiles; t += 2) {      // two row tiles per wait: the TMEM loads overlap
+                    const bool two = t + 1 < p.tiles;
                     for (int c = sub; c < nc8; c += 4) {
-                        float v[8];
-                        umma::tmem_ld8(tmem + lane_base + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi + c * 8), v);
+                        float v0[8], v1[8];
+                        const uint32_t ta = tmem + lane_base + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi + c * 8);
+                        umma::tmem_ld8(ta, v0);
+                        if (two) umma::tmem_ld8(ta + (uint32_t)Fi, v1);
                         umma::tmem_ld_wait();
-                        if (r < Rg) {
-                            const uint32_t row = gb + 4u * (uint32_t)(r * Fi);
-                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)r & SWZ)), make_float4(v[0], v[1], v[2], v[3]));
-                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)r & SWZ)), make_float4(v[4], v[5], v[6], v[7]));
+                        const int ra = t * 128 + 32 * q + lane, rb = ra + 128;
+                        if (ra < Rg) {
+                            const uint32_t row = gb + 4u * (uint32_t)(ra * Fi);
+                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)ra & SWZ)), make_float4(v0[0], v0[1], v0[2], v0[3]));
+                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)ra & SWZ)), make_float4(v0[4], v0[5], v0[6], v0[7]));
+                        }
+                        if (two && rb < Rg) {
+                            const uint32_t row = gb + 4u * (uint32_t)(rb * Fi);
+                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)rb & SWZ)), make_float4(v1[0], v1[1], v1[2], v1[3]));
+                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)rb & SWZ)), make_float4(v1[4], v1[5], v1[6], v1[7]));
                         }
                     }
                 }
@@ -499,8 +531,10 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
 #pragma unroll
                 for (int r = 0; r < 4; ++r) old[0][r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const bool trc = trg && tid == 0;
             for (int s = 0; s < K; ++s) {
                 const int k = K - 1 - s;
+                CG_STAMP(trc, s * 10 + 0);
                 const uint32_t prev = slab0 + (uint32_t)((s + 1) & 1) * p.slab_bytes;     // b_{k+1}
                 const uint32_t cur = slab0 + (uint32_t)(s & 1) * p.slab_bytes;            // receives b_k (holds b_{k+2})
                 const uint32_t gb = gbuf0 + (uint32_t)(k & 1) * p.slab_bytes;
@@ -512,12 +546,12 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s > 0) blk_gather<LPR>(prev + a_g[i], it.tab[i], it.trips[i], acc);
+                    CG_STAMP(trc && i == 0, s * 10 + 1);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const bool v = r < nr[i];
-                        const uint32_t rr = (uint32_t)(r0[i] + r);
                         float4 Gv = make_float4(0.f, 0.f, 0.f, 0.f), o = Gv;
-                        if (v) Gv = lds128(gb + 4u * rr * (uint32_t)Fi + 16u * (lc ^ (rr & SWZ)));
+                        if (v) Gv = lds128(gb + a_goff[i][r]);
                         if constexpr (OLD_REGS) {
                             o = old[i][r];
                         } else {
@@ -536,9 +570,12 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                         }
                     }
                 }
+                CG_STAMP(trc, s * 10 + 2);
                 if (k > 0) dump(k - 1);
+                CG_STAMP(trc, s * 10 + 3);
                 umma::fence_before_sync();
                 __syncthreads();                     // sync s+1
+                CG_STAMP(trc, s * 10 + 4);
             }
         }
     }
@@ -682,6 +719,12 @@ static cudaError_t launch_c(const CPlan &pl, dim3 grid, cudaStream_t s) {
 }  // namespace
 
 extern int g_fused_last_plan[8];
+static long long *g_clenshaw_trace = nullptr;
+// debug aid: clock64 stamps of CTA 0's second group in k_cheb_clenshaw_b, [K][10] int64 on the device
+extern "C" int cg_debug_clenshaw_trace(long long *dev_buf) {
+    g_clenshaw_trace = dev_buf;
+    return CG_OK;
+}
 
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K) {
     return choose_cplan(g, N, Fin, Fout, K).ok;
@@ -714,6 +757,7 @@ int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *d
     cp.Fi = Fin;
     cp.Fo = Fout;
     cp.K = K;
+    cp.trace = g_clenshaw_trace;
     const int64_t G = cg_ceil_div(N, pl.S);
     dim3 grid((unsigned)std::min<int64_t>(G, g->sm_count));
     g_fused_last_plan[4] = pl.blocked ? 1 : 0;

@@ -24,6 +24,20 @@
 #include "cg_umma.cuh"
 #include "cg_fused_common.cuh"
 
+// clock64 stamps for scripts/prof_fused.py: compiled in only with -DCG_TRACE_BUILD (CG_TRACE_BUILD=1 python -m
+// cnn_graph_b200.build --force); even a predicated-off stamp costs issue slots in the hot loops
+#ifdef CG_TRACE_BUILD
+#define CG_STAMP(cond, idx)                    \
+    do {                                       \
+        if (cond) p.trace[idx] = clock64();    \
+    } while (0)
+#else
+#define CG_STAMP(cond, idx) \
+    do {                    \
+        (void)(cond);       \
+    } while (0)
+#endif
+
 namespace {
 
 constexpr int FC = 512;        // compute threads
@@ -104,12 +118,12 @@ __device__ __forceinline__ void fused_issue_group(const FusedParams &p, const Fu
         __syncthreads();                                  // staging of step k is complete
         if (lane == 0 && umma::elect_lane0()) {
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1;
-            if (tr) p.trace[k * 10 + 4] = clock64();
+            CG_STAMP(tr, k * 10 + 4);
             const int b = k & (p.nw - 1);
             umma::mbar_wait(c.wbar + b, (wpar >> b) & 1u);
             wpar ^= 1u << b;
             umma::fence_after_sync();
-            if (tr) p.trace[k * 10 + 5] = clock64();
+            CG_STAMP(tr, k * 10 + 5);
             const uint32_t wb = c.w0 + (uint32_t)b * c.wbytes;
             const uint32_t b_lo = umma::desc_lo(wb, lbo_w);
             uint32_t at = a_lo, acc = c.tmem;
@@ -125,12 +139,12 @@ __device__ __forceinline__ void fused_issue_group(const FusedParams &p, const Fu
                 }
             }
             umma::commit(c.mbar);
-            if (tr) p.trace[k * 10 + 6] = clock64();
+            CG_STAMP(tr, k * 10 + 6);
             // W_{k+nw} goes where W_k was, once the MMAs of step k have read it; waiting for every
             // step also guarantees that nothing is in flight when the group ends
             umma::mbar_wait(c.mbar, mpar);
             mbar_arrive(c.sbar);                    // compute warps may overwrite the planes (once the store warp agrees)
-            if (tr) p.trace[k * 10 + 7] = clock64();
+            CG_STAMP(tr, k * 10 + 7);
             if (k + p.nw < K) {
                 mbar_expect_tx(c.wbar + b, c.wbytes);
                 bulk_g2s(wb, p.wp + (size_t)(k + p.nw) * c.wbytes, c.wbytes, c.wbar + b);
@@ -154,7 +168,7 @@ __device__ __forceinline__ void fused_store_group(const FusedParams &p, const Fu
         __syncthreads();                                  // staging of step k is complete
         if (p.planes_out != nullptr && lane == 0 && umma::elect_lane0()) {
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && sw == 0;
-            if (tr) p.trace[k * 10 + 8] = clock64();
+            CG_STAMP(tr, k * 10 + 8);
             unsigned char *kbase = p.planes_out + (size_t)k * p.planes_k;
             for (long long ch = (g0 >> 7) + sw; ch <= (g1 - 1) >> 7; ch += NSTORE) {
                 const long long a = max(g0, ch << 7), b = min(g1, (ch + 1) << 7);
@@ -171,7 +185,7 @@ __device__ __forceinline__ void fused_store_group(const FusedParams &p, const Fu
             bulk_commit();
             bulk_wait_read();
             mbar_arrive(c.sbar);
-            if (tr) p.trace[k * 10 + 9] = clock64();
+            CG_STAMP(tr, k * 10 + 9);
         }
         __syncwarp();
     }
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 if (a_soff[i] < limb) res[i] = lds128(aP + a_soff[i]);
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && tid == 0;
             for (int k = 0; k < K; ++k) {
-                if (tr) p.trace[k * 10 + 0] = clock64();
+                CG_STAMP(tr, k * 10 + 0);
                 if (k > 0) {
                     const uint32_t prev = (k & 1) ? aP : aQ;     // X_{k-1}
                     const uint32_t cur = (k & 1) ? aQ : aP;      // X_{k-2} -> X_k
@@ -341,11 +355,11 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                         if (a_soff[i1] < limb) sts128(cur + a_soff[i1], acc1);
                     }
                     // the staging planes are free once the MMAs (and bulk stores) of step k-1 have read them
-                    if (tr) p.trace[k * 10 + 1] = clock64();
+                    CG_STAMP(tr, k * 10 + 1);
                     umma::mbar_wait(sbar, mpar);
                     mpar ^= 1;
                 }
-                if (tr) p.trace[k * 10 + 2] = clock64();
+                CG_STAMP(tr, k * 10 + 2);
                 if (p.stack_out != nullptr) {       // side output for the backward pass (coalesced 128-bit stores)
                     char *dst = reinterpret_cast<char *>(p.stack_out + ((size_t)k * p.N + n0) * M * Fin);
 #pragma unroll
@@ -371,7 +385,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused(const FusedParams p) {
                 }
                 umma::fence_proxy_async();
                 if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
-                if (tr) p.trace[k * 10 + 3] = clock64();
+                CG_STAMP(tr, k * 10 + 3);
                 __syncthreads();
             }
             // ---- epilogue: TMEM -> registers -> y
@@ -421,9 +435,10 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused_b(const FusedParams p) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.M, Fin = p.Fin, Fout = p.Fout, K = p.K, S = p.S;
+    constexpr int Fin = 4 * LPR;                 // compile-time row width: no multiplications in the address arithmetic
+    const int M = p.M, Fout = p.Fout, K = p.K, S = p.S;
     const bool is_issuer = warp >= FC / 32;      // MMA issue warp or plane store warp
-    const uint32_t rowb = (uint32_t)Fin * 4u;
+    constexpr uint32_t rowb = (uint32_t)Fin * 4u;
 
     // ---- one-time setup ------------------------------------------------------------
     {   // pad rows of the A operand are never written by the steps: clear the staging planes once
@@ -507,7 +522,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused_b(const FusedParams p) {
             }
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gi == 1 && tid == 0;
             for (int k = 0; k < K; ++k) {
-                if (tr) p.trace[k * 10 + 0] = clock64();
+                CG_STAMP(tr, k * 10 + 0);
                 if (k > 0) {
                     const uint32_t prev = (k & 1) ? aP : aQ;     // X_{k-1}
                     const uint32_t cur = (k & 1) ? aQ : aP;      // X_{k-2} -> X_k
@@ -534,11 +549,11 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused_b(const FusedParams p) {
                             if (r < nr[i]) sts128(cur + a_soff[i] + (uint32_t)r * rowb, acc[r]);
                         }
                     }
-                    if (tr) p.trace[k * 10 + 1] = clock64();
+                    CG_STAMP(tr, k * 10 + 1);
                     umma::mbar_wait(sbar, mpar);
                     mpar ^= 1;
                 }
-                if (tr) p.trace[k * 10 + 2] = clock64();
+                CG_STAMP(tr, k * 10 + 2);
                 if (p.stack_out != nullptr) {       // side output for the backward pass (coalesced 128-bit stores)
                     char *dst = reinterpret_cast<char *>(p.stack_out + ((size_t)k * p.N + n0) * M * Fin);
 #pragma unroll
@@ -566,7 +581,7 @@ __global__ void __launch_bounds__(FT, 1) k_cheb_fused_b(const FusedParams p) {
                     }
                 umma::fence_proxy_async();
                 if (k == 0) umma::fence_before_sync();     // orders the previous group's TMEM loads
-                if (tr) p.trace[k * 10 + 3] = clock64();
+                CG_STAMP(tr, k * 10 + 3);
                 __syncthreads();
             }
             // ---- epilogue: TMEM -> registers -> y

@@ -175,6 +175,7 @@ __device__ __forceinline__ void blk_gather(uint32_t gbase, uint32_t tab, int tri
     constexpr uint32_t REC = BlkGeom<LPR>::REC;
     float4 wa = lds128(tab), wb = lds128(tab + REC);
     uint32_t oa = lds32(tab + 16u), ob = lds32(tab + REC + 16u);
+#pragma unroll 2
     for (int j = 0; j < trips; j += 2) {
         const float4 xa = lds128(gbase + oa), xb = lds128(gbase + ob);
         const float4 ca = wa, cb = wb;

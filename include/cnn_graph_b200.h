@@ -263,6 +263,7 @@ int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, 
  * recent fused forward ([0..3]) and Clenshaw ([4..7]) launch: {row-block gather used, samples per group, items per
  * thread, dynamic shared-memory bytes}.                                                                        */
 int cg_debug_fused_trace(long long *dev_buf);
+int cg_debug_clenshaw_trace(long long *dev_buf);     /* same for the row-block Clenshaw kernel */
 int cg_debug_fused_plan_info(int *info8);
 
 /* ---- host-side native loops of the coarsening -------------------------- */

@@ -76,6 +76,21 @@ if os.environ.get('CG_TRACE'):
     for k in range(a.K):
         print('%2d ' % k + ' '.join('%9d' % (v - t0 if v else -1) for v in t[k]))
 
+if os.environ.get('CG_TRACE_CL'):
+    fn = _lib.cg_debug_clenshaw_trace
+    buf = torch.zeros(a.K * 10, dtype=torch.int64, device='cuda')
+    fn(buf.data_ptr())
+    y = ops.cheb_filter(x, W, L, a.K, flags=a.flags)
+    y.backward(gy)
+    torch.cuda.synchronize()
+    fn(None)
+    t = buf.cpu().numpy().reshape(a.K, 10)
+    t0 = t[0, 0]
+    names = ['start', 'gathered', 'stored', 'dumped', 'synced', 'I_start', 'I_issued', 'I_done', '-', '-']
+    print(' s ' + ' '.join('%9s' % n for n in names))
+    for k in range(a.K):
+        print('%2d ' % k + ' '.join('%9d' % (v - t0 if v else -1) for v in t[k]))
+
 if os.environ.get('CG_TRACE_DW'):
     fn = ctypes.CDLL(_native.LIB_PATH).cg_debug_dw_trace
     fn.argtypes = [ctypes.c_void_p]
