@@ -62,8 +62,8 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
         CG_CHECK_CUDA(cudaMalloc(&dst.ell, sizeof(float2) * ell.size()));
         CG_CHECK_CUDA(cudaMemcpy(dst.ell, ell.data(), sizeof(float2) * ell.size(), cudaMemcpyHostToDevice));
     }
-    if (want_ell) {
-        // row-block (4 rows) union form, see CgCsr
+    {
+        // row-block (4 rows) union form, see CgCsr (built for every operator: the streaming step uses it too)
         const int nblk = (M + 3) / 4;
         std::vector<int> bptr(nblk + 1, 0), bcol;
         std::vector<float4> bw;
@@ -98,7 +98,8 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
         const size_t nt = std::max<size_t>(bcol.size(), 1);
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_order, sizeof(int) * (size_t)nblk));
-        CG_CHECK_CUDA(cudaMalloc(&dst.blk_col, sizeof(int) * nt));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_col, sizeof(int) * (nt + 8)));      // + slack: the tiled step copies 16-byte aligned runs
+        CG_CHECK_CUDA(cudaMemset(dst.blk_col, 0, sizeof(int) * (nt + 8)));
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_w, sizeof(float4) * nt));
         CG_CHECK_CUDA(cudaMemcpy(dst.blk_ptr, bptr.data(), sizeof(int) * (size_t)(nblk + 1), cudaMemcpyHostToDevice));
         CG_CHECK_CUDA(cudaMemcpy(dst.blk_order, border.data(), sizeof(int) * (size_t)nblk, cudaMemcpyHostToDevice));

@@ -9,6 +9,8 @@
 //                      HBM traffic = read X once + write the K-1 new slabs.
 //   k_spmm_step     -- one step per launch for operators too large for SMEM
 //                      (CSR from HBM/L2, 128-bit gathers along the column axis).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "cg_common.cuh"
@@ -94,17 +96,268 @@ k_spmm_step(const int *__restrict__ rowptr, const int *__restrict__ col, const f
     *reinterpret_cast<V *>(out + m * C + c) = r;
 }
 
-static int launch_step(const CgCsr &L, int M, const float *X1, const float *X0, float *out, int64_t C,
+// The same step on the row-block form of the operator (CgCsr::blk_*): a thread owns 4 consecutive rows x 4 columns and
+// walks the UNION of the four rows' entries -- one 128-bit gather of X1 feeds 16 FMAs, and a neighbour that several of
+// the four rows reference is fetched once.  On a locality-ordered kNN graph (C5: Morton order, 18 entries per row) the
+// union is 0.44 of the entry count, which is what the L1 gather path -- the limiter of k_spmm_step, not HBM -- sees.
+// block = 256 threads = (256 / lpr) row blocks x lpr lanes.
+template <int U, int B>
+__global__ void __launch_bounds__(256, B)
+k_spmm_step_b(const int *__restrict__ bptr, const int *__restrict__ bcol, const float4 *__restrict__ bw,
+              const float *__restrict__ X1, const float *__restrict__ X0, float *__restrict__ out, int M, int64_t C,
+              float alpha, int lpr) {
+    const int lane = threadIdx.x % lpr;
+    const int64_t blk = (int64_t)blockIdx.x * (256 / lpr) + threadIdx.x / lpr;
+    const int64_t m0 = 4 * blk;
+    const int64_t c = ((int64_t)blockIdx.y * lpr + lane) * 4;
+    if (m0 >= M || c >= C) return;
+    const int beg = bptr[blk], end = bptr[blk + 1];
+    float4 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *x1 = X1 + c;
+    int e = beg;
+    for (; e + U - 1 < end; e += U) {
+        int cc[U];
+        float4 ww[U], xx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cc[u] = bcol[e + u];
+            ww[u] = bw[e + u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xx[u] = *reinterpret_cast<const float4 *>(x1 + (int64_t)cc[u] * C);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            fma_acc(acc[0], ww[u].x, xx[u]);
+            fma_acc(acc[1], ww[u].y, xx[u]);
+            fma_acc(acc[2], ww[u].z, xx[u]);
+            fma_acc(acc[3], ww[u].w, xx[u]);
+        }
+    }
+    for (; e < end; ++e) {
+        const float4 w = bw[e];
+        const float4 x = *reinterpret_cast<const float4 *>(x1 + (int64_t)bcol[e] * C);
+        fma_acc(acc[0], w.x, x);
+        fma_acc(acc[1], w.y, x);
+        fma_acc(acc[2], w.z, x);
+        fma_acc(acc[3], w.w, x);
+    }
+    const int nrow = (int)min((int64_t)4, (int64_t)M - m0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r >= nrow) break;
+        float4 v;
+        if (X0 != nullptr) {
+            const float4 old = *reinterpret_cast<const float4 *>(X0 + (m0 + r) * C + c);
+            v = axmb(alpha, acc[r], old);
+        } else {
+            v = scale(alpha, acc[r]);
+        }
+        *reinterpret_cast<float4 *>(out + (m0 + r) * C + c) = v;
+    }
+}
+
+// Tiled form of the row-block step for slabs of at most 128 columns: a CTA owns TR = 4 * (512 / lpr) consecutive rows
+// (128 at C = 64).  The tile's rows of X1 and X0 and its entries (columns + weights, one contiguous run of the block
+// arrays) come in by four bulk copies (TMA engine, one mbarrier): every streaming operand of the step is read by large
+// sequential copies with nothing in registers, so two resident CTAs keep far more bytes in flight than the register
+// path (which ncu showed latency bound: 71 - 78 % long-scoreboard stalls at 33 % of the DRAM rate).  Entries whose
+// column falls inside the tile -- 3/4 of them on a Morton-ordered kNN graph -- are gathered from the staged X1 tile in
+// shared memory, the rest from L1 / L2.
+constexpr int ST_THREADS = 512;
+constexpr int ST_EMAX = 2048;              // entries staged per tile: 32 KB of weights + 8 KB of columns
+constexpr int ST_TILE_BYTES = ST_THREADS * 64;      // bytes of one X tile: every thread owns 4 rows x 16 bytes
+
+struct TileParams {
+    const int *bptr, *bcol;
+    const float4 *bw;
+    const float *X1, *X0;
+    float *out;
+    int M, C, lpr, TR;
+    float alpha;
+};
+
+__device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(ST_THREADS, 2) k_spmm_tile(const TileParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *x1t = reinterpret_cast<float *>(smem);
+    float *x0t = reinterpret_cast<float *>(smem + ST_TILE_BYTES);
+    float4 *wt = reinterpret_cast<float4 *>(smem + 2 * ST_TILE_BYTES);
+    int *ct = reinterpret_cast<int *>(smem + 2 * ST_TILE_BYTES + ST_EMAX * 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * ST_TILE_BYTES + ST_EMAX * 16 + (ST_EMAX + 8) * 4);
+    __shared__ int s_e0, s_ne;
+
+    const int tid = threadIdx.x, lpr = p.lpr, C = p.C;
+    const int row0 = blockIdx.x * p.TR;
+    const int rows = min(p.TR, p.M - row0);
+    const int b0 = row0 >> 2, nb = (rows + 3) >> 2;
+    if (tid == 0) {
+        const int e0 = p.bptr[b0], e1 = p.bptr[b0 + nb];
+        s_e0 = e0;
+        s_ne = e1 - e0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t xb = (uint32_t)rows * (uint32_t)C * 4u;
+        const bool staged = e1 - e0 <= ST_EMAX;
+        const int a0 = e0 & ~3;                                   // 16-byte aligned start of the column run
+        const uint32_t cb = staged ? (uint32_t)(((e1 - a0) + 3) & ~3) * 4u : 0u;
+        const uint32_t wb = staged ? (uint32_t)(e1 - e0) * 16u : 0u;
+        const uint32_t total = xb + (p.X0 != nullptr ? xb : 0u) + cb + wb;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem(bar)), "r"(total) : "memory");
+        const uint32_t mb = st_smem(bar);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(x1t)),
+                     "l"(p.X1 + (size_t)row0 * C), "r"(xb), "r"(mb)
+                     : "memory");
+        if (p.X0 != nullptr)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(x0t)),
+                         "l"(p.X0 + (size_t)row0 * C), "r"(xb), "r"(mb)
+                         : "memory");
+        if (wb != 0u)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(wt)),
+                         "l"(p.bw + e0), "r"(wb), "r"(mb)
+                         : "memory");
+        if (cb != 0u)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(ct)),
+                         "l"(p.bcol + a0), "r"(cb), "r"(mb)
+                         : "memory");
+    }
+    __syncthreads();
+    const int e0 = s_e0, ne = s_ne;
+    const bool staged = ne <= ST_EMAX;
+    const int lane = tid % lpr, bl = tid / lpr;          // block of the tile, lane inside the row
+    const bool active = bl < nb && lane * 4 < C;
+    int beg = 0, end = 0;
+    if (active) {                                         // overlaps the copies
+        beg = p.bptr[b0 + bl] - e0;
+        end = p.bptr[b0 + bl + 1] - e0;
+    }
+    {   // wait for the tile
+        uint32_t done = 0;
+        while (!done)
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                : "=r"(done)
+                : "r"(st_smem(bar))
+                : "memory");
+    }
+    if (!active) return;
+    const int c = lane * 4;
+    const int coff = e0 & 3;                              // the staged column run starts at the aligned entry
+    const int *cols = staged ? ct + coff : p.bcol + e0;
+    const float4 *ws = staged ? wt : p.bw + e0;
+    const float *x1g = p.X1 + c;
+    const float *x1s = x1t + c;
+    float4 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 4;
+    int e = beg;
+    for (; e + U - 1 < end; e += U) {
+        int cc[U];
+        float4 ww[U], xx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cc[u] = cols[e + u];
+            ww[u] = ws[e + u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned rel = (unsigned)(cc[u] - row0);
+            if (rel < (unsigned)rows)
+                xx[u] = *reinterpret_cast<const float4 *>(x1s + (size_t)rel * C);
+            else
+                xx[u] = *reinterpret_cast<const float4 *>(x1g + (size_t)cc[u] * C);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            fma_acc(acc[0], ww[u].x, xx[u]);
+            fma_acc(acc[1], ww[u].y, xx[u]);
+            fma_acc(acc[2], ww[u].z, xx[u]);
+            fma_acc(acc[3], ww[u].w, xx[u]);
+        }
+    }
+    for (; e < end; ++e) {
+        const int cc = cols[e];
+        const float4 w = ws[e];
+        const unsigned rel = (unsigned)(cc - row0);
+        const float4 x = rel < (unsigned)rows ? *reinterpret_cast<const float4 *>(x1s + (size_t)rel * C)
+                                               : *reinterpret_cast<const float4 *>(x1g + (size_t)cc * C);
+        fma_acc(acc[0], w.x, x);
+        fma_acc(acc[1], w.y, x);
+        fma_acc(acc[2], w.z, x);
+        fma_acc(acc[3], w.w, x);
+    }
+    const int nrow = min(4, rows - 4 * bl);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r >= nrow) break;
+        const int lr = 4 * bl + r;
+        float4 v;
+        if (p.X0 != nullptr) {
+            const float4 old = *reinterpret_cast<const float4 *>(x0t + (size_t)lr * C + c);
+            v = axmb(p.alpha, acc[r], old);
+        } else {
+            v = scale(p.alpha, acc[r]);
+        }
+        *reinterpret_cast<float4 *>(p.out + (size_t)(row0 + lr) * C + c) = v;
+    }
+}
+
+// row-block form wanted?  It pays when neighbouring rows share neighbours; CG_SPMM_BLOCK=0/1 overrides (tests).
+static bool step_blocked(const CgCsr &L, int64_t nnz_hint) {
+    if (L.nblk == 0) return false;
+    if (const char *env = getenv("CG_SPMM_BLOCK")) return atoi(env) != 0;
+    return (int64_t)L.blk_total * 10 <= nnz_hint * 7;
+}
+
+static int launch_step(const CgCsr &L, int64_t nnz, int M, const float *X1, const float *X0, float *out, int64_t C,
                        float alpha, cudaStream_t s) {
     const bool vec4 = (C % 4 == 0) && ((((uintptr_t)X1 | (uintptr_t)out | (uintptr_t)X0) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     int64_t lanes_needed = cg_ceil_div(C, vec);
     int lpr = 32;
     while (lpr > 1 && lpr / 2 >= lanes_needed) lpr /= 2;
+    CgProfScope prof("spmm_step", s);
+    if (vec4 && step_blocked(L, nnz) && lanes_needed <= 32 && (int64_t)M * C < ((int64_t)1 << 31)) {
+        // tiled form (see k_spmm_tile); CG_SPMM_TILE=0 keeps the register-path block kernel
+        const char *env = getenv("CG_SPMM_TILE");
+        if (env == nullptr || atoi(env) != 0) {
+            TileParams tp;
+            tp.bptr = L.blk_ptr;
+            tp.bcol = L.blk_col;
+            tp.bw = L.blk_w;
+            tp.X1 = X1;
+            tp.X0 = X0;
+            tp.out = out;
+            tp.M = M;
+            tp.C = (int)C;
+            tp.lpr = lpr;
+            tp.TR = 4 * (ST_THREADS / lpr);
+            tp.alpha = alpha;
+            const size_t smem = 2 * (size_t)ST_TILE_BYTES + (size_t)ST_EMAX * 16 + (size_t)(ST_EMAX + 8) * 4 + 16;
+            static bool attr_set = false;
+            if (!attr_set) {
+                CG_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            k_spmm_tile<<<(unsigned)cg_ceil_div(M, tp.TR), ST_THREADS, smem, s>>>(tp);
+            CG_LAUNCH_CHECK();
+            return CG_OK;
+        }
+    }
+    if (vec4 && step_blocked(L, nnz)) {
+        const int blocks_per_cta = 256 / lpr;
+        dim3 grid((unsigned)cg_ceil_div(cg_ceil_div(M, 4), blocks_per_cta), (unsigned)cg_ceil_div(lanes_needed, lpr));
+        CG_REQUIRE(grid.y <= 65535, "spmm_step: too many columns (C=%lld)", (long long)C);
+        k_spmm_step_b<4, 3><<<grid, 256, 0, s>>>(L.blk_ptr, L.blk_col, L.blk_w, X1, X0, out, M, C, alpha, lpr);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     const int rows_per_block = 256 / lpr;
     dim3 grid((unsigned)cg_ceil_div(M, rows_per_block), (unsigned)cg_ceil_div(lanes_needed, lpr));
     CG_REQUIRE(grid.y <= 65535, "spmm_step: too many columns (C=%lld)", (long long)C);
-    CgProfScope prof("spmm_step", s);
     // measured at C5 (2^20 vertices, 18.6 M entries, C = 64): U = 4 gathers in flight at full occupancy (register cap 32)
     // 0.339 ms; without the cap (39 registers, 6 blocks) 0.378; U = 8 0.374 (6 blocks) / 0.465 (4); U = 2 at 8 blocks 0.351
     if (vec4)
@@ -408,7 +661,7 @@ static int run_basis_from(const cg_graph *g, int transpose, const float *in, flo
     for (int k = 1; k < K; ++k) {
         const float *x1 = stack + (int64_t)(k - 1) * slab;
         const float *x0 = k > 1 ? stack + (int64_t)(k - 2) * slab : nullptr;
-        int rc = launch_step(L, M, x1, x0, stack + (int64_t)k * slab, C, k > 1 ? 2.0f : 1.0f, s);
+        int rc = launch_step(L, g->nnz, M, x1, x0, stack + (int64_t)k * slab, C, k > 1 ? 2.0f : 1.0f, s);
         if (rc != CG_OK) return rc;
     }
     return CG_OK;
@@ -433,5 +686,5 @@ extern "C" int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev
     CG_REQUIRE(g && dev_X1 && dev_out, "cg_cheb_step: NULL argument");
     CG_REQUIRE(C > 0 && rows >= 0 && rows <= g->M, "cg_cheb_step: bad C / rows (C=%lld rows=%d M=%d)", (long long)C, rows, g->M);
     if (rows == 0) return CG_OK;
-    return launch_step(cg_side(g, transpose), rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
+    return launch_step(cg_side(g, transpose), g->nnz, rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
 }

@@ -54,6 +54,16 @@ def gather(request):
     os.environ.pop('CG_FUSED_BLOCK', None)
 
 
+@pytest.fixture(params=['csr', 'blocks'])
+def spmm_form(request):
+    """Both forms of the streaming recurrence step: one row per thread group (k_spmm_step) and 4-row union blocks
+    (k_spmm_step_b); the library picks by the operator's locality unless CG_SPMM_BLOCK says otherwise."""
+    import os
+    os.environ['CG_SPMM_BLOCK'] = '1' if request.param == 'blocks' else '0'
+    yield request.param
+    os.environ.pop('CG_SPMM_BLOCK', None)
+
+
 FLAG_SETS = [0, 1, 4]   # default (fused / on-chip when it fits), forced streaming, on-chip without the fused kernel
 
 
@@ -70,6 +80,26 @@ def test_basis_matches_reference_fixtures(ops, c2, directed, flags):
     close(ops.cheb_basis(h0, dev(c2['basis0_X']), 25, flags=flags), c2['basis0_K25'], 1e-5)    # C = 5: scalar path
     hd = ops.GraphHandle(csr_from(directed, 'Lr'))
     close(ops.cheb_basis(hd, dev(directed['X']), 6, flags=flags), directed['basis_K6'], 1e-5)
+
+
+def test_streaming_step_forms_vs_reference(ops, c2, c1, directed, spmm_form):
+    """Forced streaming path (one launch per recurrence step) in both step forms: reference fixtures of the basis, a
+    directed operator on both sides, a vertex count that is not a multiple of 4, wide and narrow slabs."""
+    from oracle import graph_ref
+    h0 = ops.GraphHandle(csr_from(c2, 'Lr0'))
+    close(ops.cheb_basis(h0, dev(c2['basis0_X'][:, :4]), 25, flags=1), c2['basis0_K25'][:, :, :4], 1e-5)
+    h2 = ops.GraphHandle(csr_from(c2, 'Lr2'))
+    close(ops.cheb_basis(h2, dev(c2['basis_X']), 7, flags=1), c2['basis_K7'], 1e-5)
+    Lr = csr_from(directed, 'Lr')           # M = 57
+    hd = ops.GraphHandle(Lr)
+    rng = np.random.RandomState(3)
+    for C in (4, 64, 520):
+        X = rng.standard_normal((Lr.shape[0], C)).astype(np.float32)
+        close(ops.cheb_basis(hd, dev(X), 6, flags=1), graph_ref.chebyshev(Lr, X, 6), 1e-5)
+        close(ops.cheb_basis(hd, dev(X), 6, transpose=True, flags=1), graph_ref.chebyshev(scipy.sparse.csr_matrix(Lr.T), X, 6), 1e-5)
+    L1 = csr_from(c1, 'Lr1')
+    X = rng.standard_normal((L1.shape[0], 96)).astype(np.float32)
+    close(ops.cheb_basis(ops.GraphHandle(L1), dev(X), 9, flags=1), graph_ref.chebyshev(L1, X, 9), 1e-5)
 
 
 def test_basis_transpose_and_wide(ops, directed):
