@@ -77,6 +77,8 @@ struct CgCsr {
     int *blk_ptr = nullptr;  // [nblk + 1]
     int *blk_col = nullptr;  // [blk_total]
     float4 *blk_w = nullptr; // [blk_total]  weights of rows 4b .. 4b+3 for that column
+    int *blk_ps = nullptr;   // [2 * nblk + 1] interleaved {ptr[b], split[b]}: inside a block the entries whose column lies in
+                             // the block's own 128-row window come first ("near": [ptr, split)), the others after ("far")
     int *blk_order = nullptr;            // blocks by descending union size (stable)
     std::vector<int> blk_len_sorted;     // host copy: union sizes in that order (kernel planning)
 };

@@ -2,6 +2,7 @@
 // Replaces the per-call COO -> tf.SparseTensor -> tf.sparse_reorder staging of the
 // reference (lib/models.py:198-201, lib/filter.py:66-70).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -65,7 +66,10 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
     {
         // row-block (4 rows) union form, see CgCsr (built for every operator: the streaming step uses it too)
         const int nblk = (M + 3) / 4;
-        std::vector<int> bptr(nblk + 1, 0), bcol;
+        // experiment switch: near entries (the block's own 128-row window) first; default off (column-sorted run: the tiled
+        // step with a far batch was slower than the plain sorted walk)
+        const bool split_near_far = getenv("CG_BLK_SPLIT") != nullptr && atoi(getenv("CG_BLK_SPLIT")) != 0;
+        std::vector<int> bptr(nblk + 1, 0), bcol, bps(2 * (size_t)nblk + 1 + 8, 0);
         std::vector<float4> bw;
         for (int b = 0; b < nblk; ++b) {
             int cur[4], end[4];
@@ -85,7 +89,30 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
                 bcol.push_back(c);
                 bw.push_back(make_float4(w[0], w[1], w[2], w[3]));
             }
+            // near entries (column inside the block's 128-row window) first: the tiled streaming step gathers them from
+            // shared memory and batches the far ones (cg_spmm.cu); a stable partition keeps both parts sorted by column
+            if (split_near_far) {
+                const int lo = bptr[b], hi = (int)bcol.size(), win = (4 * b) >> 7;
+                std::vector<int> tc;
+                std::vector<float4> tw;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int e = lo; e < hi; ++e)
+                        if (((bcol[e] >> 7) == win) == (pass == 0)) {
+                            tc.push_back(bcol[e]);
+                            tw.push_back(bw[e]);
+                        }
+                int nnear = 0;
+                for (int e = lo; e < hi; ++e) nnear += (bcol[e] >> 7) == win ? 1 : 0;
+                std::copy(tc.begin(), tc.end(), bcol.begin() + lo);
+                std::copy(tw.begin(), tw.end(), bw.begin() + lo);
+                bps[2 * b] = lo;
+                bps[2 * b + 1] = lo + nnear;
+            } else {
+                bps[2 * b] = bptr[b];
+                bps[2 * b + 1] = (int)bcol.size();      // everything "near": one column-sorted run
+            }
             bptr[b + 1] = (int)bcol.size();
+            bps[2 * b + 2] = (int)bcol.size();
         }
         std::vector<int> border(nblk);
         for (int b = 0; b < nblk; ++b) border[b] = b;
@@ -96,8 +123,11 @@ static int upload_side(CgCsr &dst, int M, int64_t nnz, const std::vector<int> &r
         dst.blk_len_sorted.resize(nblk);
         for (int i = 0; i < nblk; ++i) dst.blk_len_sorted[i] = bptr[border[i] + 1] - bptr[border[i]];
         const size_t nt = std::max<size_t>(bcol.size(), 1);
-        CG_CHECK_CUDA(cudaMalloc(&dst.blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_ptr, sizeof(int) * (size_t)(nblk + 1 + 8)));     // + slack, as blk_col
+        CG_CHECK_CUDA(cudaMemset(dst.blk_ptr, 0, sizeof(int) * (size_t)(nblk + 1 + 8)));
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_order, sizeof(int) * (size_t)nblk));
+        CG_CHECK_CUDA(cudaMalloc(&dst.blk_ps, sizeof(int) * bps.size()));
+        CG_CHECK_CUDA(cudaMemcpy(dst.blk_ps, bps.data(), sizeof(int) * bps.size(), cudaMemcpyHostToDevice));
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_col, sizeof(int) * (nt + 8)));      // + slack: the tiled step copies 16-byte aligned runs
         CG_CHECK_CUDA(cudaMemset(dst.blk_col, 0, sizeof(int) * (nt + 8)));
         CG_CHECK_CUDA(cudaMalloc(&dst.blk_w, sizeof(float4) * nt));
@@ -121,6 +151,7 @@ static void free_side(CgCsr &s) {
     cudaFree(s.blk_col);
     cudaFree(s.blk_w);
     cudaFree(s.blk_order);
+    cudaFree(s.blk_ps);
     s = CgCsr();
 }
 

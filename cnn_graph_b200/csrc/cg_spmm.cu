@@ -158,100 +158,119 @@ k_spmm_step_b(const int *__restrict__ bptr, const int *__restrict__ bcol, const 
     }
 }
 
-// Tiled form of the row-block step for slabs of at most 128 columns: a CTA owns TR = 4 * (512 / lpr) consecutive rows
-// (128 at C = 64).  The tile's rows of X1 and X0 and its entries (columns + weights, one contiguous run of the block
-// arrays) come in by four bulk copies (TMA engine, one mbarrier): every streaming operand of the step is read by large
-// sequential copies with nothing in registers, so two resident CTAs keep far more bytes in flight than the register
-// path (which ncu showed latency bound: 71 - 78 % long-scoreboard stalls at 33 % of the DRAM rate).  Entries whose
-// column falls inside the tile -- 3/4 of them on a Morton-ordered kNN graph -- are gathered from the staged X1 tile in
-// shared memory, the rest from L1 / L2.
+// Tiled form of the row-block step for slabs of 16 .. 128 columns: a tile is TR = 4 * (512 / lpr) consecutive rows
+// (128 at C = 64).  The tile's rows of X1 and X0, its block pointers and its entries (columns + weights, one contiguous
+// run of the block arrays) come in by five bulk copies (TMA engine, one mbarrier): every streaming operand of the step
+// is read by large sequential copies with nothing in registers (the register path is latency bound: ncu shows 71 - 78 %
+// long-scoreboard stalls at 33 % of the DRAM rate).  Entries whose column falls inside the tile -- 3/4 of them on a
+// Morton-ordered kNN graph -- are gathered from the staged X1 tile in shared memory; the others ("far", stored last in
+// every block) are fetched from L1 / L2 eight at a time before the near ones are applied.
 constexpr int ST_THREADS = 512;
-constexpr int ST_EMAX = 2048;              // entries staged per tile: 32 KB of weights + 8 KB of columns
 constexpr int ST_TILE_BYTES = ST_THREADS * 64;      // bytes of one X tile: every thread owns 4 rows x 16 bytes
 
 struct TileParams {
-    const int *bptr, *bcol;
+    const int *bps, *bcol;       // CgCsr::blk_ps, blk_col
     const float4 *bw;
     const float *X1, *X0;
     float *out;
-    int M, C, lpr, TR;
+    int flags;                   // bit 0: L2 prefetch two tiles ahead
+    int M, Mx, C, lpr, TR;       // M rows to compute; Mx >= M rows of X1 exist (row partition: halo rows follow the local ones)
     float alpha;
 };
 
 __device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(ST_THREADS, 2) k_spmm_tile(const TileParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    float *x1t = reinterpret_cast<float *>(smem);
-    float *x0t = reinterpret_cast<float *>(smem + ST_TILE_BYTES);
-    float4 *wt = reinterpret_cast<float4 *>(smem + 2 * ST_TILE_BYTES);
-    int *ct = reinterpret_cast<int *>(smem + 2 * ST_TILE_BYTES + ST_EMAX * 16);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * ST_TILE_BYTES + ST_EMAX * 16 + (ST_EMAX + 8) * 4);
-    __shared__ int s_e0, s_ne;
+// Persistent and double-buffered: one CTA per SM walks tiles blockIdx.x, + gridDim.x, ...; a producer warp keeps the
+// NEXT tile's copies in flight while the 16 compute warps work on the current one.
+constexpr int SP_EMAX = 1536;              // entries staged per tile and stage: 24 KB of weights + 6 KB of columns
+constexpr int SP_PTRS = 264;               // {ptr, split} pairs of a tile (<= 2 * 128 + 1 + alignment slack)
+constexpr uint32_t SP_OFF_X0 = ST_TILE_BYTES, SP_OFF_W = 2 * ST_TILE_BYTES, SP_OFF_C = SP_OFF_W + SP_EMAX * 16,
+                   SP_OFF_P = SP_OFF_C + (SP_EMAX + 8) * 4, SP_OFF_H = SP_OFF_P + SP_PTRS * 4,
+                   SP_STAGE = (SP_OFF_H + 32 + 127) / 128 * 128;
+static_assert(SP_STAGE % 128 == 0, "stage size keeps the tiles 128-byte aligned");
 
-    const int tid = threadIdx.x, lpr = p.lpr, C = p.C;
-    const int row0 = blockIdx.x * p.TR;
+__device__ __forceinline__ void sp_bulk(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void sp_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+}
+
+__device__ __forceinline__ void sp_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 sp_lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int sp_lds32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// one tile's copies (or, with bar == 0, their L2 prefetch two tiles ahead: one stage pair holds 2 x 95 KB, which is
+// not enough bytes in flight per SM to cover the HBM latency; the prefetch makes the real copies L2 hits)
+__device__ __forceinline__ void sp_issue_tile(const TileParams &p, int tile, unsigned char *st, uint32_t bar) {
+    const int C = p.C;
+    const int row0 = tile * p.TR;
     const int rows = min(p.TR, p.M - row0);
     const int b0 = row0 >> 2, nb = (rows + 3) >> 2;
-    if (tid == 0) {
-        const int e0 = p.bptr[b0], e1 = p.bptr[b0 + nb];
-        s_e0 = e0;
-        s_ne = e1 - e0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t xb = (uint32_t)rows * (uint32_t)C * 4u;
-        const bool staged = e1 - e0 <= ST_EMAX;
-        const int a0 = e0 & ~3;                                   // 16-byte aligned start of the column run
-        const uint32_t cb = staged ? (uint32_t)(((e1 - a0) + 3) & ~3) * 4u : 0u;
-        const uint32_t wb = staged ? (uint32_t)(e1 - e0) * 16u : 0u;
-        const uint32_t total = xb + (p.X0 != nullptr ? xb : 0u) + cb + wb;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem(bar)), "r"(total) : "memory");
-        const uint32_t mb = st_smem(bar);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(x1t)),
-                     "l"(p.X1 + (size_t)row0 * C), "r"(xb), "r"(mb)
-                     : "memory");
-        if (p.X0 != nullptr)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(x0t)),
-                         "l"(p.X0 + (size_t)row0 * C), "r"(xb), "r"(mb)
-                         : "memory");
-        if (wb != 0u)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(wt)),
-                         "l"(p.bw + e0), "r"(wb), "r"(mb)
-                         : "memory");
-        if (cb != 0u)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(ct)),
-                         "l"(p.bcol + a0), "r"(cb), "r"(mb)
-                         : "memory");
+    const int e0 = p.bps[2 * b0], e1 = p.bps[2 * (b0 + nb)];
+    const bool staged = e1 - e0 <= SP_EMAX;
+    const uint32_t xb = (uint32_t)rows * (uint32_t)C * 4u;
+    const uint32_t x1b = (uint32_t)min(p.TR, p.Mx - row0) * (uint32_t)C * 4u;      // the whole window of X1: near entries may name rows >= M
+    const int a0 = e0 & ~3, pa0 = (2 * b0) & ~3;      // 16-byte aligned starts of the column and pointer runs
+    const uint32_t cb = staged ? (uint32_t)(((e1 - a0) + 3) & ~3) * 4u : 0u;
+    const uint32_t wb = staged ? (uint32_t)(e1 - e0) * 16u : 0u;
+    const uint32_t pb = (uint32_t)(((2 * (b0 + nb) + 1 - pa0) + 3) & ~3) * 4u;
+    if (bar == 0u) {
+        sp_prefetch_l2(p.X1 + (size_t)row0 * C, x1b);
+        if (p.X0 != nullptr) sp_prefetch_l2(p.X0 + (size_t)row0 * C, xb);
+        if (wb != 0u) sp_prefetch_l2(p.bw + e0, wb);
+        if (cb != 0u) sp_prefetch_l2(p.bcol + a0, cb);
+        return;
     }
-    __syncthreads();
-    const int e0 = s_e0, ne = s_ne;
-    const bool staged = ne <= ST_EMAX;
-    const int lane = tid % lpr, bl = tid / lpr;          // block of the tile, lane inside the row
-    const bool active = bl < nb && lane * 4 < C;
-    int beg = 0, end = 0;
-    if (active) {                                         // overlaps the copies
-        beg = p.bptr[b0 + bl] - e0;
-        end = p.bptr[b0 + bl + 1] - e0;
-    }
-    {   // wait for the tile
-        uint32_t done = 0;
-        while (!done)
-            asm volatile(
-                "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
-                : "=r"(done)
-                : "r"(st_smem(bar))
-                : "memory");
-    }
-    if (!active) return;
-    const int c = lane * 4;
-    const int coff = e0 & 3;                              // the staged column run starts at the aligned entry
-    const int *cols = staged ? ct + coff : p.bcol + e0;
-    const float4 *ws = staged ? wt : p.bw + e0;
-    const float *x1g = p.X1 + c;
-    const float *x1s = x1t + c;
-    float4 acc[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int *hdr = reinterpret_cast<int *>(st + SP_OFF_H);
+    hdr[0] = e0;
+    hdr[1] = e1 - e0;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"(x1b + (p.X0 != nullptr ? xb : 0u) + cb + wb + pb)
+                 : "memory");
+    sp_bulk(st_smem(st), p.X1 + (size_t)row0 * C, x1b, bar);
+    if (p.X0 != nullptr) sp_bulk(st_smem(st + SP_OFF_X0), p.X0 + (size_t)row0 * C, xb, bar);
+    sp_bulk(st_smem(st + SP_OFF_P), p.bps + pa0, pb, bar);
+    if (wb != 0u) sp_bulk(st_smem(st + SP_OFF_W), p.bw + e0, wb, bar);
+    if (cb != 0u) sp_bulk(st_smem(st + SP_OFF_C), p.bcol + a0, cb, bar);
+}
+
+// STAGED: the tile's entries are in shared memory (else, more than SP_EMAX of them: read from global memory).
+// `st` points into the kernel's shared-memory array (plain loads: after inlining the compiler emits LDS and batches them).
+// One walk over the block's entries in stored order, four gathers in flight; an entry whose row lies in the tile is read
+// from the staged X1 rows, any other from L1 / L2.
+template <bool STAGED>
+__device__ __forceinline__ void sp_block(const TileParams &p, const unsigned char *st, int row0, int rows1, int e0, int beg,
+                                         int end, int c, float4 (&acc)[4]) {
+    const int *cols = STAGED ? reinterpret_cast<const int *>(st + SP_OFF_C) + (e0 & 3) : p.bcol + e0;
+    const float4 *ws = STAGED ? reinterpret_cast<const float4 *>(st + SP_OFF_W) : p.bw + e0;
+    // ONE generic load per entry and no branch: the BASE is selected (a warp holds two row blocks whose entries fall
+    // inside / outside the tile independently), the index is the global row for both -- the shared-memory base is
+    // pre-shifted by row0 rows.  Plain 64-bit integer arithmetic: 5 instructions per address.
+    const uint32_t rowb = 4u * (uint32_t)p.C;
+    const uint64_t gb = (uint64_t)(uintptr_t)(p.X1 + c);
+    const uint64_t sb = (uint64_t)(uintptr_t)(reinterpret_cast<const float *>(st) + c) - (uint64_t)(uint32_t)row0 * rowb;
+    auto gather = [&](int cc) {
+        const uint64_t base = (unsigned)(cc - row0) < (unsigned)rows1 ? sb : gb;
+        return *reinterpret_cast<const float4 *>((uintptr_t)(base + (uint64_t)(uint32_t)cc * rowb));
+    };
     constexpr int U = 4;
     int e = beg;
     for (; e + U - 1 < end; e += U) {
@@ -263,13 +282,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_spmm_tile(const TileParams p)
             ww[u] = ws[e + u];
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned rel = (unsigned)(cc[u] - row0);
-            if (rel < (unsigned)rows)
-                xx[u] = *reinterpret_cast<const float4 *>(x1s + (size_t)rel * C);
-            else
-                xx[u] = *reinterpret_cast<const float4 *>(x1g + (size_t)cc[u] * C);
-        }
+        for (int u = 0; u < U; ++u) xx[u] = gather(cc[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             fma_acc(acc[0], ww[u].x, xx[u]);
@@ -279,29 +292,94 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_spmm_tile(const TileParams p)
         }
     }
     for (; e < end; ++e) {
-        const int cc = cols[e];
         const float4 w = ws[e];
-        const unsigned rel = (unsigned)(cc - row0);
-        const float4 x = rel < (unsigned)rows ? *reinterpret_cast<const float4 *>(x1s + (size_t)rel * C)
-                                               : *reinterpret_cast<const float4 *>(x1g + (size_t)cc * C);
+        const float4 x = gather(cols[e]);
         fma_acc(acc[0], w.x, x);
         fma_acc(acc[1], w.y, x);
         fma_acc(acc[2], w.z, x);
         fma_acc(acc[3], w.w, x);
     }
-    const int nrow = min(4, rows - 4 * bl);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (r >= nrow) break;
-        const int lr = 4 * bl + r;
-        float4 v;
-        if (p.X0 != nullptr) {
-            const float4 old = *reinterpret_cast<const float4 *>(x0t + (size_t)lr * C + c);
-            v = axmb(p.alpha, acc[r], old);
-        } else {
-            v = scale(p.alpha, acc[r]);
+}
+
+__global__ void __launch_bounds__(ST_THREADS + 32, 1) k_spmm_tile_p(const TileParams p, int ntiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * SP_STAGE);      // full[2], empty[2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lpr = p.lpr, C = p.C;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(bars + i)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem(bars + 2 + i)), "r"(ST_THREADS / 32) : "memory");
         }
-        *reinterpret_cast<float4 *>(p.out + (size_t)(row0 + lr) * C + c) = v;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t full0 = st_smem(bars), empty0 = st_smem(bars + 2);
+
+    if (warp == ST_THREADS / 32) {
+        // =========================== producer warp =====================================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it & 1;
+                if (p.flags & 1) {
+                    if (it == 0 && tile + (int)gridDim.x < ntiles) sp_issue_tile(p, tile + gridDim.x, nullptr, 0u);
+                    if (tile + 2 * (int)gridDim.x < ntiles) sp_issue_tile(p, tile + 2 * gridDim.x, nullptr, 0u);      // L2 prefetch
+                }
+                if (it >= 2) sp_wait(empty0 + 8u * s, (uint32_t)(((it >> 1) - 1) & 1));
+                sp_issue_tile(p, tile, smem + (size_t)s * SP_STAGE, full0 + 8u * s);
+            }
+        }
+        return;
+    }
+    // =========================== compute warps =========================================
+    const int ln = tid % lpr, bl = tid / lpr;
+    const int c = ln * 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        unsigned char *st = smem + (size_t)s * SP_STAGE;
+        const int row0 = tile * p.TR;
+        const int rows = min(p.TR, p.M - row0);
+        const int b0 = row0 >> 2, nb = (rows + 3) >> 2;
+        if (p.flags & 2) {
+            if (lane == 0) sp_wait(full0 + 8u * s, (uint32_t)((it >> 1) & 1));      // one polling lane per warp
+            __syncwarp();
+        } else {
+            sp_wait(full0 + 8u * s, (uint32_t)((it >> 1) & 1));
+        }
+        const int *hdr = reinterpret_cast<const int *>(st + SP_OFF_H);
+        const int e0 = hdr[0], ne = hdr[1];
+        if (bl < nb && c < C) {
+            const int *pt = reinterpret_cast<const int *>(st + SP_OFF_P) + ((2 * b0) & 3) + 2 * bl;
+            const int beg = pt[0] - e0, end = pt[2] - e0;
+            const int rows1 = min(p.TR, p.Mx - row0);       // rows of X1 staged (>= rows)
+            float4 acc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ne <= SP_EMAX)
+                sp_block<true>(p, st, row0, rows1, e0, beg, end, c, acc);
+            else
+                sp_block<false>(p, st, row0, rows1, e0, beg, end, c, acc);
+            const int nrow = min(4, rows - 4 * bl);
+            const float *x0t = reinterpret_cast<const float *>(st + SP_OFF_X0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r >= nrow) break;
+                const int lr = 4 * bl + r;
+                float4 v;
+                if (p.X0 != nullptr) {
+                    const float4 old = *reinterpret_cast<const float4 *>(x0t + (size_t)lr * C + c);
+                    v = axmb(p.alpha, acc[r], old);
+                } else {
+                    v = scale(p.alpha, acc[r]);
+                }
+                *reinterpret_cast<float4 *>(p.out + (size_t)(row0 + lr) * C + c) = v;
+            }
+        }
+        // this warp has finished reading the stage
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * s) : "memory");
     }
 }
 
@@ -312,7 +390,7 @@ static bool step_blocked(const CgCsr &L, int64_t nnz_hint) {
     return (int64_t)L.blk_total * 10 <= nnz_hint * 7;
 }
 
-static int launch_step(const CgCsr &L, int64_t nnz, int M, const float *X1, const float *X0, float *out, int64_t C,
+static int launch_step(const CgCsr &L, int64_t nnz, int Mx, int M, const float *X1, const float *X0, float *out, int64_t C,
                        float alpha, cudaStream_t s) {
     const bool vec4 = (C % 4 == 0) && ((((uintptr_t)X1 | (uintptr_t)out | (uintptr_t)X0) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
@@ -320,29 +398,41 @@ static int launch_step(const CgCsr &L, int64_t nnz, int M, const float *X1, cons
     int lpr = 32;
     while (lpr > 1 && lpr / 2 >= lanes_needed) lpr /= 2;
     CgProfScope prof("spmm_step", s);
-    if (vec4 && step_blocked(L, nnz) && lanes_needed <= 32 && (int64_t)M * C < ((int64_t)1 << 31)) {
-        // tiled form (see k_spmm_tile); CG_SPMM_TILE=0 keeps the register-path block kernel
+    if (vec4 && step_blocked(L, nnz) && lanes_needed >= 4 && lanes_needed <= 32 && (int64_t)M * C < ((int64_t)1 << 31)) {
+        // (16 <= C <= 128: at most 128 row blocks per tile, whole rows in one contiguous X tile)
+        // tiled form (k_spmm_tile_p); CG_SPMM_TILE=0 keeps the register-path block kernel
         const char *env = getenv("CG_SPMM_TILE");
         if (env == nullptr || atoi(env) != 0) {
             TileParams tp;
-            tp.bptr = L.blk_ptr;
+            tp.bps = L.blk_ps;
             tp.bcol = L.blk_col;
             tp.bw = L.blk_w;
             tp.X1 = X1;
             tp.X0 = X0;
             tp.out = out;
+            {
+                const char *pf = getenv("CG_SPMM_PREFETCH");
+                tp.flags = (pf != nullptr && atoi(pf) != 0) ? 1 : 0;      // L2 prefetch two tiles ahead: measured slower (11.6 vs 11.0 ms per 38 steps), off by default
+                const char *pl = getenv("CG_SPMM_POLL1");
+                if (pl != nullptr && atoi(pl) != 0) tp.flags |= 2;
+            }
             tp.M = M;
+            tp.Mx = Mx;
             tp.C = (int)C;
             tp.lpr = lpr;
             tp.TR = 4 * (ST_THREADS / lpr);
             tp.alpha = alpha;
-            const size_t smem = 2 * (size_t)ST_TILE_BYTES + (size_t)ST_EMAX * 16 + (size_t)(ST_EMAX + 8) * 4 + 16;
-            static bool attr_set = false;
-            if (!attr_set) {
-                CG_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+            const int ntiles = (int)cg_ceil_div(M, tp.TR);
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const size_t smem_p = 2 * (size_t)SP_STAGE + 64;
+            static bool attr_p = false;
+            if (!attr_p) {
+                CG_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_tile_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                attr_p = true;
             }
-            k_spmm_tile<<<(unsigned)cg_ceil_div(M, tp.TR), ST_THREADS, smem, s>>>(tp);
+            k_spmm_tile_p<<<(unsigned)std::min(ntiles, sms), ST_THREADS + 32, smem_p, s>>>(tp, ntiles);
             CG_LAUNCH_CHECK();
             return CG_OK;
         }
@@ -661,7 +751,7 @@ static int run_basis_from(const cg_graph *g, int transpose, const float *in, flo
     for (int k = 1; k < K; ++k) {
         const float *x1 = stack + (int64_t)(k - 1) * slab;
         const float *x0 = k > 1 ? stack + (int64_t)(k - 2) * slab : nullptr;
-        int rc = launch_step(L, g->nnz, M, x1, x0, stack + (int64_t)k * slab, C, k > 1 ? 2.0f : 1.0f, s);
+        int rc = launch_step(L, g->nnz, g->M, M, x1, x0, stack + (int64_t)k * slab, C, k > 1 ? 2.0f : 1.0f, s);
         if (rc != CG_OK) return rc;
     }
     return CG_OK;
@@ -686,5 +776,5 @@ extern "C" int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev
     CG_REQUIRE(g && dev_X1 && dev_out, "cg_cheb_step: NULL argument");
     CG_REQUIRE(C > 0 && rows >= 0 && rows <= g->M, "cg_cheb_step: bad C / rows (C=%lld rows=%d M=%d)", (long long)C, rows, g->M);
     if (rows == 0) return CG_OK;
-    return launch_step(cg_side(g, transpose), g->nnz, rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
+    return launch_step(cg_side(g, transpose), g->nnz, g->M, rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
 }
