@@ -491,24 +491,16 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                 umma::fence_after_sync();
                 const uint32_t gb = gbuf0 + (uint32_t)(k & 1) * p.slab_bytes;
                 constexpr int nc8 = Fi / 8;
-                for (int t = 0; t < p.tiles; t += 2) {      // two row tiles per wait: the TMEM loads overlap
-                    const bool two = t + 1 < p.tiles;
+                for (int t = 0; t < p.tiles; ++t) {
+                    const int r = t * 128 + 32 * q + lane;
                     for (int c = sub; c < nc8; c += 4) {
-                        float v0[8], v1[8];
-                        const uint32_t ta = tmem + lane_base + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi + c * 8);
-                        umma::tmem_ld8(ta, v0);
-                        if (two) umma::tmem_ld8(ta + (uint32_t)Fi, v1);
+                        float v[8];
+                        umma::tmem_ld8(tmem + lane_base + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi + c * 8), v);
                         umma::tmem_ld_wait();
-                        const int ra = t * 128 + 32 * q + lane, rb = ra + 128;
-                        if (ra < Rg) {
-                            const uint32_t row = gb + 4u * (uint32_t)(ra * Fi);
-                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)ra & SWZ)), make_float4(v0[0], v0[1], v0[2], v0[3]));
-                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)ra & SWZ)), make_float4(v0[4], v0[5], v0[6], v0[7]));
-                        }
-                        if (two && rb < Rg) {
-                            const uint32_t row = gb + 4u * (uint32_t)(rb * Fi);
-                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)rb & SWZ)), make_float4(v1[0], v1[1], v1[2], v1[3]));
-                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)rb & SWZ)), make_float4(v1[4], v1[5], v1[6], v1[7]));
+                        if (r < Rg) {
+                            const uint32_t row = gb + 4u * (uint32_t)(r * Fi);
+                            sts128(row + 16u * ((uint32_t)(2 * c) ^ ((uint32_t)r & SWZ)), make_float4(v[0], v[1], v[2], v[3]));
+                            sts128(row + 16u * ((uint32_t)(2 * c + 1) ^ ((uint32_t)r & SWZ)), make_float4(v[4], v[5], v[6], v[7]));
                         }
                     }
                 }

@@ -207,5 +207,10 @@ bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,
                     void *workspace, cudaStream_t s);
 
+// SMs the persistent kernels may occupy: all of them minus CG_SM_RESERVE (environment; default 0).  Data-parallel runs
+// reserve a few SMs so that NCCL's all-reduce kernels can start while a persistent backward kernel is resident
+// (one CTA per SM with ~200 KB of shared memory leaves no room for another CTA).
+int cg_sm_budget(int device);
+
 static inline int64_t cg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -610,3 +610,108 @@ extern "C" int cg_lstm_gates_bwd(const float *pre, const float *bias, const floa
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Loss + optimiser tail of cgcnn (lib/graph_model.py:246-310): softmax cross-entropy with its
+// gradient in one launch, momentum SGD over every variable in one launch.
+// ---------------------------------------------------------------------------------------------------------------
+// loss = mean_n ( logsumexp(z_n) - z_n[y_n] ),  dz[n, c] = (softmax(z_n)[c] - [c == y_n]) / N.  One block: a thread owns
+// whole rows (C is the class count: 3 .. 20 here), partial losses are summed in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) k_softmax_xent(const float *__restrict__ z, const long long *__restrict__ y,
+                                                       float *__restrict__ loss, float *__restrict__ dz, int N, int C) {
+    __shared__ float red[32];
+    float part = 0.f;
+    const float invN = 1.f / (float)N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float *row = z + (size_t)n * C;
+        float mx = row[0];
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+        const int label = (int)y[n];
+        const float lse = logf(sum) + mx;
+        if (label >= 0 && label < C) part += lse - row[label];
+        const float inv = 1.f / sum;
+        float *drow = dz + (size_t)n * C;
+        for (int c = 0; c < C; ++c) drow[c] = (expf(row[c] - mx) * inv - (c == label ? 1.f : 0.f)) * invN;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *loss = v * invN;
+    }
+}
+
+extern "C" int cg_softmax_xent(const float *dev_logits, const long long *dev_labels, float *dev_loss, float *dev_dlogits, int N,
+                               int C, void *stream) {
+    CG_REQUIRE(dev_logits && dev_labels && dev_loss && dev_dlogits, "cg_softmax_xent: NULL tensor");
+    CG_REQUIRE(N > 0 && C > 0 && C <= 4096, "cg_softmax_xent: bad shape N=%d C=%d", N, C);
+    CgProfScope prof("softmax_xent", (cudaStream_t)stream);
+    k_softmax_xent<<<1, 1024, 0, (cudaStream_t)stream>>>(dev_logits, dev_labels, dev_loss, dev_dlogits, N, C);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// table[t] = {param, grad, momentum buffer, element count}; buf = momentum * buf + grad; param -= lr * buf
+// (torch.optim.SGD / tf.train.MomentumOptimizer without Nesterov; a zero buffer makes the first step buf = grad).
+struct CgSgdEntry {
+    float *p;
+    const float *g;
+    float *buf;
+    long long n;
+};
+
+constexpr int CG_SGD_MAX = 64;      // records per launch: they travel as kernel arguments (2 KB), so a captured CUDA graph
+struct CgSgdTable {                 // replays them without any device-side table to keep up to date
+    CgSgdEntry e[CG_SGD_MAX];
+};
+
+__global__ void __launch_bounds__(256) k_sgd_momentum(const __grid_constant__ CgSgdTable table, float lr, float momentum) {
+    const CgSgdEntry e = table.e[blockIdx.y];
+    const long long n4 = ((((uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.buf) & 15) == 0) ? e.n / 4 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 g = reinterpret_cast<const float4 *>(e.g)[i];
+        float4 b = reinterpret_cast<float4 *>(e.buf)[i], w = reinterpret_cast<float4 *>(e.p)[i];
+        b.x = fmaf(momentum, b.x, g.x);
+        b.y = fmaf(momentum, b.y, g.y);
+        b.z = fmaf(momentum, b.z, g.z);
+        b.w = fmaf(momentum, b.w, g.w);
+        w.x = fmaf(-lr, b.x, w.x);
+        w.y = fmaf(-lr, b.y, w.y);
+        w.z = fmaf(-lr, b.z, w.z);
+        w.w = fmaf(-lr, b.w, w.w);
+        reinterpret_cast<float4 *>(e.buf)[i] = b;
+        reinterpret_cast<float4 *>(e.p)[i] = w;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += stride) {
+        const float b = fmaf(momentum, e.buf[i], e.g[i]);
+        e.buf[i] = b;
+        e.p[i] = fmaf(-lr, b, e.p[i]);
+    }
+}
+
+extern "C" int cg_sgd_momentum(const void *host_table, int ntensors, long long max_numel, float lr, float momentum, void *stream) {
+    CG_REQUIRE(host_table != nullptr && ntensors > 0, "cg_sgd_momentum: bad table (%d tensors)", ntensors);
+    long long blocks = cg_ceil_div(cg_ceil_div(max_numel, 4), 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;       // 4 x 148: the large fc weight streams at full rate, small tensors take one block
+    const CgSgdEntry *src = reinterpret_cast<const CgSgdEntry *>(host_table);
+    for (int t0 = 0; t0 < ntensors; t0 += CG_SGD_MAX) {
+        const int n = ntensors - t0 < CG_SGD_MAX ? ntensors - t0 : CG_SGD_MAX;
+        CgSgdTable tab;
+        memset(&tab, 0, sizeof(tab));
+        for (int i = 0; i < n; ++i) {
+            tab.e[i] = src[t0 + i];
+            CG_REQUIRE(tab.e[i].p && tab.e[i].g && tab.e[i].buf && tab.e[i].n >= 0, "cg_sgd_momentum: NULL tensor in record %d", t0 + i);
+        }
+        CgProfScope prof("sgd_momentum", (cudaStream_t)stream);
+        k_sgd_momentum<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(tab, lr, momentum);
+        CG_LAUNCH_CHECK();
+    }
+    return CG_OK;
+}

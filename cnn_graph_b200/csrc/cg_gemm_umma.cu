@@ -297,7 +297,7 @@ static GPlan gemm_plan(int M, int N, int K, int sm_count) {
 extern "C" size_t cg_gemm_f32_workspace_bytes(int M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaGetDevice(&dev) == cudaSuccess) sms = cg_sm_budget(dev);
     return std::max(gemm_plan(M, N, K, sms).ws, cg_gemm_pipe_workspace(M, N, K, sms));
 }
 
@@ -321,7 +321,7 @@ int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, i
     CG_REQUIRE(!(a_kblk > 0 && transA) && !(b_kblk > 0 && transB), "cg_gemm_f32: K blocking needs the untransposed operand");
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms = cg_sm_budget(dev);
     if (cg_gemm_pipe_eligible(A, B, M, N, K, lda, ldb, transA, transB, a_kblk, a_kbs, b_kblk))
         return cg_run_gemm_pipe(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, a_kblk, a_kbs, b_kblk, b_shi,
                                 b_slo, workspace, workspace_bytes, sms, s);
@@ -382,7 +382,7 @@ int cg_run_gemm_mblocked(const float *A, const float *B, float *C, int M, int N,
     CG_REQUIRE(cg_gemm_mblocked_ok(A, B, M, N, K, lda, ldb, a_mblk, a_mbs), "cg_run_gemm_mblocked: operands not eligible");
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms = cg_sm_budget(dev);
     return cg_run_gemm_pipe(A, B, C, M, N, K, 1, 0, lda, ldb, ldc, nullptr, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes, sms, s,
                             a_mblk, a_mbs);
 }

@@ -19,6 +19,17 @@ void cg_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *cg_last_error(void) { return g_err; }
+
+int cg_sm_budget(int device) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    if (v <= 0) v = 148;
+    if (const char *env = getenv("CG_SM_RESERVE")) {
+        const int r = atoi(env);
+        if (r > 0 && r < v) v -= r;
+    }
+    return v;
+}
 extern "C" int cg_abi_version(void) { return CG_ABI_VERSION; }
 
 // ELL budget: the on-chip kernels keep one orientation's ELL plus two signal
@@ -207,8 +218,7 @@ extern "C" int cg_graph_create(cg_graph_t **out, int M, int64_t nnz, const int32
         return CG_ERR_CUDA;
     }
     int v = 0;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g->device);
-    g->sm_count = v > 0 ? v : 148;
+    g->sm_count = cg_sm_budget(g->device);
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device);
     g->smem_optin = (size_t)v;
     int rc = upload_side(g->fwd, M, nnz, rowptr, col, val, onchip);

@@ -425,7 +425,7 @@ static int launch_step(const CgCsr &L, int64_t nnz, int Mx, int M, const float *
             const int ntiles = (int)cg_ceil_div(M, tp.TR);
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            sms = cg_sm_budget(dev);
             const size_t smem_p = 2 * (size_t)SP_STAGE + 64;
             static bool attr_p = false;
             if (!attr_p) {

@@ -261,8 +261,11 @@ class cgcnn(GraphConvOps, GraphModel):
         return torch.int64
 
     def _make_optimizer(self):
-        # upstream cgcnn: momentum SGD (plain SGD when momentum == 0)
-        return torch.optim.SGD(self.store.parameters(), lr=self.learning_rate, momentum=self.momentum)
+        # upstream cgcnn: momentum SGD (plain SGD when momentum == 0); on the GPU the whole update is one native launch
+        params = list(self.store.parameters())
+        if params and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            return ops.NativeMomentumSGD(params, lr=self.learning_rate, momentum=self.momentum)
+        return torch.optim.SGD(params, lr=self.learning_rate, momentum=self.momentum)
 
     def _inference(self, x, dropout):
         """x [N, M] -> logits [N, M[-1]]: (filter, brelu, pool) per layer on L[i], flatten,
@@ -318,7 +321,10 @@ class cgcnn(GraphConvOps, GraphModel):
 
     def loss(self, logits, labels, regularization):
         """softmax cross-entropy + L2 on the regularised variables (upstream cgcnn loss)."""
-        ce = torch.nn.functional.cross_entropy(logits, labels)
+        if logits.is_cuda and logits.dim() == 2 and logits.shape[1] <= 4096:
+            ce = ops.softmax_xent(logits, labels)         # loss and its gradient in one native launch
+        else:
+            ce = torch.nn.functional.cross_entropy(logits, labels)
         if regularization and self.regularizers:
             ce = ce + regularization * l2_loss_sum(self.regularizers)
         return ce

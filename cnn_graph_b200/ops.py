@@ -705,3 +705,64 @@ def lstm_gates(pre, bias, c, variant='fork'):
     if pre.is_meta:
         return c.new_empty(c.shape), c.new_empty(c.shape)
     return LstmGatesFn.apply(pre, bias, c, v)
+
+
+# ---------------------------------------------------------------------------------------
+# loss + optimiser tail (native: one launch each)
+# ---------------------------------------------------------------------------------------
+
+class SoftmaxXentFn(torch.autograd.Function):
+    """mean softmax cross-entropy of logits [N, C] against int64 labels [N] (lib/graph_model.py:250-252); the forward
+    launch also leaves the gradient (softmax - onehot) / N behind."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _require_cuda(logits, labels)
+        logits = _f32c(logits)
+        labels = labels.to(torch.int64).contiguous()
+        N, C = logits.shape
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dz = torch.empty_like(logits)
+        check(_native.lib().cg_softmax_xent(ptr(logits), ptr(labels), ptr(loss), ptr(dz), N, C, _stream()), 'cg_softmax_xent')
+        ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return dz * g, None
+
+
+def softmax_xent(logits, labels):
+    return SoftmaxXentFn.apply(logits, labels)
+
+
+class NativeMomentumSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(momentum) semantics with the whole update in ONE native launch (cg_sgd_momentum): the
+    {param, grad, momentum buffer, numel} records travel as kernel arguments, so a captured CUDA graph replays the
+    addresses it was captured with (its private pool keeps them alive).  Gradients are read where autograd left them."""
+
+    def __init__(self, params, lr, momentum=0.0):
+        super().__init__(params, dict(lr=lr, momentum=momentum))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.grad is not None]
+            if not ps:
+                continue
+            rec = []
+            for p in ps:
+                st = self.state[p]
+                if 'momentum_buffer' not in st or st['momentum_buffer'] is None:
+                    st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError('NativeMomentumSGD: fp32 contiguous variables only')
+                rec += [p.data_ptr(), p.grad.data_ptr(), st['momentum_buffer'].data_ptr(), p.numel()]
+            table = np.array(rec, dtype=np.int64)
+            check(_native.lib().cg_sgd_momentum(table.ctypes.data, len(ps), max(p.numel() for p in ps),
+                                                ctypes.c_float(group['lr']), ctypes.c_float(group['momentum']), _stream()),
+                  'cg_sgd_momentum')
+        return None

@@ -258,6 +258,18 @@ int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, i
 /* A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A operand): dev_A [128][Kd], dev_B [N][Kd]. */
 int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, void *stream);
 
+/* ---- loss + optimiser tail of cgcnn (lib/graph_model.py:246-310, upstream cgcnn.loss / training) ----------------- */
+/* Softmax cross-entropy averaged over the batch AND its gradient in one launch: dev_logits [N][C] fp32, dev_labels [N]
+ * int64 -> *dev_loss (scalar) and dev_dlogits [N][C] = (softmax - onehot) / N (tf.nn.sparse_softmax_cross_entropy_with_logits
+ * + tf.reduce_mean, lib/graph_model.py:250-252).  Deterministic (fixed summation order).                               */
+int cg_softmax_xent(const float *dev_logits, const long long *dev_labels, float *dev_loss, float *dev_dlogits, int N, int C,
+                    void *stream);
+/* Momentum SGD on every variable in one launch (tf.train.MomentumOptimizer, lib/graph_model.py:291-295):
+ * host_table: ntensors records {float *param; const float *grad; float *momentum_buffer; int64 numel} (32 bytes each, HOST
+ * memory, device pointers inside; they travel as kernel arguments, 64 per launch); buffer = momentum * buffer + grad;
+ * param -= lr * buffer.  max_numel sizes the grid.                                                                     */
+int cg_sgd_momentum(const void *host_table, int ntensors, long long max_numel, float lr, float momentum, void *stream);
+
 /* Debug aids of the fused recurrence kernels.  cg_debug_fused_trace: device buffer [K][10] of int64 that receives
  * clock64 stamps of CTA 0's second group (NULL switches it off).  cg_debug_fused_plan_info: the plan of the most
  * recent fused forward ([0..3]) and Clenshaw ([4..7]) launch: {row-block gather used, samples per group, items per
