@@ -77,7 +77,7 @@ def run_ours(args, config):
     L = workloads.knn_graph_laplacian(args.log2m, 16, args.order)
     Lr = ops.rescale_csr(L, 2)
     t_build = time.time() - t0
-    pf = partition.PartitionedFilter(Lr, K)
+    pf = partition.PartitionedFilter(Lr, K, exchange=os.environ.get('CG_C5_EXCHANGE', 'peer'))
     part = pf.part
     gen = torch.Generator().manual_seed(7)
     x_host = torch.randn(M, F, generator=gen)[part.r0:part.r1].contiguous().pin_memory()

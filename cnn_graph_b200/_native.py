@@ -30,6 +30,9 @@ _SIGNATURES = {
     'cg_graph_info': (c_int, [c_void_p, ctypes.POINTER(c_i64)]),
     'cg_cheb_basis': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     'cg_cheb_step': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_float, c_void_p]),
+    'cg_cheb_step_tile_rows': (c_int, [c_void_p, c_int, c_i64]),
+    'cg_cheb_step_tiles': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_float, c_void_p, c_int, c_void_p]),
+    'cg_halo_pull': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p]),
     'cg_cheb_filter_fwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     'cg_cheb_filter_bwd_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     'cg_cheb_filter_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -173,6 +173,7 @@ struct TileParams {
     const float4 *bw;
     const float *X1, *X0;
     float *out;
+    const int *tiles;            // optional: the tiles to process (row-partitioned runs do interior and boundary tiles apart)
     int flags;                   // bit 0: L2 prefetch two tiles ahead
     int M, Mx, C, lpr, TR;       // M rows to compute; Mx >= M rows of X1 exist (row partition: halo rows follow the local ones)
     float alpha;
@@ -320,9 +321,10 @@ __global__ void __launch_bounds__(ST_THREADS + 32, 1) k_spmm_tile_p(const TilePa
         // =========================== producer warp =====================================
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+                const int tile = p.tiles != nullptr ? p.tiles[ti] : ti;
                 const int s = it & 1;
-                if (p.flags & 1) {
+                if ((p.flags & 1) && p.tiles == nullptr) {
                     if (it == 0 && tile + (int)gridDim.x < ntiles) sp_issue_tile(p, tile + gridDim.x, nullptr, 0u);
                     if (tile + 2 * (int)gridDim.x < ntiles) sp_issue_tile(p, tile + 2 * gridDim.x, nullptr, 0u);      // L2 prefetch
                 }
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(ST_THREADS + 32, 1) k_spmm_tile_p(const TilePa
     const int ln = tid % lpr, bl = tid / lpr;
     const int c = ln * 4;
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+        const int tile = p.tiles != nullptr ? p.tiles[ti] : ti;
         const int s = it & 1;
         unsigned char *st = smem + (size_t)s * SP_STAGE;
         const int row0 = tile * p.TR;
@@ -390,8 +393,18 @@ static bool step_blocked(const CgCsr &L, int64_t nnz_hint) {
     return (int64_t)L.blk_total * 10 <= nnz_hint * 7;
 }
 
+// rows of one tile of the tiled step for slabs of C columns on this operator side; 0 when the tiled form does not apply
+static int step_tile_rows(const CgCsr &L, int64_t nnz, int64_t C) {
+    if (C % 4 != 0 || C / 4 < 4 || C / 4 > 32 || !step_blocked(L, nnz)) return 0;
+    if (const char *env = getenv("CG_SPMM_TILE"))
+        if (atoi(env) == 0) return 0;
+    int lpr = 32;
+    while (lpr > 1 && lpr / 2 >= C / 4) lpr /= 2;
+    return 4 * (ST_THREADS / lpr);
+}
+
 static int launch_step(const CgCsr &L, int64_t nnz, int Mx, int M, const float *X1, const float *X0, float *out, int64_t C,
-                       float alpha, cudaStream_t s) {
+                       float alpha, cudaStream_t s, const int *tiles = nullptr, int ntiles_list = 0) {
     const bool vec4 = (C % 4 == 0) && ((((uintptr_t)X1 | (uintptr_t)out | (uintptr_t)X0) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     int64_t lanes_needed = cg_ceil_div(C, vec);
@@ -422,7 +435,9 @@ static int launch_step(const CgCsr &L, int64_t nnz, int Mx, int M, const float *
             tp.lpr = lpr;
             tp.TR = 4 * (ST_THREADS / lpr);
             tp.alpha = alpha;
-            const int ntiles = (int)cg_ceil_div(M, tp.TR);
+            tp.tiles = tiles;
+            const int ntiles = tiles != nullptr ? ntiles_list : (int)cg_ceil_div(M, tp.TR);
+            if (ntiles == 0) return CG_OK;
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             sms = cg_sm_budget(dev);
@@ -437,6 +452,7 @@ static int launch_step(const CgCsr &L, int64_t nnz, int Mx, int M, const float *
             return CG_OK;
         }
     }
+    CG_REQUIRE(tiles == nullptr, "spmm_step: a tile list needs the tiled step (16 <= C <= 128, C %% 4 == 0, aligned slabs, a local operator)");
     if (vec4 && step_blocked(L, nnz)) {
         const int blocks_per_cta = 256 / lpr;
         dim3 grid((unsigned)cg_ceil_div(cg_ceil_div(M, 4), blocks_per_cta), (unsigned)cg_ceil_div(lanes_needed, lpr));
@@ -777,4 +793,52 @@ extern "C" int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev
     CG_REQUIRE(C > 0 && rows >= 0 && rows <= g->M, "cg_cheb_step: bad C / rows (C=%lld rows=%d M=%d)", (long long)C, rows, g->M);
     if (rows == 0) return CG_OK;
     return launch_step(cg_side(g, transpose), g->nnz, g->M, rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int cg_cheb_step_tile_rows(const cg_graph_t *g, int transpose, int64_t C) {
+    if (g == nullptr || C <= 0) return 0;
+    return step_tile_rows(cg_side(g, transpose), g->nnz, C);
+}
+
+extern "C" int cg_cheb_step_tiles(const cg_graph_t *g, int transpose, const float *dev_X1, const float *dev_X0, float *dev_out,
+                                  int rows, int64_t C, float alpha, const int32_t *dev_tiles, int ntiles, void *stream) {
+    CG_REQUIRE(g && dev_X1 && dev_out && dev_tiles, "cg_cheb_step_tiles: NULL argument");
+    CG_REQUIRE(C > 0 && rows >= 0 && rows <= g->M && ntiles >= 0, "cg_cheb_step_tiles: bad C / rows / ntiles");
+    CG_REQUIRE(step_tile_rows(cg_side(g, transpose), g->nnz, C) > 0, "cg_cheb_step_tiles: the tiled step does not take C=%lld on this operator",
+               (long long)C);
+    CG_REQUIRE(((((uintptr_t)dev_X1) | ((uintptr_t)dev_X0) | ((uintptr_t)dev_out)) & 15) == 0, "cg_cheb_step_tiles: unaligned slab");
+    if (ntiles == 0) return CG_OK;
+    return launch_step(cg_side(g, transpose), g->nnz, g->M, rows, dev_X1, dev_X0, dev_out, C, alpha, (cudaStream_t)stream, dev_tiles,
+                       ntiles);
+}
+
+
+// Halo rows of a row-partitioned slab fetched straight from the owners' buffers (peer memory over NVLink / NVSwitch):
+// dst[i][:] = peer[src_rank[i]][slab_off + src_row[i] * C ...].  8 lanes x 16 bytes cover a 128-byte line per access.
+__global__ void __launch_bounds__(256) k_halo_pull(const float *const *__restrict__ peers, const int *__restrict__ src_rank,
+                                                   const int *__restrict__ src_row, long long slab_off, float *__restrict__ dst,
+                                                   long long nhalo, int C) {
+    const int c4 = C / 4;
+    const long long total = nhalo * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c4;
+        const int q = (int)(i - r * c4);
+        const float4 *src = reinterpret_cast<const float4 *>(peers[src_rank[r]] + slab_off + (long long)src_row[r] * C) + q;
+        reinterpret_cast<float4 *>(dst + r * C)[q] = *src;
+    }
+}
+
+extern "C" int cg_halo_pull(const void *dev_peer_ptrs, const int32_t *dev_src_rank, const int32_t *dev_src_row, int64_t slab_offset,
+                            float *dev_dst, int64_t nhalo, int C, void *stream) {
+    CG_REQUIRE(dev_peer_ptrs && dev_dst, "cg_halo_pull: NULL argument");
+    CG_REQUIRE(C > 0 && C % 4 == 0 && nhalo >= 0 && slab_offset % 4 == 0, "cg_halo_pull: C must be a multiple of 4 (C=%d)", C);
+    if (nhalo == 0) return CG_OK;
+    CG_REQUIRE(dev_src_rank && dev_src_row, "cg_halo_pull: NULL index arrays");
+    const long long total = nhalo * (C / 4);
+    const long long blocks = std::min<long long>(cg_ceil_div(total, 256), 148 * 8);
+    CgProfScope prof("halo_pull", (cudaStream_t)stream);
+    k_halo_pull<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float *const *>(dev_peer_ptrs), dev_src_rank,
+                                                                   dev_src_row, slab_offset, dev_dst, nhalo, C);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
 }

@@ -60,6 +60,66 @@ class RowPartition:
         self.local.sort_indices()
 
 
+class PeerHalo:
+    """Halo exchange through peer memory instead of a collective ("P2P NVLink reads on symmetric-memory
+    buffers"): the [K, rows, C] slab buffer of every rank is allocated with torch's symmetric-memory allocator and mapped
+    into all peers; per recurrence step the ranks meet at a device-side barrier (signal pads, no host round trip) and
+    every rank PULLS its halo rows of X_{k-1} straight out of the owners' slabs with one kernel (cg_halo_pull: NVLink
+    loads, 128-byte lines).  With a tile list from `split_tiles` the pull runs on a side stream under the interior tiles of
+    the step (cg_cheb_step_tiles); the boundary tiles follow.  NCCL is not involved in the recurrence at all."""
+
+    def __init__(self, part, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.part, self.device, self.group = part, device, group if group is not None else dist.group.WORLD
+        # rows of the shared buffer: the same on every rank (symmetric allocation)
+        n = torch.tensor([part.n_ext], dtype=torch.int64, device=device)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+        self.rows = int(n.item())
+        owner_edges = np.array([b for b, _ in part.bounds] + [part.M])
+        own = np.searchsorted(owner_edges, part.halo, side='right') - 1
+        starts = np.array([b for b, _ in part.bounds], dtype=np.int64)
+        self.src_rank = torch.as_tensor(own.astype(np.int32), device=device)
+        self.src_row = torch.as_tensor((part.halo - starts[own]).astype(np.int32), device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self._bufs = {}
+
+    def buffer(self, K, C):
+        """The symmetric [K, rows, C] buffer for this shape (allocated and exchanged once) and its handle."""
+        key = (int(K), int(C))
+        if key not in self._bufs:
+            t = self.symm_mem.empty((K, self.rows, C), dtype=torch.float32, device=self.device)
+            hdl = self.symm_mem.rendezvous(t, self.group)
+            self._bufs[key] = (t, hdl)
+        return self._bufs[key]
+
+    def barrier(self, hdl):
+        hdl.barrier(channel=0)          # device side, on the current stream
+
+    def pull(self, ext, hdl, k, stream=None):
+        """ext[k, nloc:nloc + nhalo] <- the owners' rows of slab k."""
+        part = self.part
+        if part.nhalo == 0:
+            return
+        K, rows, C = ext.shape
+        s = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        _native.check(_native.lib().cg_halo_pull(ctypes.c_void_p(hdl.buffer_ptrs_dev), self.src_rank.data_ptr(), self.src_row.data_ptr(),
+                                                 k * rows * C, ext[k, part.nloc:].data_ptr(), part.nhalo, C, s), 'cg_halo_pull')
+
+
+def split_tiles(part, tile_rows, device):
+    """(interior, boundary) tile lists (int32 device tensors) of this rank's row block: a tile of `tile_rows` rows is
+    boundary when one of its rows has an entry in a halo column."""
+    ntiles = -(-part.nloc // tile_rows)
+    L = part.local
+    rows_with_halo = np.unique(np.repeat(np.arange(L.shape[0]), np.diff(L.indptr))[L.indices >= part.nloc])
+    bt = np.unique(rows_with_halo[rows_with_halo < part.nloc] // tile_rows)
+    mask = np.ones(ntiles, bool)
+    mask[bt] = False
+    interior = np.nonzero(mask)[0].astype(np.int32)
+    return (torch.as_tensor(interior, device=device), torch.as_tensor(bt.astype(np.int32), device=device))
+
+
 def _exchange(part, x_ext, send_index_dev, group=None):
     """Fill x_ext[nloc:] with the halo rows (x_ext[:nloc] holds this rank's rows); all-to-all of packed rows."""
     C = x_ext.shape[1]
@@ -75,8 +135,9 @@ class PartitionedBasis:
     """T_k(L~) X for the rows of this rank.  `step_fn(x1_ext, x0_loc_or_None, alpha) -> out_loc` applies the local
     operator; the default is the native CUDA step (cg_cheb_step), tests inject a host function."""
 
-    def __init__(self, L_rescaled, rank=None, world=None, device=None, step_fn=None, group=None):
+    def __init__(self, L_rescaled, rank=None, world=None, device=None, step_fn=None, group=None, exchange='collective'):
         # rank / world are those of `group` (None = the default process group): the halo exchange runs on it
+        # exchange: 'collective' (all_to_all_single of packed rows) or 'peer' (PeerHalo: symmetric memory + pull kernel)
         self.group = group
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -91,6 +152,10 @@ class PartitionedBasis:
         if step_fn is None:
             from . import ops
             self._handle = ops.GraphHandle(self.part.local)
+        self.peer = None
+        self._tiles = {}
+        if exchange == 'peer' and self.part.world > 1 and step_fn is None:
+            self.peer = PeerHalo(self.part, self.device, group)
 
     def _native_step(self, x1_ext, x0, alpha, out):
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -103,8 +168,46 @@ class PartitionedBasis:
         tail rows hold the halo of every X_k: each step writes its block in place, no staging copies)."""
         return self.basis_ext(x_loc, K)[:, :self.part.nloc]
 
+    def _native_step_tiles(self, x1_ext, x0, alpha, out, tiles):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _native.check(_native.lib().cg_cheb_step_tiles(self._handle.handle, 0, x1_ext.data_ptr(),
+                                                       None if x0 is None else x0.data_ptr(), out.data_ptr(), self.part.nloc,
+                                                       x1_ext.shape[1], ctypes.c_float(alpha), tiles.data_ptr(), tiles.numel(),
+                                                       stream), 'cg_cheb_step_tiles')
+
+    def _basis_ext_peer(self, x_loc, K):
+        """Peer-memory form: barrier, pull on a side stream under the interior tiles, boundary tiles."""
+        part, peer = self.part, self.peer
+        C = x_loc.shape[1]
+        ext, hdl = peer.buffer(K, C)
+        if C not in self._tiles:
+            tr = _native.lib().cg_cheb_step_tile_rows(self._handle.handle, 0, C)
+            self._tiles[C] = split_tiles(part, tr, x_loc.device) if tr > 0 else None
+        tiles = self._tiles[C]
+        main = torch.cuda.current_stream()
+        peer.barrier(hdl)                       # nobody still reads the slabs of the previous call
+        ext[0, :part.nloc] = x_loc
+        for k in range(1, K):
+            peer.barrier(hdl)                   # every rank has written its rows of X_{k-1}
+            x0 = ext[k - 2, :part.nloc] if k > 1 else None
+            alpha = 2.0 if k > 1 else 1.0
+            out = ext[k, :part.nloc]
+            if tiles is None:
+                peer.pull(ext, hdl, k - 1)
+                self._native_step(ext[k - 1], x0, alpha, out)
+            else:
+                peer.side.wait_stream(main)
+                with torch.cuda.stream(peer.side):
+                    peer.pull(ext, hdl, k - 1, peer.side)
+                self._native_step_tiles(ext[k - 1], x0, alpha, out, tiles[0])       # interior: no halo row needed
+                main.wait_stream(peer.side)
+                self._native_step_tiles(ext[k - 1], x0, alpha, out, tiles[1])       # boundary
+        return ext
+
     def basis_ext(self, x_loc, K):
         """The whole [K, nloc + nhalo, C] buffer (rows [0, nloc) of every slab are this rank's rows)."""
+        if self.peer is not None:
+            return self._basis_ext_peer(x_loc, K)
         part = self.part
         C = x_loc.shape[1]
         ext = torch.empty((K, part.n_ext, C), dtype=torch.float32, device=x_loc.device)
@@ -133,13 +236,18 @@ class PartitionedFilter:
     pieces (cg_cheb_step, cg_cheb_contract, cg_cheb_contract_dw) in host-side tests."""
 
     def __init__(self, L_rescaled, K, rank=None, world=None, device=None, step_fn=None, step_fn_t=None,
-                 contract_fn=None, dw_fn=None, group=None):
+                 contract_fn=None, dw_fn=None, group=None, exchange='collective'):
         L_rescaled = scipy.sparse.csr_matrix(L_rescaled, dtype=np.float32)
         self.K = int(K)
         self.group = group
-        self.fwd = PartitionedBasis(L_rescaled, rank, world, device, step_fn, group=group)
-        self.bwd = PartitionedBasis(scipy.sparse.csr_matrix(L_rescaled.T), rank, world, device, step_fn_t, group=group)
-        self.exchange_kind = 'all_to_all_single (%s)' % (dist.get_backend(group) if dist.is_initialized() else 'single rank')
+        self.fwd = PartitionedBasis(L_rescaled, rank, world, device, step_fn, group=group, exchange=exchange)
+        self.bwd = PartitionedBasis(scipy.sparse.csr_matrix(L_rescaled.T), rank, world, device, step_fn_t, group=group,
+                                    exchange=exchange)
+        if self.fwd.peer is not None:
+            self.exchange_kind = ('peer memory: device barrier + cg_halo_pull over NVLink (symmetric memory), halo pulled under the '
+                                  'interior tiles of the step')
+        else:
+            self.exchange_kind = 'all_to_all_single (%s)' % (dist.get_backend(group) if dist.is_initialized() else 'single rank')
         self.part = self.fwd.part
         self._contract_fn, self._dw_fn = contract_fn, dw_fn
         self._saved = None

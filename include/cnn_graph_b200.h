@@ -76,6 +76,18 @@ int cg_cheb_basis(const cg_graph_t *g, int transpose, const float *dev_X, float 
  * recurrence of config C5, which exchanges the halo rows of X1 between two steps.              */
 int cg_cheb_step(const cg_graph_t *g, int transpose, const float *dev_X1, const float *dev_X0, float *dev_out,
                  int rows, int64_t C, float alpha, void *stream);
+/* The same step restricted to a list of row tiles (row-partitioned runs compute the tiles that need no halo row while
+ * the halo is in flight, the others after).  cg_cheb_step_tile_rows: rows per tile for slabs of C columns on this side
+ * of the operator, 0 when the tiled step does not apply (then use cg_cheb_step).  dev_tiles [ntiles] int32 on the device. */
+int cg_cheb_step_tile_rows(const cg_graph_t *g, int transpose, int64_t C);
+int cg_cheb_step_tiles(const cg_graph_t *g, int transpose, const float *dev_X1, const float *dev_X0, float *dev_out, int rows,
+                       int64_t C, float alpha, const int32_t *dev_tiles, int ntiles, void *stream);
+/* Halo rows of a row-partitioned slab read from the owners' buffers over NVLink (peer / symmetric memory, SURVEY.md
+ * 8(e)(2)): dev_dst [nhalo][C] <- peer[src_rank[i]][slab_offset + src_row[i] * C ...].  dev_peer_ptrs: device array of
+ * world float* (the ranks' buffer bases, e.g. _SymmetricMemory.buffer_ptrs_dev); slab_offset in elements.             */
+int cg_halo_pull(const void *dev_peer_ptrs, const int32_t *dev_src_rank, const int32_t *dev_src_row, int64_t slab_offset,
+                 float *dev_dst, int64_t nhalo, int C, void *stream);
+
 
 /* ---- Chebyshev filter (chebyshev5 / chebyshev2 / cheby_conv) ---------- */
 /* Forward: lib/models.py:192-224, lib/graph_conv.py:144-176, lib/filter.py:45-95

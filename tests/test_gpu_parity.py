@@ -1047,3 +1047,54 @@ def test_native_momentum_sgd_matches_torch(ops):
             ob.step()
             for p, q in zip(pa, pb):
                 close(p, q.detach().cpu().numpy(), 1e-6)
+
+
+def test_step_tiles_and_halo_pull_single_process(ops):
+    """The pieces of the peer-memory halo exchange that one process can check: cg_cheb_step_tiles over two disjoint tile
+    lists equals cg_cheb_step bit for bit, and cg_halo_pull gathers rows through a table of buffer pointers (here: two
+    local buffers standing in for two ranks)."""
+    import ctypes
+    from cnn_graph_b200 import _native
+    lib = _native.lib()
+    rng = np.random.RandomState(4)
+    n, C = 1500, 64
+    pts = rng.rand(n, 2)
+    order = np.lexsort((pts[:, 1], (pts[:, 0] * 12).astype(int)))          # strips: neighbours stay close in index
+    pts = pts[order]
+    import scipy.spatial
+    _, idx = scipy.spatial.cKDTree(pts).query(pts, k=9)
+    rows = np.repeat(np.arange(n), 8)
+    A = scipy.sparse.csr_matrix((np.full(n * 8, -0.1, np.float32), (rows, idx[:, 1:].ravel())), shape=(n, n))
+    A = ((A + A.T) * 0.5).tocsr().astype(np.float32)
+    A.sum_duplicates()
+    A.sort_indices()
+    h = ops.GraphHandle(A)
+    tr = lib.cg_cheb_step_tile_rows(h.handle, 0, C)
+    assert tr > 0, 'tiled step expected for a locality-ordered operator'
+    x1 = dev(rng.standard_normal((n, C)).astype(np.float32))
+    x0 = dev(rng.standard_normal((n, C)).astype(np.float32))
+    ref, got = torch.empty_like(x1), torch.zeros_like(x1)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(lib.cg_cheb_step(h.handle, 0, x1.data_ptr(), x0.data_ptr(), ref.data_ptr(), n, C, ctypes.c_float(2.0), stream), 'step')
+    ntiles = -(-n // tr)
+    perm = rng.permutation(ntiles).astype(np.int32)
+    for part in (perm[:ntiles // 2], perm[ntiles // 2:]):
+        t = dev(np.ascontiguousarray(part))
+        _native.check(lib.cg_cheb_step_tiles(h.handle, 0, x1.data_ptr(), x0.data_ptr(), got.data_ptr(), n, C, ctypes.c_float(2.0),
+                                             t.data_ptr(), t.numel(), stream), 'step_tiles')
+    assert torch.equal(ref, got)
+    # oracle: 2 A x1 - x0
+    close(ref, 2.0 * (A @ x1.cpu().numpy()) - x0.cpu().numpy(), 1e-5)
+    # halo pull: rows of two "ranks"
+    bufs = [dev(rng.standard_normal((3, 40, C)).astype(np.float32)) for _ in range(2)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device='cuda')
+    src_rank = rng.randint(0, 2, size=25).astype(np.int32)
+    src_row = rng.randint(0, 40, size=25).astype(np.int32)
+    dst = torch.zeros((25, C), device='cuda')
+    k = 2
+    d_rank, d_row = dev(src_rank), dev(src_row)        # kept alive: the launch is asynchronous
+    _native.check(lib.cg_halo_pull(table.data_ptr(), d_rank.data_ptr(), d_row.data_ptr(), k * 40 * C, dst.data_ptr(), 25, C,
+                                   stream), 'halo_pull')
+    torch.cuda.synchronize()
+    want = np.stack([bufs[r][k, j].cpu().numpy() for r, j in zip(src_rank, src_row)])
+    assert np.array_equal(dst.cpu().numpy(), want)
