@@ -63,6 +63,8 @@ def main():
     ap.add_argument('--overlap-allreduce', action='store_true', help='all-reduce the large gradients from autograd hooks, '
                     'overlapped with the backward pass (default: one flat all-reduce after it, which measured faster)')
     ap.add_argument('--eager', action='store_true', help='kernel-by-kernel launches instead of CUDA-graph replay')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'],
+                    help='tensor-core products: fp32-equivalent bf16 hi+mid split x3 (default, rtol 1e-4) or single-pass bf16 (rtol 2e-2)')
     ap.add_argument('--traffic-tag', default='r2', help='profiles/roofline_traffic_<tag>.json: ncu dram bytes per launch')
     # c4 / c5 knobs
     ap.add_argument('--T', type=int, default=3, help='c4: unrolled cell steps')
@@ -88,6 +90,9 @@ def main():
     if args.impl == 'reference':
         mod.run_reference(args, args.config)
     else:
+        if args.precision != 'fp32':
+            from cnn_graph_b200 import ops
+            ops.set_precision(args.precision)
         mod.run_ours(args, args.config)
         from benchmarks import common
         common.shutdown()

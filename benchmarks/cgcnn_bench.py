@@ -308,9 +308,9 @@ def run_ours(args, config):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': ('bf16' if getattr(args, 'precision', 'fp32') == 'bf16' else 'f32'), 'data': 'synthetic',
         'config': {'workload': cfg['workload'], 'name': config, 'batch_per_gpu': B, 'global_batch': B * world,
-                   'precision': 'fp32 storage and recurrence; tensor-core products as bf16 hi+mid split x3 with fp32 '
+                   'precision': 'fp32 storage and recurrence; single-pass bf16 tensor-core products (opt-in --precision bf16, rtol 2e-2)' if getattr(args, 'precision', 'fp32') == 'bf16' else 'fp32 storage and recurrence; tensor-core products as bf16 hi+mid split x3 with fp32 '
                                 'accumulation (error <= 2^-16 relative, inside rtol 1e-4)',
                    'parallelism': 'dp%d' % world, 'l2': 'flushed between timed iterations (256 MB fill)',
                    'timing': 'CUDA events per step on the launch stream, summed; max over ranks', 'launch': mode,

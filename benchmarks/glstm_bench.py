@@ -196,7 +196,7 @@ def run_ours(args, config):
                          'reference TF graph, all host threads)' % (B, time.perf_counter() - t0)}
     print(json.dumps({
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
-        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': ('bf16' if getattr(args, 'precision', 'fp32') == 'bf16' else 'f32'),
         'data': 'synthetic',
         'config': {'workload': workload_name(args), 'name': 'c4', 'batch_per_gpu': B, 'global_batch': B * world, 'T': T, 'H': H, 'K': K,
                    'gate_variant': 'fork (lib/gconv_lstm.py:185-215)', 'parallelism': 'dp%d' % world, 'launch': mode,

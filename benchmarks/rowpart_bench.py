@@ -178,7 +178,7 @@ def run_ours(args, config):
                          '(work is linear in M), %.1f s of CPU work incl. graph build; oracle/tf_ref.py' % (log2m, scale, time.perf_counter() - t0)}
     print(json.dumps({
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W_,
-        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': ('bf16' if getattr(args, 'precision', 'fp32') == 'bf16' else 'f32'),
         'data': 'synthetic',
         'config': {'workload': workload_name(args), 'name': 'c5', 'M': M, 'nnz': int(Lr.nnz), 'F': F, 'K': K, 'rows_rank0': part.nloc,
                    'halo_rows_rank0': part.nhalo, 'parallelism': 'rows%d' % world, 'exchange': pf.exchange_kind,

@@ -41,6 +41,7 @@ constexpr int CT = CC + 32;    // + issue warp
 constexpr int MAX_NS = 6;
 
 struct ClenshawParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const int *rowptr;
     const int *col;
     const float *val;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw(const ClenshawParams p)
                     const uint32_t acc = tmem + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t a_col = tmem + (uint32_t)(t * Fo) + (pass == 1 ? (uint32_t)(Fo / 2) : 0u);
                         uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
                         for (int j = 0; j < nk16; ++j) {
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(CT, 1) k_cheb_clenshaw_b(const ClenshawParams 
                     const uint32_t acc = tmem + g_col0 + (uint32_t)slot * g_slot + (uint32_t)(t * Fi);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t a_col = tmem + (uint32_t)(t * Fo) + (pass == 1 ? (uint32_t)(Fo / 2) : 0u);
                         uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
                         for (int j = 0; j < nk16; ++j) {
@@ -622,6 +625,7 @@ static CPlan make_cplan(const cg_graph *g, int N, int Fi, int Fo, int K, bool bl
         const size_t ent_bytes = blocked ? cg_blk_table_bytes(side.blk_len_sorted, S, LPR, ipt, CC) : (size_t)M * estride * 8;
         ClenshawParams cp;
         memset(&cp, 0, sizeof(cp));
+    cp.npass = cg_mma_passes();
         uint32_t off = 0;
         cp.off_bar = off;
         off += 128;

@@ -212,5 +212,9 @@ int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *d
 // (one CTA per SM with ~200 KB of shared memory leaves no room for another CTA).
 int cg_sm_budget(int device);
 
+// MMA passes per tensor-core product: 3 = fp32-equivalent (bf16 hi*hi + mid*hi + hi*mid, the default), 1 = single-pass bf16
+// (hi*hi only; BASELINE's 2e-2 tolerance).  Process-wide, set through cg_set_precision().
+int cg_mma_passes();
+
 static inline int64_t cg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

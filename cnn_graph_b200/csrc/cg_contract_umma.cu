@@ -28,6 +28,7 @@ constexpr int XT = XC + 64;      // + MMA issue warp + TMA producer warp
 constexpr int ROWS = 256;        // rows per chunk (two 128-row MMA tiles)
 
 struct CtParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const float *stack;          // [K][R][Fa]
     const float *W;              // [Fa*K][J]  (row = f*K + k)
     float *y;                    // [R][J]
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(XT, 1) k_contract_umma(const CtParams p) {
                     const uint32_t acc = tmem + (uint32_t)((c & 1) * (ROWS / 128) * J + t * J);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t al = a_lo + (uint32_t)t * t_step + (pass == 1 ? a_mid : 0u);
                         uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
                         for (int j = 0; j < Qp / 16; ++j) {
@@ -267,6 +269,7 @@ static CtPlan ct_plan(long long R, int Fa, int J, int K, size_t smem_limit) {
     if ((R * Fa) % 4 != 0 || (ROWS * Fa) % 4 != 0) return pl;       // 16-byte aligned pieces
     CtParams cp;
     memset(&cp, 0, sizeof(cp));
+    cp.npass = cg_mma_passes();
     const uint32_t sbo = (uint32_t)(Qp / 8) * 128u;
     uint32_t off = 0;
     cp.off_bar = off;

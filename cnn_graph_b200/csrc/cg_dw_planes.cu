@@ -29,6 +29,7 @@ constexpr int PT = PC + 64;        // + issue warp + producer warp
 constexpr int MAXST = 6;
 
 struct DwpParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const unsigned char *planes;   // [2][K][ceil(R/128)][Fa/8][128][8] bf16
     const float *T;                // gy [R][Fb]
     float *part;                   // [CTAs][K*Fa][Fb]
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(PT, 1) k_dw_planes(const DwpParams p) {
                     const uint32_t acc = tmem + (uint32_t)(t * Fb);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t al = a_lo + (pass == 1 ? (p.a_plane >> 4) : 0u), bl = b_lo + (pass == 2 ? (p.b_plane >> 4) : 0u);
                         for (int j = 0; j < CR / 16; ++j) {
                             umma::mma_bf16(acc, umma::desc_join(al, d_hi), umma::desc_join(bl, d_hi), idesc, (cl | pass | j) != 0);
@@ -241,6 +243,7 @@ static DwpPlan dwp_plan(long long R, int Fa, int Fb, int K, int sm_count, size_t
     if (tiles * Fb > 512) return pl;
     DwpParams dp;
     memset(&dp, 0, sizeof(dp));
+    dp.npass = cg_mma_passes();
     int cr0 = 128;
     if (const char *env = getenv("CG_DWP_CR")) cr0 = atoi(env);     // tuning aid: 128 or 64
     if (cr0 != 64) cr0 = 128;

@@ -49,6 +49,7 @@ __device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &mid) {
 }
 
 struct DwParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const float *stack;     // [K][R][Fa]
     const float *T;         // [R][Fb], row trow(r)
     float *part;            // [splits][K*Fa][Fb]
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(DT, 1) k_dw_umma(const DwParams p) {
                     const uint32_t acc = tmem + (uint32_t)(t * Fb);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t al = a_lo + (uint32_t)t * t_step + (pass == 1 ? a_mid : 0u);
                         uint32_t bl = b_lo + (pass == 2 ? b_mid : 0u);
                         for (int j = 0; j < KD / 16; ++j) {
@@ -367,6 +369,7 @@ static DwPlan dw_plan(int N, int M, int Fa, int Fb, int K, int sm_count, size_t 
             if (((long long)KD * Fa) % 4 != 0) continue;
             DwParams dp;
             memset(&dp, 0, sizeof(dp));
+    dp.npass = cg_mma_passes();
             uint32_t off = 0;
             dp.off_bar = off;
             off += 128;

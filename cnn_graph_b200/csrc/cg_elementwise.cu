@@ -520,15 +520,22 @@ extern "C" int cg_perm_data(const float *x, const int32_t *perm, float *out, int
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 __global__ void __launch_bounds__(256)
-k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ bias, const float *__restrict__ c,
-                 float *__restrict__ new_c, float *__restrict__ new_h, int64_t R, int H, int variant) {
+k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ pre2, const float *__restrict__ bias,
+                 const float *__restrict__ c, float *__restrict__ new_c, float *__restrict__ new_h, int64_t R, int H, int variant) {
     const int64_t total = R * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / H;
         const int h = (int)(i - r * H);
         const float *p = pre + r * 4 * H;
-        const float az = p[h] + bias[h], ai = p[H + h] + bias[H + h];
-        const float af = p[2 * H + h] + bias[2 * H + h], ao = p[3 * H + h] + bias[3 * H + h];
+        float az = p[h] + bias[h], ai = p[H + h] + bias[H + h];
+        float af = p[2 * H + h] + bias[2 * H + h], ao = p[3 * H + h] + bias[3 * H + h];
+        if (pre2 != nullptr) {      // x-path and h-path pre-activations summed here (lib/gconv_lstm.py:185-207), not by a separate pass
+            const float *q = pre2 + r * 4 * H;
+            az += q[h];
+            ai += q[H + h];
+            af += q[2 * H + h];
+            ao += q[3 * H + h];
+        }
         const float z = variant == 0 ? tanf(az) : tanhf(az);
         const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
         const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
@@ -539,8 +546,8 @@ k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ bias, 
 }
 
 __global__ void __launch_bounds__(256)
-k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ bias, const float *__restrict__ c,
-                 const float *__restrict__ new_c, const float *__restrict__ g_h, const float *__restrict__ g_c,
+k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ pre2, const float *__restrict__ bias,
+                 const float *__restrict__ c, const float *__restrict__ new_c, const float *__restrict__ g_h, const float *__restrict__ g_c,
                  float *__restrict__ g_pre, float *__restrict__ g_cprev, float *__restrict__ d_bias, int64_t R, int H,
                  int variant, int64_t rows_per_block) {
     // block covers rows [blockIdx.y * rows_per_block, ...) x columns h = blockIdx.x * 256 + tid
@@ -553,7 +560,14 @@ k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ bias, 
     for (int64_t r = r_beg; r < r_end; ++r) {
         const int64_t i = r * H + h;
         const float *p = pre + r * 4 * H;
-        const float az = p[h] + bz, ai = p[H + h] + bi, af = p[2 * H + h] + bf, ao = p[3 * H + h] + bo;
+        float az = p[h] + bz, ai = p[H + h] + bi, af = p[2 * H + h] + bf, ao = p[3 * H + h] + bo;
+        if (pre2 != nullptr) {
+            const float *q = pre2 + r * 4 * H;
+            az += q[h];
+            ai += q[H + h];
+            af += q[2 * H + h];
+            ao += q[3 * H + h];
+        }
         const float z = variant == 0 ? tanf(az) : tanhf(az);
         const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
         const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
@@ -578,20 +592,36 @@ k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ bias, 
     }
 }
 
+extern "C" int cg_lstm_gates2_fwd(const float *pre, const float *pre2, const float *bias, const float *c, float *new_c, float *new_h,
+                                  int64_t R, int H, int variant, void *stream);
 extern "C" int cg_lstm_gates_fwd(const float *pre, const float *bias, const float *c, float *new_c, float *new_h,
                                  int64_t R, int H, int variant, void *stream) {
+    return cg_lstm_gates2_fwd(pre, nullptr, bias, c, new_c, new_h, R, H, variant, stream);
+}
+
+extern "C" int cg_lstm_gates2_fwd(const float *pre, const float *pre2, const float *bias, const float *c, float *new_c, float *new_h,
+                                  int64_t R, int H, int variant, void *stream) {
     CG_REQUIRE(pre && bias && c && new_c && new_h, "cg_lstm_gates_fwd: NULL tensor");
     CG_REQUIRE(variant == 0 || variant == 1, "cg_lstm_gates_fwd: variant must be 0 (fork) or 1 (standard)");
     if (R * H == 0) return CG_OK;
     CgProfScope prof("lstm_gates_fwd", (cudaStream_t)stream);
-    k_lstm_gates_fwd<<<grid_for(R * H, 256), 256, 0, (cudaStream_t)stream>>>(pre, bias, c, new_c, new_h, R, H, variant);
+    k_lstm_gates_fwd<<<grid_for(R * H, 256), 256, 0, (cudaStream_t)stream>>>(pre, pre2, bias, c, new_c, new_h, R, H, variant);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
 
+extern "C" int cg_lstm_gates2_bwd(const float *pre, const float *pre2, const float *bias, const float *c, const float *new_c,
+                                  const float *g_h, const float *g_c, float *g_pre, float *g_cprev, float *d_bias, int64_t R, int H,
+                                  int variant, void *stream);
 extern "C" int cg_lstm_gates_bwd(const float *pre, const float *bias, const float *c, const float *new_c,
                                  const float *g_h, const float *g_c, float *g_pre, float *g_cprev, float *d_bias,
                                  int64_t R, int H, int variant, void *stream) {
+    return cg_lstm_gates2_bwd(pre, nullptr, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant, stream);
+}
+
+extern "C" int cg_lstm_gates2_bwd(const float *pre, const float *pre2, const float *bias, const float *c, const float *new_c,
+                                  const float *g_h, const float *g_c, float *g_pre, float *g_cprev, float *d_bias, int64_t R, int H,
+                                  int variant, void *stream) {
     CG_REQUIRE(pre && bias && c && new_c && g_pre && g_cprev, "cg_lstm_gates_bwd: NULL tensor");
     CG_REQUIRE(variant == 0 || variant == 1, "cg_lstm_gates_bwd: variant must be 0 (fork) or 1 (standard)");
     if (R * H == 0) return CG_OK;
@@ -605,7 +635,7 @@ extern "C" int cg_lstm_gates_bwd(const float *pre, const float *bias, const floa
     const int64_t rows_per_block = cg_ceil_div(R, row_blocks);
     dim3 grid((unsigned)col_blocks, (unsigned)cg_ceil_div(R, rows_per_block));
     CgProfScope prof("lstm_gates_bwd", s);
-    k_lstm_gates_bwd<<<grid, threads, 0, s>>>(pre, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant,
+    k_lstm_gates_bwd<<<grid, threads, 0, s>>>(pre, pre2, bias, c, new_c, g_h, g_c, g_pre, g_cprev, d_bias, R, H, variant,
                                           rows_per_block);
     CG_LAUNCH_CHECK();
     return CG_OK;

@@ -45,6 +45,7 @@ constexpr int NSTORE = 3;                  // plane store warps (one 128-row chu
 constexpr int FT = FC + 32 + 32 * NSTORE;  // + MMA issue warp + plane store warps = 20 warps: still 96 registers per thread
 
 struct FusedParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const int *rowptr;
     const int *col;
     const float *val;
@@ -130,6 +131,7 @@ __device__ __forceinline__ void fused_issue_group(const FusedParams &p, const Fu
             for (int t = 0; t < p.tiles; ++t, at += 128u, acc += (uint32_t)Fout) {      // 2048 bytes per 128-row tile
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
+                    if (pass >= p.npass) break;
 #pragma unroll
                     for (int j = 0; j < NK16; ++j) {
                         const uint32_t al = at + (pass == 1 ? a_mid : 0u) + (uint32_t)j * a_k;
@@ -688,6 +690,7 @@ static Plan make_plan(const cg_graph *g, const CgCsr &side, int64_t nnz, int N, 
             const int nslab = cfg == 0 ? 3 : 2, nw = cfg == 2 ? 1 : 2;
             FusedParams fp;
             memset(&fp, 0, sizeof(fp));
+    fp.npass = cg_mma_passes();
             uint32_t off = 0;
             fp.off_bar = off;
             off += 128;

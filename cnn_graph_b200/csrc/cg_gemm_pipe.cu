@@ -48,6 +48,7 @@ __host__ __device__ constexpr uint32_t plane_bytes(int rows) {
 }
 
 struct PipeParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const float *A, *B, *bias;
     float *C;                           // [M][ldc] (split == 1) or partials [split][M][N]
     long long *trace;                   // optional (debug): clock64 stamps of CTA 0, stages 8..39: [32][8]
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(PT, 1) k_gemm_pipe(const PipeParams p) {
                     const uint32_t a_lo = umma::desc_lo(sb, a_lbo), b_lo = umma::desc_lo(sb + p.off_b, b_lbo);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= p.npass) break;
                         uint32_t al = a_lo + (pass == 1 ? (p.a_plane >> 4) : 0u), bl = b_lo + (pass == 2 ? (p.b_plane >> 4) : 0u);
 #pragma unroll
                         for (int j = 0; j < BK / 16; ++j) {
@@ -460,6 +462,7 @@ struct PipePlan {
 static PipePlan pipe_plan(int M, int N, int K, int sm_count) {
     PipePlan pl;
     memset(&pl, 0, sizeof(pl));
+    pl.pp.npass = cg_mma_passes();
     pl.BN = N > 128 ? 256 : N > 64 ? 128 : N > 32 ? 64 : 32;
     const int tiles_n = (int)cg_ceil_div(N, pl.BN);
     pl.tiles = (int)cg_ceil_div(M, BM) * tiles_n;

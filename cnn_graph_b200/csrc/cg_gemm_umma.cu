@@ -29,6 +29,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 
 struct GemmParams {
+    int npass;                   // MMA passes per product: 3 (fp32-equivalent hi/mid split) or 1 (single-pass bf16)
     const float *A, *B, *bias;
     float *C;                    // [M][ldc] (split == 1) or partials [split][M][N]
     int M, N, K, lda, ldb, ldc, transA, transB, relu, BN, split, k_per_split, vecA, vecB;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_umma(const GemmParams p) {
                 const uint32_t a_lo = umma::desc_lo(sb + p.off_a, a_lbo), b_lo = umma::desc_lo(sb + p.off_b, b_lbo);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
+                    if (pass >= p.npass) break;
                     uint32_t al = a_lo + (pass == 1 ? (p.a_plane >> 4) : 0u), bl = b_lo + (pass == 2 ? (p.b_plane >> 4) : 0u);
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j) {
@@ -267,6 +269,7 @@ struct GPlan {
 static GPlan gemm_plan(int M, int N, int K, int sm_count) {
     GPlan pl;
     memset(&pl, 0, sizeof(pl));
+    pl.gp.npass = cg_mma_passes();
     pl.BN = N > 128 ? 256 : 128;
     const int tiles = (int)(cg_ceil_div(M, BM) * cg_ceil_div(N, pl.BN));
     pl.tiles = tiles;

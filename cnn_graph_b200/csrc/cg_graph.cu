@@ -20,6 +20,15 @@ void cg_set_error(const char *fmt, ...) {
 
 extern "C" const char *cg_last_error(void) { return g_err; }
 
+static int g_mma_passes = 3;
+int cg_mma_passes() { return g_mma_passes; }
+extern "C" int cg_set_precision(int mode) {
+    CG_REQUIRE(mode == CG_PRECISION_FP32 || mode == CG_PRECISION_BF16, "cg_set_precision: mode must be CG_PRECISION_FP32 (0) or CG_PRECISION_BF16 (1)");
+    g_mma_passes = mode == CG_PRECISION_BF16 ? 1 : 3;
+    return CG_OK;
+}
+extern "C" int cg_get_precision(void) { return g_mma_passes == 1 ? CG_PRECISION_BF16 : CG_PRECISION_FP32; }
+
 int cg_sm_budget(int device) {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);

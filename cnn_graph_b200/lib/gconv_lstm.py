@@ -69,7 +69,8 @@ class GConvLSTMCell(object):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         shape = (batch_size, self._nNode, self._num_units)
-        return (torch.zeros(shape, dtype=dtype, device=device), torch.zeros(shape, dtype=dtype, device=device))
+        return (ops.mark_zero(torch.zeros(shape, dtype=dtype, device=device)),
+                ops.mark_zero(torch.zeros(shape, dtype=dtype, device=device)))
 
     def _variables(self, K, feat_in, H):
         uni = variables.random_uniform_initializer(-0.1, 0.1)
@@ -93,9 +94,12 @@ class GConvLSTMCell(object):
             # x and h are filtered separately and summed, as in the reference; the hidden path then has a
             # feature count (H) that the vectorised tensor-core kernels take, unlike [x | h] (Fin + H)
             bias = torch.cat(b, dim=0)
-            pre = (self.filter(inputs, self._laplacian, self._lmax, 4 * H, K, torch.cat(Wx, dim=1)) +
-                   self.filter(h, self._laplacian, self._lmax, 4 * H, K, torch.cat(Wh, dim=1)))
-            new_h, new_c = ops.lstm_gates(pre, bias, c, self.gate_variant)
+            pre_x = self.filter(inputs, self._laplacian, self._lmax, 4 * H, K, torch.cat(Wx, dim=1))
+            # the filter is linear: on the all-zero initial state (zero_state) its output is exactly zero -- skipped;
+            # otherwise the two addends are summed inside the gate kernels (no [N, M, 4H] pass for the addition)
+            pre_h = None if ops.is_marked_zero(h) else self.filter(h, self._laplacian, self._lmax, 4 * H, K,
+                                                                   torch.cat(Wh, dim=1))
+            new_h, new_c = ops.lstm_gates(pre_x, bias, c, self.gate_variant, pre2=pre_h)
             if self._state_is_tuple:
                 new_state = LSTMStateTuple(new_c, new_h)
             else:
@@ -323,7 +327,7 @@ class GconvModel(GraphModel):
         states = []
         for cell in cells:
             shape = (N, self.node_num, self.num_hidden)
-            states.append((first.new_zeros(shape), first.new_zeros(shape)))
+            states.append((ops.mark_zero(first.new_zeros(shape)), ops.mark_zero(first.new_zeros(shape))))
         outputs = []
         with self.variable_scope('rnn'):
             for step in range(num_time_step):

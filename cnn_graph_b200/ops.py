@@ -160,6 +160,16 @@ _STACK_SAVE_LIMIT = 8 << 30      # bytes: larger bases are recomputed in the bac
 _save_stack = True
 
 
+def set_precision(mode):
+    """'fp32' (default: bf16 hi+mid split, three tensor-core passes, inside rtol 1e-4) or 'bf16' (single pass, BASELINE's
+    2e-2 tolerance) for every tensor-core product of the library; storage and the recurrence stay fp32."""
+    check(_native.lib().cg_set_precision({'fp32': 0, 'bf16': 1}[mode]), 'cg_set_precision')
+
+
+def get_precision():
+    return 'bf16' if _native.lib().cg_get_precision() == 1 else 'fp32'
+
+
 _stack_planes = True
 FILTER_STACK_PLANES = 32
 
@@ -667,26 +677,28 @@ def perm_data_device(x, perm, out=None, perm_t=None):
 class LstmGatesFn(torch.autograd.Function):
     """Gate nonlinearities + state update of GConvLSTMCell (lib/gconv_lstm.py:185-215).
 
-    pre [N, M, 4H] (z|i|f|o), bias [4H], c [N, M, H]  ->  new_h, new_c.
+    pre [N, M, 4H] (z|i|f|o) (+ pre2, the second addend: x-path and h-path filters are summed inside the gate kernels),
+    bias [4H], c [N, M, H]  ->  new_h, new_c.
     """
 
     @staticmethod
-    def forward(ctx, pre, bias, c, variant):
+    def forward(ctx, pre, pre2, bias, c, variant):
         _require_cuda(pre, bias, c)
         pre, bias, c = _f32c(pre), _f32c(bias), _f32c(c)
+        pre2 = _f32c(pre2) if pre2 is not None else None
         H = c.shape[-1]
         R = c.numel() // H
         new_c = torch.empty_like(c)
         new_h = torch.empty_like(c)
-        check(_native.lib().cg_lstm_gates_fwd(ptr(pre), ptr(bias), ptr(c), ptr(new_c), ptr(new_h), R, H, variant,
-                                              _stream()), 'cg_lstm_gates_fwd')
-        ctx.save_for_backward(pre, bias, c, new_c)
+        check(_native.lib().cg_lstm_gates2_fwd(ptr(pre), ptr(pre2), ptr(bias), ptr(c), ptr(new_c), ptr(new_h), R, H, variant,
+                                               _stream()), 'cg_lstm_gates2_fwd')
+        ctx.save_for_backward(pre, pre2, bias, c, new_c)
         ctx.variant = variant
         return new_h, new_c
 
     @staticmethod
     def backward(ctx, g_h, g_c):
-        pre, bias, c, new_c = ctx.saved_tensors
+        pre, pre2, bias, c, new_c = ctx.saved_tensors
         H = c.shape[-1]
         R = c.numel() // H
         g_h = _f32c(g_h) if g_h is not None else None
@@ -694,17 +706,28 @@ class LstmGatesFn(torch.autograd.Function):
         g_pre = torch.empty_like(pre)
         g_cprev = torch.empty_like(c)
         d_bias = torch.empty_like(bias)
-        check(_native.lib().cg_lstm_gates_bwd(ptr(pre), ptr(bias), ptr(c), ptr(new_c), ptr(g_h), ptr(g_c),
-                                              ptr(g_pre), ptr(g_cprev), ptr(d_bias), R, H, ctx.variant, _stream()),
-              'cg_lstm_gates_bwd')
-        return g_pre, d_bias, g_cprev, None
+        check(_native.lib().cg_lstm_gates2_bwd(ptr(pre), ptr(pre2), ptr(bias), ptr(c), ptr(new_c), ptr(g_h), ptr(g_c),
+                                               ptr(g_pre), ptr(g_cprev), ptr(d_bias), R, H, ctx.variant, _stream()),
+              'cg_lstm_gates2_bwd')
+        return g_pre, (g_pre if pre2 is not None else None), d_bias, g_cprev, None
 
 
-def lstm_gates(pre, bias, c, variant='fork'):
+def lstm_gates(pre, bias, c, variant='fork', pre2=None):
+    """pre (+ pre2) are the gate pre-activations without bias; returns (new_h, new_c)."""
     v = {'fork': 0, 'standard': 1}[variant] if isinstance(variant, str) else int(variant)
     if pre.is_meta:
         return c.new_empty(c.shape), c.new_empty(c.shape)
-    return LstmGatesFn.apply(pre, bias, c, v)
+    return LstmGatesFn.apply(pre, pre2, bias, c, v)
+
+
+def mark_zero(t):
+    """Tag a tensor as known all-zero (initial LSTM state): a linear filter of it is exactly zero and can be skipped."""
+    t._cg_zero = True
+    return t
+
+
+def is_marked_zero(t):
+    return bool(getattr(t, '_cg_zero', False))
 
 
 # ---------------------------------------------------------------------------------------

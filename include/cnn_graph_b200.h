@@ -244,6 +244,15 @@ int cg_lstm_gates_bwd(const float *dev_pre, const float *dev_bias, const float *
                       const float *dev_new_c, const float *dev_g_h, const float *dev_g_c,
                       float *dev_g_pre, float *dev_g_cprev, float *dev_d_bias, int64_t R, int H,
                       int variant, void *stream);
+/* The same with the pre-activations given as TWO addends (x-path and h-path filters, lib/gconv_lstm.py:185-207:
+ * filter(x, W?x) + filter(h, W?h)): dev_pre2 [R][4H] or NULL; the sum is formed inside the gate kernels, the
+ * gradient dev_g_pre belongs to both addends.                                                                   */
+int cg_lstm_gates2_fwd(const float *dev_pre, const float *dev_pre2, const float *dev_bias, const float *dev_c, float *dev_new_c,
+                       float *dev_new_h, int64_t R, int H, int variant, void *stream);
+int cg_lstm_gates2_bwd(const float *dev_pre, const float *dev_pre2, const float *dev_bias, const float *dev_c, const float *dev_new_c,
+                       const float *dev_g_h, const float *dev_g_c, float *dev_g_pre, float *dev_g_cprev, float *dev_d_bias,
+                       int64_t R, int H, int variant, void *stream);
+
 
 /* ---- launch accounting / per-kernel timing (measurement support) -------- */
 /* cg_launch_count: kernels launched by this library since load (all threads).
@@ -269,6 +278,15 @@ int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, i
 
 /* A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A operand): dev_A [128][Kd], dev_B [N][Kd]. */
 int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, void *stream);
+
+/* ---- precision of the tensor-core products (process-wide) --------------------------------------------------------
+ * CG_PRECISION_FP32 (default): every fp32 operand is split into bf16 hi + mid and the product is formed as hi*hi + mid*hi
+ * + hi*mid with fp32 accumulation (error <= 2^-16 relative: BASELINE's fp32 tolerance, rtol 1e-4).
+ * CG_PRECISION_BF16: hi*hi only -- one tensor-core pass instead of three (BASELINE's bf16 tolerance, 2e-2).  Storage, the
+ * recurrence and all accumulation stay fp32 in both modes.                                                          */
+enum { CG_PRECISION_FP32 = 0, CG_PRECISION_BF16 = 1 };
+int cg_set_precision(int mode);
+int cg_get_precision(void);
 
 /* ---- loss + optimiser tail of cgcnn (lib/graph_model.py:246-310, upstream cgcnn.loss / training) ----------------- */
 /* Softmax cross-entropy averaged over the batch AND its gradient in one launch: dev_logits [N][C] fp32, dev_labels [N]

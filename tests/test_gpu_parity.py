@@ -1098,3 +1098,87 @@ def test_step_tiles_and_halo_pull_single_process(ops):
     torch.cuda.synchronize()
     want = np.stack([bufs[r][k, j].cpu().numpy() for r, j in zip(src_rank, src_row)])
     assert np.array_equal(dst.cpu().numpy(), want)
+
+
+def test_lstm_gates_two_addends_and_zero_state_skip(ops, tf_ref, c2):
+    """The gate kernels sum the x-path and h-path pre-activations themselves (same values and gradients as the sum formed
+    outside), and a cell step on the marked all-zero initial state (its h-path filter is skipped: the filter is linear)
+    equals the step on an ordinary zero tensor."""
+    rng = np.random.RandomState(2)
+    N, M, H = 3, 40, 16
+    px, ph = (rng.standard_normal((N, M, 4 * H)).astype(np.float32) * 0.5 for _ in range(2))
+    b = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    c = rng.standard_normal((N, M, H)).astype(np.float32)
+    gh, gc = (rng.standard_normal((N, M, H)).astype(np.float32) for _ in range(2))
+    for variant in ('fork', 'standard'):
+        outs = []
+        for two in (True, False):
+            tx, th, tb, tc = (dev(a).requires_grad_(True) for a in (px, ph, b, c))
+            if two:
+                nh, nc = ops.lstm_gates(tx, tb, tc, variant, pre2=th)
+            else:
+                nh, nc = ops.lstm_gates(tx + th, tb, tc, variant)
+            torch.autograd.backward([nh, nc], [dev(gh), dev(gc)])
+            outs.append([t.detach().cpu().numpy() for t in (nh, nc, tx.grad, th.grad, tb.grad, tc.grad)])
+        for a, r in zip(*outs):
+            close(a, r, 2e-6)
+    from cnn_graph_b200.lib import gconv_lstm, variables
+    L = csr_from(c2, 'L3')
+    Mg = L.shape[0]
+    x = dev(rng.standard_normal((2, Mg, 2)).astype(np.float32))
+    res = []
+    for marked in (True, False):
+        torch.manual_seed(0)
+        store = variables.VariableStore(torch.device('cuda'))
+        with variables.use_store(store):
+            cell = gconv_lstm.GConvLSTMCell(num_units=16, laplacian=L, lmax=2, K=3, feat_in=2, nNode=Mg, gate_variant='standard')
+            state = cell.zero_state(2) if marked else (torch.zeros(2, Mg, 16, device='cuda'), torch.zeros(2, Mg, 16, device='cuda'))
+            assert ops.is_marked_zero(state[1]) == marked
+            h1, st1 = cell(x, state)
+            h2, _ = cell(x, (st1.c, st1.h))
+        res.append((h1.detach().cpu().numpy(), h2.detach().cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0])
+    close(res[0][1], res[1][1], 1e-6)
+
+
+BF16_RTOL = 2e-2       # BASELINE.json north_star: "within rtol 1e-4 fp32 / 2e-2 bf16 for filter outputs and gradients"
+
+
+@pytest.mark.parametrize('level,N,Fin,Fout,K,flags', [(2, 19, 32, 64, 25, 0), (3, 7, 16, 32, 5, 0), (2, 6, 32, 64, 9, 4), (0, 5, 1, 32, 25, 0),
+                                                     (4, 33, 64, 512, 3, 0), (2, 4, 8, 16, 6, 1)])
+def test_single_pass_bf16_mode_within_2e_2(ops, tf_ref, c2, level, N, Fin, Fout, K, flags):
+    """Opt-in single-pass bf16 products (cg_set_precision): one tensor-core pass instead of three in every MMA kernel --
+    fused forward / Clenshaw / dW kernels, the HBM-basis contraction, the pipelined GEMMs.  Outputs and gradients stay
+    inside the bf16 tolerance, and the mode is really on (its error exceeds the fp32 mode's wherever tensor cores run)."""
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(7 * level + K)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    ref_y = tf_ref.chebyshev5(x, L, W, K)
+    ref_dx, ref_dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+
+    def run():
+        xt, Wt = dev(x).requires_grad_(True), dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, K, flags=flags)
+        y.backward(dev(gy))
+        return [t.detach().cpu().numpy() for t in (y, xt.grad, Wt.grad)]
+
+    def rel(a, r):
+        return float(np.abs(a.astype(np.float64) - r).max() / max(np.abs(r).max(), 1e-30))
+
+    full = run()
+    assert ops.get_precision() == 'fp32'
+    ops.set_precision('bf16')
+    try:
+        assert ops.get_precision() == 'bf16'
+        half = run()
+    finally:
+        ops.set_precision('fp32')
+    for a, r in zip(half, (ref_y, ref_dx, ref_dW)):
+        close(a, r, BF16_RTOL)
+    for a, r in zip(full, (ref_y, ref_dx, ref_dW)):
+        close(a, r, RTOL)
+    if flags == 0:        # default path: the forward contraction runs on the tensor cores
+        assert rel(half[0], ref_y) > 4 * rel(full[0], ref_y), 'bf16 mode did not change the forward products'
