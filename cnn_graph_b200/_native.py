@@ -82,6 +82,7 @@ _SIGNATURES = {
                                    c_void_p]),
     'cg_lstm_gates2_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    'cg_csr_densify': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'cg_set_precision': (c_int, [c_int]),
     'cg_get_precision': (c_int, []),
     'cg_launch_count': (c_i64, []),

@@ -745,3 +745,36 @@ extern "C" int cg_sgd_momentum(const void *host_table, int ntensors, long long m
     }
     return CG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse input batches (lib/graph_model.py:150-151 densifies scipy batches on the host and feeds
+// the dense array): the CSR batch travels to the device as it is (indptr, indices, values: ~1 % of the dense bytes
+// for bag-of-words rows) and is expanded here.  One block per row: zero the row, then scatter its entries; rows of
+// the batch beyond the CSR (zero padding of a last batch) are cleared.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_csr_densify(const int *__restrict__ indptr, const int *__restrict__ indices,
+                                                      const float *__restrict__ values, float *__restrict__ out, int rows, int M) {
+    const int n = blockIdx.x;
+    float *row = out + (size_t)n * M;
+    const int m4 = ((((uintptr_t)row) & 15) == 0) ? M / 4 : 0;
+    for (int i = threadIdx.x; i < m4; i += blockDim.x) reinterpret_cast<float4 *>(row)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 4 * m4 + threadIdx.x; i < M; i += blockDim.x) row[i] = 0.f;
+    if (n >= rows) return;
+    __syncthreads();
+    const int beg = indptr[n], end = indptr[n + 1];
+    for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+        const int c = indices[e];
+        if (c >= 0 && c < M) atomicAdd(row + c, values[e]);       // duplicates are summed, as scipy's toarray() does
+    }
+}
+
+extern "C" int cg_csr_densify(const int32_t *dev_indptr, const int32_t *dev_indices, const float *dev_values, float *dev_out,
+                              int csr_rows, int out_rows, int M, void *stream) {
+    CG_REQUIRE(dev_indptr && dev_out && out_rows >= csr_rows && csr_rows >= 0 && M > 0, "cg_csr_densify: bad arguments");
+    if (out_rows == 0) return CG_OK;
+    CgProfScope prof("csr_densify", (cudaStream_t)stream);
+    k_csr_densify<<<(unsigned)out_rows, 256, 0, (cudaStream_t)stream>>>(dev_indptr, dev_indices, dev_values, dev_out, csr_rows, M);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

@@ -99,7 +99,10 @@ class GraphModel(object):
     # ------------------------------------------------------------------ step / loops
     def _to_device(self, a, dtype=torch.float32):
         if not isinstance(a, np.ndarray):
-            a = a.toarray()                                      # scipy sparse batches, :150-151
+            if self.device.type == 'cuda' and dtype == torch.float32:
+                from .. import ops                               # scipy sparse batches (:150-151): CSR to the device, expanded there
+                return ops.sparse_batch_to_device(a, self.device)
+            a = a.toarray()
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.to(self.device, dtype=dtype, non_blocking=True)
 
@@ -306,6 +309,47 @@ class PipelinedTrainer(object):
             if self.x is None:
                 self.x = torch.empty_like(self.raw[b])
             self.x.copy_(self.raw[b], non_blocking=True)
+        if self.y is None:
+            self.y = torch.empty_like(self.lab[b])
+        self.y.copy_(self.lab[b], non_blocking=True)
+        self.consumed[b].record(cur)
+        step = self.model.train_step_graphed if self.use_graph else self.model.train_step
+        loss = step(self.x, self.y)
+        self.loss_host[b:b + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.loss_done[b].record(cur)
+        self.count += 1
+
+    def submit_csr(self, indptr_host, indices_host, values_host, n_cols, y_host):
+        """The same for a SPARSE batch: pinned CSR arrays (int32 indptr / indices, float32 values) instead of a dense
+        array -- the H2D copy carries only the stored entries (about 1 % of the dense bytes for bag-of-words rows) and
+        cg_csr_densify expands them into the step's static input buffer.  No perm (sparse data sets have no coarsening
+        here: 20news.ipynb cell 1).  The index arrays may differ in length from batch to batch."""
+        from .. import ops
+        i, b = self.count, self.count % self.depth
+        if i >= self.depth:
+            self._collect(b)
+        nnz, rows = int(indices_host.numel()), int(indptr_host.numel()) - 1
+        slot = self.raw[b]
+        if slot is None or slot[1].numel() < nnz or slot[0].numel() != rows + 1:
+            cap = max(nnz, 1) * 2
+            slot = self.raw[b] = (torch.empty(rows + 1, dtype=torch.int32, device=self.device),
+                                  torch.empty(cap, dtype=torch.int32, device=self.device),
+                                  torch.empty(cap, dtype=torch.float32, device=self.device))
+            self.lab[b] = torch.empty(y_host.shape, dtype=y_host.dtype, device=self.device)
+        self.h2d_bytes_per_step = 4 * (rows + 1) + 8 * nnz + y_host.numel() * y_host.element_size()
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if i >= self.depth:
+                self.copy_stream.wait_event(self.consumed[b])
+            slot[0].copy_(indptr_host, non_blocking=True)
+            slot[1][:nnz].copy_(indices_host, non_blocking=True)
+            slot[2][:nnz].copy_(values_host, non_blocking=True)
+            self.lab[b].copy_(y_host, non_blocking=True)
+            self.copied[b].record(self.copy_stream)
+        cur.wait_event(self.copied[b])
+        if self.x is None:
+            self.x = torch.empty((rows, int(n_cols)), dtype=torch.float32, device=self.device)
+        ops.csr_densify(slot[0], slot[1], slot[2], int(n_cols), out_rows=rows, out=self.x)
         if self.y is None:
             self.y = torch.empty_like(self.lab[b])
         self.y.copy_(self.lab[b], non_blocking=True)

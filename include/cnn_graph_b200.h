@@ -279,6 +279,12 @@ int cg_debug_umma_gemm_m(const float *dev_A, const float *dev_B, float *dev_D, i
 /* A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A operand): dev_A [128][Kd], dev_B [N][Kd]. */
 int cg_debug_umma_gemm_ts(const float *dev_A, const float *dev_B, float *dev_D, int N, int Kd, void *stream);
 
+/* ---- sparse input batches (lib/graph_model.py:145-158: scipy batches densified on the host, then fed) ------------- */
+/* dev_out [out_rows][M] fp32 <- CSR batch (dev_indptr [csr_rows + 1], dev_indices, dev_values: int32 / fp32, on the
+ * device); duplicates are summed like scipy's toarray(); rows csr_rows .. out_rows-1 are zero (padded last batch).   */
+int cg_csr_densify(const int32_t *dev_indptr, const int32_t *dev_indices, const float *dev_values, float *dev_out, int csr_rows,
+                   int out_rows, int M, void *stream);
+
 /* ---- precision of the tensor-core products (process-wide) --------------------------------------------------------
  * CG_PRECISION_FP32 (default): every fp32 operand is split into bf16 hi + mid and the product is formed as hi*hi + mid*hi
  * + hi*mid with fp32 accumulation (error <= 2^-16 relative: BASELINE's fp32 tolerance, rtol 1e-4).
