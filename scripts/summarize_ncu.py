@@ -16,8 +16,9 @@ COLS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__shared_mem_per_block_dynamic']
 # profile-scope names of bench.py (cg_profile_*) for the kernels whose DRAM traffic the roofline line quotes
-SCOPE = {'k_cheb_fused': 'fused_fwd', 'k_cheb_clenshaw': 'clenshaw_dx', 'k_dw_planes': 'dw_umma', 'k_dw_umma': 'dw_umma', 'k_dw_thin': 'dw_thin',
-         'k_contract_umma': 'contract_umma', 'k_gemm_pipe': 'gemm_umma', 'k_basis_onchip': 'basis_onchip'}
+SCOPE = {'k_cheb_fused': 'fused_fwd', 'k_cheb_clenshaw': 'clenshaw_dx', 'k_dw_planes': 'dw_planes', 'k_dw_umma': 'dw_umma', 'k_dw_thin': 'dw_thin',
+         'k_contract_umma': 'contract_umma', 'k_gemm_pipe': 'gemm_pipe', 'k_gemm_umma': 'gemm_umma', 'k_basis_onchip': 'basis_onchip',
+         'k_spmm_tile_p': 'spmm_step', 'k_spmm_step': 'spmm_step'}
 
 
 def launches(path, out, header):
@@ -65,7 +66,7 @@ def full(rep, out, traffic_out=None):
     if traffic_out:
         t = {k: sum(v) / len(v) for k, v in traffic.items()}
         t['_note'] = ('dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of the '
-                      'scope), ncu --set full, bench.py batch 1024 --eager (%s)' % out)
+                      'scope), ncu --set full --clock-control none of the same bench.py command with --eager (%s)' % out)
         json.dump(t, open(traffic_out, 'w'), indent=1)
 
 
