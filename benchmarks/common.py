@@ -120,11 +120,15 @@ class Timer:
         torch = self.torch
         for _ in range(warmup):
             fn()
-        torch.cuda.synchronize()
-        cgdist.barrier()
+        # the clock sampler (an nvidia-smi subprocess) starts BEFORE the barrier: spawning it takes tens of milliseconds
+        # that differ from rank to rank, and a step with a collective in it makes every rank wait for the last one --
+        # started after the barrier, that skew landed inside the first timed step of every rank (8 GPUs: +1 ms per step
+        # over 20 steps)
         sampler = ClockSampler(self.local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
+        torch.cuda.synchronize()
+        cgdist.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in ev:
             self.flush()
