@@ -58,7 +58,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -66,9 +66,18 @@ class ClockSampler:
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
-            time.sleep(0.15)          # let the first sample land inside the timed region
+            # wait for the first sample: nvidia-smi's start-up (NVML initialisation over every GPU of the box) stalls the
+            # GPUs for tens of milliseconds -- it must be over before the timed region begins, the 100 ms polls that follow
+            # are what the timed region should see
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """Samples from here on count (start of the timed region)."""
+        self.first = len(self.lines)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -77,11 +86,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, power, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 8:
                 continue
@@ -107,6 +115,8 @@ class Timer:
         import torch
         self.torch = torch
         self.device, self.local_rank = device, local_rank
+        if os.environ.get('CG_BENCH_NOFLUSH'):            # debugging aid only: a published number needs the flush
+            flush = False
         self.flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device) if flush else None
 
     def flush(self):
@@ -118,17 +128,19 @@ class Timer:
         untimed-in-`total_ms` but timed separately until that much wall time has passed (sustained-rate check)."""
         from cnn_graph_b200 import dist as cgdist
         torch = self.torch
-        for _ in range(warmup):
-            fn()
-        # the clock sampler (an nvidia-smi subprocess) starts BEFORE the barrier: spawning it takes tens of milliseconds
-        # that differ from rank to rank, and a step with a collective in it makes every rank wait for the last one --
-        # started after the barrier, that skew landed inside the first timed step of every rank (8 GPUs: +1 ms per step
-        # over 20 steps)
-        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        # the clock sampler (ONE nvidia-smi subprocess, on local rank 0) starts before the warm-up and is given time to
+        # finish initialising: started after the barrier, its spawn skew landed inside the first timed step of every rank
+        # and its NVML start-up stalled all GPUs for ~28 ms in the middle of the timed region (8 GPUs: +1 ms per step
+        # over 20 steps; per-step times printed with CG_BENCH_STEPTIMES=1 showed 1.53 ms steps and one 28 ms outlier)
+        sampler = ClockSampler(self.local_rank) if (sample_clocks and self.local_rank == 0) else None
         if sampler:
             sampler.start()
+        for _ in range(warmup):
+            fn()
         torch.cuda.synchronize()
         cgdist.barrier()
+        if sampler:
+            sampler.mark()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in ev:
             self.flush()
@@ -137,7 +149,19 @@ class Timer:
             b.record()
         torch.cuda.synchronize()
         cgdist.barrier()
+        if sample_clocks:
+            # the timed region is a few tens of milliseconds, nvidia-smi polls every 100 ms: keep the same step running
+            # (untimed) for 0.3 s so that the clocks / throttle reasons are sampled under this very load
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 0.3:
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+            cgdist.barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
+        if os.environ.get('CG_BENCH_STEPTIMES'):          # debugging aid: per-step device times of this rank
+            import sys
+            sys.stderr.write('rank %s step ms: %s\n' % (os.environ.get('RANK', '0'), ' '.join('%.3f' % a.elapsed_time(b) for a, b in ev)))
         sustained = None
         if min_seconds > 0:
             t0 = time.perf_counter()
