@@ -517,7 +517,11 @@ extern "C" int cg_perm_data(const float *x, const int32_t *perm, float *out, int
 // ---------------------------------------------------------------------------
 // gconv-LSTM gates
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Gate nonlinearities on the special-function unit (ex2 + fast reciprocal: absolute error ~1e-7, two orders below the
+// parity tolerance); the precise expf / tanhf / division sequences made the gate kernels instruction bound (~200
+// instructions per element).  tan (the fork's z gate) stays the precise tanf: it is ill-conditioned near its poles.
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_(float v) { return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f); }
 
 __global__ void __launch_bounds__(256)
 k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ pre2, const float *__restrict__ bias,
@@ -536,12 +540,12 @@ k_lstm_gates_fwd(const float *__restrict__ pre, const float *__restrict__ pre2, 
             af += q[2 * H + h];
             ao += q[3 * H + h];
         }
-        const float z = variant == 0 ? tanf(az) : tanhf(az);
-        const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
+        const float z = variant == 0 ? tanf(az) : tanhf_(az);
+        const float o = variant == 0 ? tanhf_(ao) : sigmoidf_(ao);
         const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
         const float cn = fg * c[i] + ig * z;
         new_c[i] = cn;
-        new_h[i] = o * tanhf(cn);
+        new_h[i] = o * tanhf_(cn);
     }
 }
 
@@ -568,10 +572,10 @@ k_lstm_gates_bwd(const float *__restrict__ pre, const float *__restrict__ pre2, 
             af += q[2 * H + h];
             ao += q[3 * H + h];
         }
-        const float z = variant == 0 ? tanf(az) : tanhf(az);
-        const float o = variant == 0 ? tanhf(ao) : sigmoidf_(ao);
+        const float z = variant == 0 ? tanf(az) : tanhf_(az);
+        const float o = variant == 0 ? tanhf_(ao) : sigmoidf_(ao);
         const float ig = sigmoidf_(ai), fg = sigmoidf_(af);
-        const float tc = tanhf(new_c[i]);
+        const float tc = tanhf_(new_c[i]);
         const float gh = g_h ? g_h[i] : 0.f;
         const float dcn = (g_c ? g_c[i] : 0.f) + gh * o * (1.f - tc * tc);
         const float d_o = gh * tc;

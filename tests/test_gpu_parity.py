@@ -1209,3 +1209,39 @@ def test_csr_densify_matches_scipy_toarray(ops):
     va = dev(np.array([1.0, 2.0, 4.0, 8.0], np.float32))
     got = ops.csr_densify(ip, ix, va, 4).cpu().numpy()
     assert np.array_equal(got, np.array([[4, 0, 3, 0], [0, 8, 0, 0]], np.float32))
+
+
+def test_c5_shaped_streaming_properties(ops):
+    """BASELINE config C5's operator family at 2^17 vertices (Morton-ordered 16-NN graph, ~18 entries per row, C = 64;
+    the bench runs 2^20): the three streaming step forms agree bit for bit (zero weights of the row blocks add exact
+    zeros and the summation order is the stored column order in all of them), the basis is linear in X, and
+    <T_k(L~) x, g> = <x, T_k(L~^T) g> for every k (no oracle needed at this size)."""
+    import os
+    from benchmarks import workloads
+    L = workloads.knn_graph_laplacian(17, 16, 'morton')
+    Lr = ops.rescale_csr(L, 2)
+    h = ops.GraphHandle(Lr)
+    M, C, K = Lr.shape[0], 64, 6
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(M, C, device='cuda', generator=gen)
+    g = torch.randn(M, C, device='cuda', generator=gen)
+    outs = {}
+    for name, env in (('tiled', {}), ('blocks', {'CG_SPMM_TILE': '0'}), ('csr', {'CG_SPMM_BLOCK': '0'})):
+        os.environ.update(env)
+        try:
+            outs[name] = ops.cheb_basis(h, x, K, flags=1)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    assert torch.equal(outs['tiled'], outs['blocks']) and torch.equal(outs['tiled'], outs['csr'])
+    B = outs['tiled']
+    x2 = torch.randn(M, C, device='cuda', generator=gen)
+    B2 = ops.cheb_basis(h, x2, K, flags=1)
+    B12 = ops.cheb_basis(h, 1.5 * x - 0.25 * x2, K, flags=1)
+    close(B12, (1.5 * B - 0.25 * B2).cpu().numpy(), 2e-5)
+    Bt = ops.cheb_basis(h, g, K, transpose=True, flags=1)
+    for k in range(K):
+        lhs = float((B[k].double() * g.double()).sum())
+        rhs = float((x.double() * Bt[k].double()).sum())
+        scale = float(B[k].double().norm() * g.double().norm())
+        assert abs(lhs - rhs) <= 1e-6 * scale, (k, lhs, rhs)
