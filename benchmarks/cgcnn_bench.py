@@ -170,8 +170,10 @@ def run_ours(args, config):
         if world > 1:
             for p_ in model.store.parameters():                   # identical initial weights on every rank
                 torch.distributed.broadcast(p_.data, src=0)
-            model.grad_hook = (cgdist.OverlappedGradAllReducer(model.store.parameters(), average=True)
-                               if args.overlap_allreduce else cgdist.GradAllReducer(average=True))
+            kind = 'overlap' if args.overlap_allreduce else args.allreduce
+            model.grad_hook = (cgdist.OverlappedGradAllReducer(model.store.parameters(), average=True) if kind == 'overlap'
+                               else cgdist.DeferredGradAllReducer(model, average=True) if kind == 'deferred'
+                               else cgdist.GradAllReducer(average=True))
         raw, labels = workloads.cgcnn_batch(config, L, perm, batch, 99 + rank + seed)
         raw_host = torch.from_numpy(raw).pin_memory()
         labels_host = torch.from_numpy(labels).pin_memory()
@@ -323,7 +325,7 @@ def run_ours(args, config):
         'config': {'workload': cfg['workload'], 'name': config, 'batch_per_gpu': B, 'global_batch': B * world,
                    'precision': 'fp32 storage and recurrence; single-pass bf16 tensor-core products (opt-in --precision bf16, rtol 2e-2)' if getattr(args, 'precision', 'fp32') == 'bf16' else 'fp32 storage and recurrence; tensor-core products as bf16 hi+mid split x3 with fp32 '
                                 'accumulation (error <= 2^-16 relative, inside rtol 1e-4)',
-                   'parallelism': 'dp%d' % world, 'l2': 'flushed between timed iterations (256 MB fill)',
+                   'parallelism': 'dp%d' % world, 'allreduce': ('overlap' if args.overlap_allreduce else args.allreduce) if world > 1 else None, 'l2': 'flushed between timed iterations (256 MB fill)',
                    'timing': 'CUDA events per step on the launch stream, summed; max over ranks', 'launch': mode,
                    'e2e_input': 'sparse CSR batch (pinned indptr / indices / values) expanded on the device by cg_csr_densify' if config == 'c3' else 'dense pinned batch',
                    'e2e_path': 'GraphModel.pipelined_trainer: pinned host batch -> H2D on a copy stream (2 buffers) -> '

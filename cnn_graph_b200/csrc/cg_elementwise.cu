@@ -704,7 +704,9 @@ struct CgSgdTable {                 // replays them without any device-side tabl
     CgSgdEntry e[CG_SGD_MAX];
 };
 
-__global__ void __launch_bounds__(256) k_sgd_momentum(const __grid_constant__ CgSgdTable table, float lr, float momentum) {
+__global__ void __launch_bounds__(256) k_sgd_momentum(const __grid_constant__ CgSgdTable table, float lr, float momentum,
+                                                       const float *__restrict__ lr_dev) {
+    if (lr_dev != nullptr) lr = *lr_dev;      // learning rate read at run time (a replayed CUDA graph bakes kernel arguments)
     const CgSgdEntry e = table.e[blockIdx.y];
     const long long n4 = ((((uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.buf) & 15) == 0) ? e.n / 4 : 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -729,7 +731,14 @@ __global__ void __launch_bounds__(256) k_sgd_momentum(const __grid_constant__ Cg
     }
 }
 
+extern "C" int cg_sgd_momentum_dev(const void *host_table, int ntensors, long long max_numel, float lr, const float *dev_lr,
+                                   float momentum, void *stream);
 extern "C" int cg_sgd_momentum(const void *host_table, int ntensors, long long max_numel, float lr, float momentum, void *stream) {
+    return cg_sgd_momentum_dev(host_table, ntensors, max_numel, lr, nullptr, momentum, stream);
+}
+
+extern "C" int cg_sgd_momentum_dev(const void *host_table, int ntensors, long long max_numel, float lr, const float *dev_lr,
+                                   float momentum, void *stream) {
     CG_REQUIRE(host_table != nullptr && ntensors > 0, "cg_sgd_momentum: bad table (%d tensors)", ntensors);
     long long blocks = cg_ceil_div(cg_ceil_div(max_numel, 4), 256);
     if (blocks < 1) blocks = 1;
@@ -744,7 +753,7 @@ extern "C" int cg_sgd_momentum(const void *host_table, int ntensors, long long m
             CG_REQUIRE(tab.e[i].p && tab.e[i].g && tab.e[i].buf && tab.e[i].n >= 0, "cg_sgd_momentum: NULL tensor in record %d", t0 + i);
         }
         CgProfScope prof("sgd_momentum", (cudaStream_t)stream);
-        k_sgd_momentum<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(tab, lr, momentum);
+        k_sgd_momentum<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(tab, lr, momentum, dev_lr);
         CG_LAUNCH_CHECK();
     }
     return CG_OK;

@@ -131,6 +131,125 @@ class OverlappedGradAllReducer:
         self._handles = []
 
 
+class DeferredGradAllReducer:
+    """Data-parallel averaging that takes the LARGE gradients off the critical path without changing the trajectory.
+
+    After the backward pass of step t the small gradients are averaged (one flat all-reduce) and applied as usual; the
+    gradients of the variables with at least `min_numel` elements (cgcnn: the first dense weight, 97 % of the bytes) are
+    only copied aside.  Their all-reduce and momentum-SGD update run at the START of step t + 1 on a side stream, under
+    the graph-convolution forward kernels -- whose first kernel leaves SMs free, unlike the persistent backward kernels
+    that made an all-reduce overlapped with the backward pass slower -- and the model joins the side stream right before
+    the dense head first reads those variables (`join`).  Every variable therefore has received the update of step t
+    before step t + 1 uses it: same numbers as the plain reducer, step for step.
+
+    The update uses the learning rate of the step that produced the gradient, read from a device scalar so that a replayed
+    CUDA graph follows the staircase schedule.  `flush()` applies a pending update at once (evaluation, checkpoints).
+    `force=True` runs the deferral without a process group (single-process tests of the capture logic)."""
+
+    def __init__(self, model, min_numel=1 << 16, average=True, force=False):
+        self.model, self.average, self.force = model, average, force
+        params = list(model.store.parameters())
+        self.big = [p for p in params if p.numel() >= min_numel]
+        big_ids = {id(p) for p in self.big}
+        self.small = [p for p in params if id(p) not in big_ids]
+        self.bufs = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.big]
+        self.valid = False                     # a gradient is waiting in bufs
+        self.lr = None                         # learning rate of the step that produced it
+        dev = self.big[0].device if self.big else torch.device('cpu')
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        self._flat = GradAllReducer(average=average)
+        self._launched = False
+
+    def active(self):
+        return bool(self.big) and (self.force or (dist.is_initialized() and dist.get_world_size() > 1))
+
+    def set_lr(self, lr):
+        """Host side, outside any captured graph: the rate the next deferred update will read."""
+        if self.lr != lr:
+            self.lr = lr
+            self.lr_dev.fill_(float(lr))
+
+    # ---- pieces called by GraphModel.train_step
+    def begin_step(self):
+        if not self.active() or not self.valid:
+            return
+        if self.side is None:
+            self._apply()
+            return
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._apply()
+        self._launched = True
+        if not getattr(self.model, 'joins_deferred_update', False):
+            self.join()                        # the model does not say where it first reads the large variables
+
+    def join(self):
+        if self._launched:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._launched = False
+
+    def __call__(self, params=None):
+        """After the backward pass: average + keep the small gradients, set the large ones aside."""
+        if not self.active():
+            return
+        self.join()
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            self._flat(self.small)
+        for p, b in zip(self.big, self.bufs):
+            if p.grad is not None:
+                b.copy_(p.grad)
+                p.grad = None                  # the optimiser step that follows skips it
+        self.valid = True
+
+    def flush(self):
+        if self.active() and self.valid:
+            self.join()
+            self._apply()
+
+    # ---- internals
+    @torch.no_grad()
+    def _apply(self):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            for b in self.bufs:
+                if self.average and dist.get_backend() == 'nccl':
+                    dist.all_reduce(b, op=dist.ReduceOp.AVG)
+                else:
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+                    if self.average:
+                        b.div_(dist.get_world_size())
+        opt = self.model.optimizer
+        momentum = opt.param_groups[0].get('momentum', 0.0)
+        if hasattr(opt, 'apply'):              # ops.NativeMomentumSGD: one launch, rate from the device scalar
+            opt.apply(self.big, self.bufs, self.lr, momentum, lr_dev=self.lr_dev)
+        else:                                  # torch.optim.SGD (CPU / gloo tests): the same update by hand
+            for p, b in zip(self.big, self.bufs):
+                st = opt.state[p]
+                mb = st.get('momentum_buffer')
+                if momentum != 0:
+                    if mb is None:
+                        mb = st['momentum_buffer'] = torch.clone(b).detach()
+                    else:
+                        mb.mul_(momentum).add_(b)
+                    p.add_(mb, alpha=-self.lr)
+                else:
+                    p.add_(b, alpha=-self.lr)
+        self.valid = False
+
+    def snapshot(self):
+        return {'bufs': [b.clone() for b in self.bufs], 'valid': self.valid, 'lr': self.lr}
+
+    def restore(self, state):
+        with torch.no_grad():
+            for b, old in zip(self.bufs, state['bufs']):
+                b.copy_(old)
+        self.valid = state['valid']
+        self.lr = None
+        if state['lr'] is not None:
+            self.set_lr(state['lr'])
+
+
 def max_over_ranks(value, device):
     """Max of a python float over all ranks (device-side all-reduce)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -94,6 +94,9 @@ class GraphModel(object):
 
     def get_var(self, name):
         """Value of a variable by scoped name, e.g. 'conv1/weights' (lib/graph_model.py:199-204)."""
+        hook = getattr(self, 'grad_hook', None)
+        if hook is not None and hasattr(hook, 'flush'):
+            hook.flush()
         return self.store.vars[name].detach().cpu().numpy()
 
     # ------------------------------------------------------------------ step / loops
@@ -112,12 +115,17 @@ class GraphModel(object):
         for group in self.optimizer.param_groups:
             group['lr'] = self._current_lr()
         self.optimizer.zero_grad(set_to_none=True)
+        hook = getattr(self, 'grad_hook', None)
+        if hook is not None and hasattr(hook, 'begin_step'):
+            hook.begin_step()                            # deferred exchange + update of the previous step's large gradients
         out = self.inference(batch_data, self.dropout)
         loss = self.loss(out, batch_labels, self.regularization)
         loss.backward()
-        if getattr(self, 'grad_hook', None) is not None:
-            self.grad_hook(self.store.parameters())      # e.g. data-parallel all-reduce of the gradients
+        if hook is not None:
+            hook(self.store.parameters())                # e.g. data-parallel all-reduce of the gradients
         self.optimizer.step()
+        if hook is not None and hasattr(hook, 'set_lr') and not torch.cuda.is_current_stream_capturing():
+            hook.set_lr(self.optimizer.param_groups[0]['lr'])
         self.global_step += 1
         self.is_train = False
         return loss
@@ -130,6 +138,20 @@ class GraphModel(object):
         input buffers; the returned loss tensor is overwritten by the next replay."""
         lr = self._current_lr()
         key = (tuple(batch_data.shape), batch_data.dtype, tuple(batch_labels.shape), batch_labels.dtype, lr)
+        hook = getattr(self, 'grad_hook', None)
+        if hook is not None and hasattr(hook, 'begin_step') and hook.active() and not hook.valid:
+            # a deferred reducer has nothing pending yet (very first step): the captured graph always applies a pending
+            # update, so this one step runs eagerly and leaves one behind.  On a side stream: autograd binds the variables'
+            # AccumulateGrad nodes to the stream of their first use and keeps them alive (self.nets holds activations);
+            # bound to the legacy default stream they would break the capture that follows.
+            if getattr(self, '_eager_stream', None) is None:
+                self._eager_stream = torch.cuda.Stream(device=self.device)
+            cur, side = torch.cuda.current_stream(), self._eager_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                loss = self.train_step(batch_data, batch_labels)
+            cur.wait_stream(side)
+            return loss
         cap = getattr(self, '_captured', None)
         if cap is None or cap['key'] != key:
             cap = self._capture_step(batch_data, batch_labels, key)
@@ -138,6 +160,8 @@ class GraphModel(object):
         if batch_labels.data_ptr() != cap['y'].data_ptr():
             cap['y'].copy_(batch_labels, non_blocking=True)
         cap['graph'].replay()
+        if hook is not None and hasattr(hook, 'set_lr'):
+            hook.set_lr(lr)                              # the rate of THIS step, for the deferred update inside the next replay
         self.global_step += 1
         return cap['loss']
 
@@ -150,6 +174,8 @@ class GraphModel(object):
         snap_p = [q.detach().clone() for q in params]
         snap_s = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state.get(q, {}).items()}
                   for q in params]
+        hook = getattr(self, 'grad_hook', None)
+        snap_h = hook.snapshot() if hook is not None and hasattr(hook, 'snapshot') else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -171,6 +197,8 @@ class GraphModel(object):
                     elif k in old_s:
                         state[k] = old_s[k]
         self.global_step = step0
+        if snap_h is not None:
+            hook.restore(snap_h)
         self.optimizer.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         n0 = _native.lib().cg_launch_count()
@@ -224,6 +252,9 @@ class GraphModel(object):
         """Batched forward over a data set, last batch zero-padded (lib/graph_model.py:64-94)."""
         size = data.shape[0]
         outs, loss = [], 0.0
+        hook = getattr(self, 'grad_hook', None)
+        if hook is not None and hasattr(hook, 'flush'):
+            hook.flush()                                 # a deferred data-parallel update must land before the weights are read
         with torch.no_grad():
             for begin in range(0, size, self.batch_size):
                 end = min(begin + self.batch_size, size)

@@ -207,6 +207,8 @@ def l2_loss_sum(ws):
 
 
 class cgcnn(GraphConvOps, GraphModel):
+    joins_deferred_update = True       # _inference joins a deferred data-parallel update before the dense head (dist.py)
+
     """Graph CNN with Chebyshev filters.
 
     L: list of graph Laplacians (one per coarsening level); F, K, p: features, polynomial
@@ -290,6 +292,9 @@ class cgcnn(GraphConvOps, GraphModel):
                 self.nets['conv{}/pooling'.format(i + 1)] = x
         N, Mv, Fv = (int(d) for d in x.shape)
         x = x.reshape(N, Mv * Fv)
+        hook = getattr(self, 'grad_hook', None)
+        if hook is not None and hasattr(hook, 'join'):
+            hook.join()          # dist.DeferredGradAllReducer: the dense weights get their deferred update before this point
         for i, width in enumerate(self.M[:-1]):
             with self.variable_scope('fc{}'.format(i + 1)):
                 x = self.fc(x, width)

@@ -769,25 +769,31 @@ class NativeMomentumSGD(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum))
 
     @torch.no_grad()
+    def apply(self, params, grads, lr, momentum, lr_dev=None):
+        """buffer = momentum * buffer + grad; param -= lr * buffer for the given (param, grad) pairs in one launch; with
+        `lr_dev` (a one-element float32 device tensor) the rate is read on the device when the kernel runs."""
+        rec = []
+        for p, g in zip(params, grads):
+            st = self.state[p]
+            if 'momentum_buffer' not in st or st['momentum_buffer'] is None:
+                st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            if p.dtype != torch.float32 or g.dtype != torch.float32 or not p.is_contiguous() or not g.is_contiguous():
+                raise TypeError('NativeMomentumSGD: fp32 contiguous variables and gradients only')
+            rec += [p.data_ptr(), g.data_ptr(), st['momentum_buffer'].data_ptr(), p.numel()]
+        if not rec:
+            return
+        table = np.array(rec, dtype=np.int64)
+        check(_native.lib().cg_sgd_momentum_dev(table.ctypes.data, len(params), max(p.numel() for p in params), ctypes.c_float(lr),
+                                                ptr(lr_dev), ctypes.c_float(momentum), _stream()), 'cg_sgd_momentum_dev')
+
+    @torch.no_grad()
     def step(self, closure=None):
         for group in self.param_groups:
             ps = [p for p in group['params'] if p.grad is not None]
-            if not ps:
-                continue
-            rec = []
             for p in ps:
-                st = self.state[p]
-                if 'momentum_buffer' not in st or st['momentum_buffer'] is None:
-                    st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 if not p.grad.is_contiguous():
                     p.grad = p.grad.contiguous()
-                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous():
-                    raise TypeError('NativeMomentumSGD: fp32 contiguous variables only')
-                rec += [p.data_ptr(), p.grad.data_ptr(), st['momentum_buffer'].data_ptr(), p.numel()]
-            table = np.array(rec, dtype=np.int64)
-            check(_native.lib().cg_sgd_momentum(table.ctypes.data, len(ps), max(p.numel() for p in ps),
-                                                ctypes.c_float(group['lr']), ctypes.c_float(group['momentum']), _stream()),
-                  'cg_sgd_momentum')
+            self.apply(ps, [p.grad for p in ps], group['lr'], group['momentum'])
         return None
 
 

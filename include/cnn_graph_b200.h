@@ -305,6 +305,10 @@ int cg_softmax_xent(const float *dev_logits, const long long *dev_labels, float 
  * memory, device pointers inside; they travel as kernel arguments, 64 per launch); buffer = momentum * buffer + grad;
  * param -= lr * buffer.  max_numel sizes the grid.                                                                     */
 int cg_sgd_momentum(const void *host_table, int ntensors, long long max_numel, float lr, float momentum, void *stream);
+/* The same with the learning rate read from device memory when dev_lr is not NULL (a replayed CUDA graph bakes kernel
+ * arguments; the deferred data-parallel update of dist.DeferredGradAllReducer applies the PREVIOUS step's rate).      */
+int cg_sgd_momentum_dev(const void *host_table, int ntensors, long long max_numel, float lr, const float *dev_lr, float momentum,
+                        void *stream);
 
 /* Debug aids of the fused recurrence kernels.  cg_debug_fused_trace: device buffer [K][10] of int64 that receives
  * clock64 stamps of CTA 0's second group (NULL switches it off).  cg_debug_fused_plan_info: the plan of the most

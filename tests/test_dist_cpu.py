@@ -269,3 +269,72 @@ def test_row_partitioned_filter_on_subgroup():
         out = mgr.dict()
         mp.spawn(_subgroup_worker, args=(3, port, out), nprocs=3, join=True)
         assert dict(out) == {r: (True, True, True) for r in range(3)}
+
+
+def _deferred_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    from cnn_graph_b200 import dist as cgdist
+    cgdist.init_from_env('gloo')
+
+    class Store:
+        def __init__(self, ps):
+            self.ps = ps
+
+        def parameters(self):
+            return self.ps
+
+    class Model:
+        joins_deferred_update = True
+
+    def make():
+        g = torch.Generator().manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(40, 50, generator=g)), torch.nn.Parameter(torch.randn(7, generator=g)),
+              torch.nn.Parameter(torch.randn(3, 5, generator=g))]
+        m = Model()
+        m.store = Store(ps)
+        m.optimizer = torch.optim.SGD(ps, lr=0.1, momentum=0.9)
+        return m
+
+    def grads(step):
+        g = torch.Generator().manual_seed(100 * step + rank)
+        return [torch.randn(40, 50, generator=g), torch.randn(7, generator=g), torch.randn(3, 5, generator=g)]
+
+    lrs = [0.1, 0.1, 0.1, 0.05, 0.05, 0.025]
+    plain, deferred = make(), make()
+    flat = cgdist.GradAllReducer(average=True)
+    hook = cgdist.DeferredGradAllReducer(deferred, min_numel=1000)
+    assert hook.active() and len(hook.big) == 1 and len(hook.small) == 2
+    for step, lr in enumerate(lrs):
+        for m, h in ((plain, flat), (deferred, hook)):
+            for grp in m.optimizer.param_groups:
+                grp['lr'] = lr
+            m.optimizer.zero_grad(set_to_none=True)
+            if h is hook:
+                h.begin_step()
+                h.join()
+            for p_, g_ in zip(m.store.parameters(), grads(step)):
+                p_.grad = g_.clone()
+            h(m.store.parameters())
+            m.optimizer.step()
+            if h is hook:
+                h.set_lr(lr)
+        # the small variables agree after every step, the large one is exactly one update behind until flushed
+        ok_small = all(torch.allclose(a, b, rtol=0, atol=1e-6) for a, b in zip(plain.store.parameters()[1:], deferred.store.parameters()[1:]))
+        assert ok_small, step
+    assert hook.valid
+    hook.flush()
+    out[rank] = all(torch.allclose(a, b, rtol=0, atol=1e-6) for a, b in zip(plain.store.parameters(), deferred.store.parameters()))
+    cgdist.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_deferred_reducer_same_trajectory_world2():
+    """DeferredGradAllReducer: large gradients exchanged and applied at the start of the next step (with that gradient's own
+    learning rate, across staircase boundaries) -- same weights as the flat all-reduce after every step + flush."""
+    world, port = 2, _free_port()
+    with mp.Manager() as manager:
+        out = manager.dict()
+        mp.spawn(_deferred_worker, args=(world, port, out), nprocs=world, join=True)
+        assert all(out.get(r) for r in range(world)), dict(out)

@@ -1245,3 +1245,25 @@ def test_c5_shaped_streaming_properties(ops):
         rhs = float((x.double() * Bt[k].double()).sum())
         scale = float(B[k].double().norm() * g.double().norm())
         assert abs(lhs - rhs) <= 1e-6 * scale, (k, lhs, rhs)
+
+
+def test_deferred_reducer_graphed_trajectory_matches_plain_steps(c2):
+    """dist.DeferredGradAllReducer(force=True) on one process: the large gradients' update moved to the start of the next
+    step (side stream, device-side learning rate, captured into the step graph) gives the same weights as plain eager
+    steps -- across a learning-rate boundary of the staircase schedule and after flush()."""
+    from cnn_graph_b200 import dist as cgdist
+    rng = np.random.RandomState(3)
+    xs = [dev(rng.uniform(0, 1, (16, 992)).astype(np.float32)) for _ in range(7)]
+    ys = [dev(rng.randint(0, 10, 16).astype(np.int64)) for _ in range(7)]
+    ref = _small_cgcnn(c2, 5)
+    for x, y in zip(xs, ys):
+        ref.train_step(x, y)
+    for graphed in (False, True):
+        m = _small_cgcnn(c2, 5)
+        m.grad_hook = cgdist.DeferredGradAllReducer(m, min_numel=2000, force=True)
+        assert m.grad_hook.active() and len(m.grad_hook.big) >= 1 and len(m.grad_hook.small) >= 1
+        for x, y in zip(xs, ys):
+            (m.train_step_graphed if graphed else m.train_step)(x, y)
+        assert m.grad_hook.valid            # the last step's large gradient is still pending ...
+        for name in ref.store.vars:         # ... get_var flushes it
+            close(m.get_var(name), ref.get_var(name), 2e-5)
