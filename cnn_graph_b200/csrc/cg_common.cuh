@@ -202,6 +202,17 @@ int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int
                      long long a_mbs = 0);
 int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s);
 
+// Streaming form for a large left operand (cg_gemm_stream.cu): B split once per call into packed bf16 planes (workspace),
+// the fp32 A tiles fetched by bulk copies of one producer warp; K a multiple of 32.  CG_GEMM_STREAM=0 disables it.
+//   cg_run_gemm_stream returns CG_TRY_NEXT (nothing launched) when the tensor map of A cannot be encoded: take the next kernel
+constexpr int CG_TRY_NEXT = -77;
+size_t cg_gemm_stream_workspace(int M, int N, int K, int sm_count);
+bool cg_gemm_stream_eligible(const float *A, int M, int N, int K, int lda, int transA, int transB, int a_kblk, long long a_kbs,
+                             int b_kblk, int a_mblk, long long a_mbs, size_t workspace_bytes, int sm_count);
+int cg_run_gemm_stream(const float *A, const float *B, float *C, int M, int N, int K, int transA, int transB, int lda, int ldb,
+                       int ldc, const float *bias, int relu, int a_kblk, long long a_kbs, int b_kblk, int b_shi, int b_slo,
+                       void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t s, int a_mblk, long long a_mbs);
+
 // Input gradient by the adjoint (Clenshaw) recurrence with gy resident in tensor memory (cg_clenshaw.cu).
 bool cg_clenshaw_supported(const cg_graph *g, int N, int Fin, int Fout, int K);
 int cg_run_clenshaw(const cg_graph *g, const float *gy, const float *W, float *dx, int N, int Fin, int Fout, int K,

@@ -301,7 +301,7 @@ extern "C" size_t cg_gemm_f32_workspace_bytes(int M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) sms = cg_sm_budget(dev);
-    return std::max(gemm_plan(M, N, K, sms).ws, cg_gemm_pipe_workspace(M, N, K, sms));
+    return std::max(std::max(gemm_plan(M, N, K, sms).ws, cg_gemm_pipe_workspace(M, N, K, sms)), cg_gemm_stream_workspace(M, N, K, sms));
 }
 
 int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s) {
@@ -325,6 +325,11 @@ int cg_run_gemm(const float *A, const float *B, float *C, int M, int N, int K, i
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
     sms = cg_sm_budget(dev);
+    if (workspace && cg_gemm_stream_eligible(A, M, N, K, lda, transA, transB, a_kblk, a_kbs, b_kblk, 0, 0, workspace_bytes, sms)) {
+        const int rc = cg_run_gemm_stream(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, a_kblk, a_kbs, b_kblk, b_shi,
+                                          b_slo, workspace, workspace_bytes, sms, s, 0, 0);
+        if (rc != CG_TRY_NEXT) return rc;
+    }
     if (cg_gemm_pipe_eligible(A, B, M, N, K, lda, ldb, transA, transB, a_kblk, a_kbs, b_kblk))
         return cg_run_gemm_pipe(A, B, C, M, N, K, transA, transB, lda, ldb, ldc, bias, relu, a_kblk, a_kbs, b_kblk, b_shi,
                                 b_slo, workspace, workspace_bytes, sms, s);
@@ -386,6 +391,11 @@ int cg_run_gemm_mblocked(const float *A, const float *B, float *C, int M, int N,
     int dev = 0, sms = 148;
     CG_CHECK_CUDA(cudaGetDevice(&dev));
     sms = cg_sm_budget(dev);
+    if (workspace && cg_gemm_stream_eligible(A, M, N, K, lda, 1, 0, 0, 0, 0, a_mblk, a_mbs, workspace_bytes, sms)) {
+        const int rc = cg_run_gemm_stream(A, B, C, M, N, K, 1, 0, lda, ldb, ldc, nullptr, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes,
+                                          sms, s, a_mblk, a_mbs);
+        if (rc != CG_TRY_NEXT) return rc;
+    }
     return cg_run_gemm_pipe(A, B, C, M, N, K, 1, 0, lda, ldb, ldc, nullptr, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes, sms, s,
                             a_mblk, a_mbs);
 }

@@ -310,8 +310,8 @@ class GconvModel(GraphModel):
             return y * mask
         if keep >= 1:
             return y
-        mask = (torch.rand_like(y) < keep).to(y.dtype) / keep
-        return y * mask
+        # Bernoulli(keep) mask scaled by 1 / keep, as tf.nn.dropout: one fused launch forward, one backward
+        return torch.nn.functional.dropout(y, p=1.0 - keep, training=True)
 
     def glstm_layer(self, x, num_time_step, layer_count):
         """Stacked GConvLSTMCells unrolled over the frames (lib/gconv_lstm.py:609-627:
