@@ -97,6 +97,7 @@ _SIGNATURES = {
     'cg_debug_fused_trace': (c_int, [c_void_p]),
     'cg_debug_clenshaw_trace': (c_int, [c_void_p]),
     'cg_debug_fused_plan_info': (c_int, [c_void_p]),
+    'cg_debug_gemm_stream': (c_int, [c_int]),
     'cg_host_metis_one_level': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                         c_void_p, ctypes.POINTER(c_i64)]),
     'cg_host_metis_one_level_f64': (c_int, [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,

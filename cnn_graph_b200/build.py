@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcnn_graph_b200.so')
 
-SOURCES = ['cg_graph.cu', 'cg_spmm.cu', 'cg_gemm.cu', 'cg_elementwise.cu', 'cg_filter.cu', 'cg_fused.cu', 'cg_dw_umma.cu', 'cg_dw_planes.cu', 'cg_dw_thin.cu', 'cg_clenshaw.cu', 'cg_contract_umma.cu', 'cg_gemm_umma.cu', 'cg_gemm_pipe.cu', 'cg_gemm_stream.cu', 'cg_bmm.cu', 'cg_profile.cu', 'cg_umma_test.cu',
+SOURCES = ['cg_graph.cu', 'cg_spmm.cu', 'cg_gemm.cu', 'cg_elementwise.cu', 'cg_filter.cu', 'cg_fused.cu', 'cg_dw_umma.cu', 'cg_dw_planes.cu', 'cg_dw_thin.cu', 'cg_clenshaw.cu', 'cg_contract_umma.cu', 'cg_gemm_umma.cu', 'cg_gemm_pipe.cu', 'cg_gemm_stream.cu', 'cg_thin.cu', 'cg_bmm.cu', 'cg_profile.cu', 'cg_umma_test.cu',
            'cg_host.cpp']
 
 NVCC_FLAGS = (['-DCG_TRACE_BUILD'] if os.environ.get('CG_TRACE_BUILD') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -202,6 +202,15 @@ int cg_run_gemm_pipe(const float *A, const float *B, float *C, int M, int N, int
                      long long a_mbs = 0);
 int cg_gemm_reduce(const float *part, const float *bias, float *C, int M, int N, int ldc, int split, int relu, cudaStream_t s);
 
+// Short reductions (K * F <= 16) on the FFMA pipe, bound by the stream of y / T (cg_thin.cu); either stack layout.
+// CG_THIN=0 disables them.
+bool cg_thin_supported(int N, int M, int F, int J, int K);
+size_t cg_thin_dw_workspace(int N, int M, int F, int J, int K, int sm_count);
+int cg_run_thin_contract(const float *stack, const float *W, float *y, int N, int M, int F, int J, int K, bool sample_major,
+                         int sm_count, cudaStream_t s);
+int cg_run_thin_dw(const float *stack, const float *T, float *dW, int N, int M, int F, int J, int K, bool sample_major,
+                   float *workspace, int sm_count, cudaStream_t s);
+
 // Streaming form for a large left operand (cg_gemm_stream.cu): B split once per call into packed bf16 planes (workspace),
 // the fp32 A tiles fetched by bulk copies of one producer warp; K a multiple of 32.  CG_GEMM_STREAM=0 disables it.
 //   cg_run_gemm_stream returns CG_TRY_NEXT (nothing launched) when the tensor map of A cannot be encoded: take the next kernel

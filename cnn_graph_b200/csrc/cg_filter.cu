@@ -53,7 +53,8 @@ static size_t dw_workspace(const cg_graph *g, int N, int Fa, int Fb, int K) {
     const size_t d = cg_dw_planes_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
     const size_t e = cg_dw_thin_workspace(R, Fa, Fb, K, g->sm_count, g->smem_optin);
     const size_t f = std::max(dw_allk_workspace(R, Fa, Fb, K), dw_allk_workspace(R, Fb, Fa, K));
-    return std::max(std::max(a, std::max(d, std::max(e, f))), std::max(b, c));
+    const size_t t = cg_thin_dw_workspace(N, g->M, Fa, Fb, K, g->sm_count);
+    return std::max(std::max(std::max(a, t), std::max(d, std::max(e, f))), std::max(b, c));
 }
 
 // stack^T x plain for a scalar-signal stack (first layers): streaming FFMA kernel
@@ -68,6 +69,8 @@ static int run_dw(const cg_graph *g, const float *stack, const float *T, float *
                   bool swap, bool sample_major, float *part, int flags, cudaStream_t s) {
     if (thin_ok(g, stack, T, part, N, Fa, Fb, K, swap, sample_major, flags))
         return cg_run_dw_thin(stack, T, dW, (long long)N * g->M, Fb, K, part, g->sm_count, g->smem_optin, s);
+    if (!swap && !(flags & CG_FILTER_NO_FUSED) && cg_thin_supported(N, g->M, Fa, Fb, K))      // K * Fa <= 16, either stack layout
+        return cg_run_thin_dw(stack, T, dW, N, g->M, Fa, Fb, K, sample_major, part, g->sm_count, s);
     const bool tc = !(flags & (CG_FILTER_NO_FUSED | CG_FILTER_FORCE_STREAMING)) &&
                     cg_dw_umma_supported(N, g->M, Fa, Fb, K, g->sm_count, g->smem_optin) &&
                     ((((uintptr_t)stack | (uintptr_t)T | (uintptr_t)part) & 15) == 0);
@@ -224,8 +227,10 @@ extern "C" int cg_cheb_filter_fwd_ex(const cg_graph_t *g, const float *x, const 
         rc = cg_run_basis_samples(g, 0, x, st, N, Fin, K, s);
         if (rc != CG_OK) return rc;
         if (!(flags & CG_FILTER_NO_FUSED) && (((uintptr_t)y) & 15) == 0 &&
-            cg_contract_umma_supported(N, M, Fin, Fout, K, g->smem_optin))
+            cg_contract_umma_supported(N, M, Fin, Fout, K, g->smem_optin))      // also the arithmetic of the fused first layer
             return cg_run_contract_umma(st, W, y, N, M, Fin, Fout, K, g->sm_count, g->smem_optin, s);
+        if (!(flags & CG_FILTER_NO_FUSED) && cg_thin_supported(N, M, Fin, Fout, K))     // K * Fin <= 16: bound by the stream of y
+            return cg_run_thin_contract(st, W, y, N, M, Fin, Fout, K, true, g->sm_count, s);
         if (!(flags & CG_FILTER_NO_FUSED) && (int64_t)N * M < (int64_t)INT32_MAX) {
             // wide outputs (Fout > 128, e.g. the 4H gates of the gconv-LSTM): general tensor-core GEMM over the
             // K-blocked basis, q = k*Fin + f  <->  W row f*K + k

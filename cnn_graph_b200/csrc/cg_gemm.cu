@@ -174,6 +174,11 @@ int cg_run_contract(const float *stack, const float *W, float *y, int N, int M, 
                     bool w_transposed, bool sample_major, cudaStream_t s) {
     const int64_t R = (int64_t)N * M;
     if (R == 0 || J == 0) return CG_OK;
+    if (!w_transposed && cg_thin_supported(N, M, F, J, K)) {
+        int dev = 0;
+        CG_CHECK_CUDA(cudaGetDevice(&dev));
+        return cg_run_thin_contract(stack, W, y, N, M, F, J, K, sample_major, cg_sm_budget(dev), s);
+    }
     const int vecA = (F % 4 == 0) && ((((uintptr_t)stack) & 15) == 0);
     const unsigned gx = (unsigned)cg_ceil_div(R, CT_BM);
     CgProfScope prof("contract", s);

@@ -428,13 +428,13 @@ static StreamPlan stream_plan(int M, int N, int K, bool ta, int sm_count) {
     return pl;
 }
 
+static int g_stream_on = -1;         // -1: not read yet (environment CG_GEMM_STREAM, default on)
 static bool stream_enabled() {
-    static int on = -1;
-    if (on < 0) {
+    if (g_stream_on < 0) {
         const char *e = getenv("CG_GEMM_STREAM");
-        on = (e && e[0] == '0') ? 0 : 1;
+        g_stream_on = (e && e[0] == '0') ? 0 : 1;
     }
-    return on == 1;
+    return g_stream_on == 1;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
@@ -477,6 +477,12 @@ static bool encode_map(CUtensorMap *map, const float *A, const cuuint64_t *dims,
 }
 
 }  // namespace
+
+extern "C" int cg_debug_gemm_stream(int on) {
+    const int before = stream_enabled() ? 1 : 0;
+    if (on >= 0) g_stream_on = on ? 1 : 0;
+    return before;
+}
 
 // shapes worth a packing launch: at least four row tiles re-use the packed B.  Measured (C4, weight gradient with M = 384
 // and a 105 MB B): packing costs 0.11 ms per step and saves 0.07.  CG_GEMM_STREAM_MIN_M overrides, for experiments.

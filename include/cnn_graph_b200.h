@@ -317,6 +317,10 @@ int cg_sgd_momentum_dev(const void *host_table, int ntensors, long long max_nume
 int cg_debug_fused_trace(long long *dev_buf);
 int cg_debug_clenshaw_trace(long long *dev_buf);     /* same for the row-block Clenshaw kernel */
 int cg_debug_fused_plan_info(int *info8);
+/* Switch of the streaming GEMM (cg_gemm_stream.cu; environment CG_GEMM_STREAM, default on): on = 1 / 0 sets it, on < 0 only
+ * queries; returns the previous setting.  With it off cg_gemm_f32 and the filter contractions take the pipelined
+ * kernel (cg_gemm_pipe.cu); the two produce bit-identical results (same split, same MMA order).                     */
+int cg_debug_gemm_stream(int on);
 
 /* ---- host-side native loops of the coarsening -------------------------- */
 /* lib/coarsening.py:119-165 (metis_one_level): greedy matching, float32

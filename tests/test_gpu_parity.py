@@ -751,6 +751,30 @@ def test_gemm_f32_tensor_core(ops, M, N, K, transA, transB):
     close(got, torch.relu(ref + bias.double()).cpu().numpy())
 
 
+@pytest.mark.parametrize('M,N,K', [(20000, 512, 384), (1024, 512, 3968), (2560, 128, 1536), (5000, 384, 512), (777, 40, 96)])
+@pytest.mark.parametrize('transA,transB', [(False, False), (False, True), (True, False), (True, True)])
+def test_streaming_gemm_bit_equal_to_pipelined(ops, M, N, K, transA, transB):
+    """cg_gemm_stream.cu (tensor-map A tiles, B packed once) against cg_gemm_pipe.cu on the same operands: the same
+    bf16 hi/mid split and the same MMA order, so every bit of the result agrees (ragged M / N tiles, split-K, column
+    tiles of 192)."""
+    from cnn_graph_b200 import _native
+    lib = _native.lib()
+    torch.manual_seed(M + N + K)
+    A = torch.randn((K, M) if transA else (M, K), device='cuda')
+    B = torch.randn((N, K) if transB else (K, N), device='cuda')
+    bias = torch.randn(N, device='cuda')
+    before = lib.cg_debug_gemm_stream(1)
+    try:
+        got = ops.gemm(A, B, transA=transA, transB=transB, bias=bias, relu=True)
+        lib.cg_debug_gemm_stream(0)
+        want = ops.gemm(A, B, transA=transA, transB=transB, bias=bias, relu=True)
+    finally:
+        lib.cg_debug_gemm_stream(before)
+    assert torch.equal(got, want)
+    ref = (A.double().t() if transA else A.double()) @ (B.double().t() if transB else B.double())
+    close(got, torch.relu(ref + bias.double()).cpu().numpy())
+
+
 def test_linear_layer_gradients(ops):
     torch.manual_seed(3)
     x = torch.randn(64, 200, device='cuda', requires_grad=True)
