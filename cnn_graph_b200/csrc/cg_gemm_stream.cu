@@ -12,8 +12,9 @@
 //     copy engine) into a raw ring, issued by one elected producer thread;
 //   * the 16 converter warps only read their 2 x 16 bytes back, split them and store the half octets: same values,
 //     same MMA order as cg_gemm_pipe.cu, so the results are bit-identical to that kernel's.
-// Restrictions (the caller falls back to cg_gemm_pipe.cu otherwise): K a multiple of 32, K blocks multiples of 32, row
-// blocks powers of two >= 32, 16-byte aligned A with a leading dimension that is a multiple of 4.
+// Restrictions (the caller falls back to cg_gemm_pipe.cu otherwise): K blocks multiples of 32, row blocks powers of two
+// >= 32, 16-byte aligned A with a leading dimension that is a multiple of 4.  A K tail needs nothing: the tensor copy
+// zero-fills A beyond K and k_pack_b zero-fills B.
 #include <cuda.h>
 
 #include <algorithm>
@@ -31,7 +32,7 @@ constexpr int ST = SC + SE + 64;        // + issue warp + producer warp
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int MAX_STAGES = 6;
-constexpr int MAX_RAW = 4;
+constexpr int MAX_RAW = 8;
 constexpr uint32_t RAW_BYTES = BM * BK * 4;         // one stage of fp32 A
 constexpr uint32_t MN_SBO = BK * 16 + 32;           // row-contiguous A: stride between 8-row groups (padded)
 constexpr uint32_t KC_LBO = BM * 16 + 32;           // K-contiguous A: stride between k octets (padded)
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(ST, 1) k_gemm_stream(const __grid_constant__ C
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int m0, n0, tn, k_beg, k_end, sp;
             item(w, m0, n0, tn, k_beg, k_end, sp);
-            total += (k_end - k_beg) / BK;
+            total += (k_end - k_beg + BK - 1) / BK;
         }
         // this thread's two 16-byte pieces of the raw tile and the half octets they become
         uint32_t src, src_step, dst;
@@ -233,13 +234,13 @@ __global__ void __launch_bounds__(ST, 1) k_gemm_stream(const __grid_constant__ C
         // =========================== producer warp (one elected thread) ===================
         if (umma::elect_one()) {
             const uint32_t bstage = 2u * p.b_plane;
-            const int nks = p.K / BK;
+            const int nks = (p.K + BK - 1) / BK;
             int slot = 0, rs = 0;
             uint32_t use = 0, ruse = 0;
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 int m0, n0, tn, k_beg, k_end, sp;
                 item(w, m0, n0, tn, k_beg, k_end, sp);
-                const int nst = (k_end - k_beg) / BK;
+                const int nst = (k_end - k_beg + BK - 1) / BK;
                 const unsigned char *bsrc = p.Bp + ((size_t)tn * nks + (size_t)(k_beg / BK)) * bstage;
                 for (int s = 0; s < nst; ++s) {
                     const int k0 = k_beg + s * BK;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(ST, 1) k_gemm_stream(const __grid_constant__ C
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++it) {
             int m0, n0, tn, k_beg, k_end, sp;
             item(w, m0, n0, tn, k_beg, k_end, sp);
-            const int nst = (k_end - k_beg) / BK;
+            const int nst = (k_end - k_beg + BK - 1) / BK;
             const int ab = it & 1;
             if (it >= 2) wait_warp<64>(acc_free + ab, (uint32_t)(((it >> 1) - 1) & 1), lane);
             umma::fence_after_sync();
@@ -412,19 +413,28 @@ static StreamPlan stream_plan(int M, int N, int K, bool ta, int sm_count) {
     pp.off_b = 2 * pp.a_plane;
     pp.stage_bytes = (uint32_t)cg_align_up(2 * pp.a_plane + 2 * pp.b_plane, 128);
     const size_t ep = (size_t)(SE / 32) * EP_BYTES;
-    const size_t budget = (size_t)227 * 1024 - ep - 256;
-    // the raw ring is what hides the HBM latency of A: four stages (64 KB in flight) when three operand stages still fit
-    pl.nraw = (budget - (size_t)MAX_RAW * RAW_BYTES) / pp.stage_bytes >= 3 ? MAX_RAW : 3;
+    const size_t budget = (size_t)227 * 1024 - ep - 512;
+    // Raw stages hide the HBM latency of A, operand stages the conversion -> MMA -> release hand-over.  Measured at the C5
+    // contraction shape (BN = 64), operand + raw stages: 6 + 4 1.13 ms, 5 + 5 1.10 ms, 4 + 6 1.27 ms, 3 + 8 1.56 ms -- the
+    // hand-over needs the depth more than the copies do.  CG_GEMM_STREAM_RAW overrides the raw depth (experiments).
+    static int raw_env = -1;
+    if (raw_env < 0) {
+        const char *e = getenv("CG_GEMM_STREAM_RAW");
+        raw_env = e ? std::min(MAX_RAW, std::max(2, atoi(e))) : 0;
+    }
+    int raw_want = raw_env > 0 ? raw_env : ((budget - 5u * RAW_BYTES) / pp.stage_bytes >= 5 ? 5 : 4);
+    if ((budget - (size_t)raw_want * RAW_BYTES) / pp.stage_bytes < 3) raw_want = 3;
+    pl.nraw = raw_want;
     pl.nstage = (int)std::min<size_t>(MAX_STAGES, (budget - (size_t)pl.nraw * RAW_BYTES) / pp.stage_bytes);
     pp.off_raw = (uint32_t)pl.nstage * pp.stage_bytes;
     pp.off_ep = pp.off_raw + (uint32_t)pl.nraw * RAW_BYTES;
     pp.off_bar = pp.off_ep + (uint32_t)ep;
-    pl.smem = pp.off_bar + 256;
+    pl.smem = pp.off_bar + 512;
     pp.tmem_cols = 32;
     while (pp.tmem_cols < 2u * (uint32_t)pl.BN) pp.tmem_cols *= 2;
     pp.tiles_n = tiles_n;
     pl.ws_part = pl.split > 1 ? cg_align_up(sizeof(float) * (size_t)pl.split * M * N, 256) : 0;
-    pl.ws_pack = (size_t)tiles_n * (size_t)(K / BK) * 2 * pp.b_plane;
+    pl.ws_pack = (size_t)tiles_n * (size_t)cg_ceil_div(K, BK) * 2 * pp.b_plane;
     return pl;
 }
 
@@ -492,7 +502,7 @@ static bool stream_shape(int M, int N, int K) {
         const char *e = getenv("CG_GEMM_STREAM_MIN_M");
         min_m = e ? std::max(1, atoi(e)) : 4 * BM;
     }
-    return stream_enabled() && M >= min_m && N >= 1 && K >= BK && (K % BK) == 0;
+    return stream_enabled() && M >= min_m && N >= 1 && K >= BK;
 }
 
 size_t cg_gemm_stream_workspace(int M, int N, int K, int sm_count) {
@@ -560,7 +570,7 @@ int cg_run_gemm_stream(const float *A, const float *B, float *C, int M, int N, i
         if (!encode_map(&map, A, dims, strides, box, estr)) return CG_TRY_NEXT;
     }
     unsigned char *packed = reinterpret_cast<unsigned char *>(workspace) + pl.ws_part;
-    const int nks = K / BK;
+    const int nks = (int)cg_ceil_div(K, BK);
     {
         CgProfScope prof("gemm_pack_b", s);
         const long long total = (long long)pl.pp.tiles_n * nks * 4 * pl.BN;

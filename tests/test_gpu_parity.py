@@ -751,7 +751,8 @@ def test_gemm_f32_tensor_core(ops, M, N, K, transA, transB):
     close(got, torch.relu(ref + bias.double()).cpu().numpy())
 
 
-@pytest.mark.parametrize('M,N,K', [(20000, 512, 384), (1024, 512, 3968), (2560, 128, 1536), (5000, 384, 512), (777, 40, 96)])
+@pytest.mark.parametrize('M,N,K', [(20000, 512, 384), (1024, 512, 3968), (2560, 128, 1536), (5000, 384, 512), (777, 40, 96),
+                                   (1000, 36, 200), (640, 20, 100)])       # K tails: zero-filled by the tensor copy
 @pytest.mark.parametrize('transA,transB', [(False, False), (False, True), (True, False), (True, True)])
 def test_streaming_gemm_bit_equal_to_pipelined(ops, M, N, K, transA, transB):
     """cg_gemm_stream.cu (tensor-map A tiles, B packed once) against cg_gemm_pipe.cu on the same operands: the same
