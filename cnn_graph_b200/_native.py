@@ -79,6 +79,7 @@ _SIGNATURES = {
     'cg_softmax_xent': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'cg_sgd_momentum': (c_int, [c_void_p, c_int, c_i64, c_float, c_float, c_void_p]),
     'cg_sgd_momentum_dev': (c_int, [c_void_p, c_int, c_i64, c_float, c_void_p, c_float, c_void_p]),
+    'cg_adam': (c_int, [c_void_p, c_int, c_i64, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     'cg_lstm_gates2_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
                                    c_void_p]),
     'cg_lstm_gates2_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -760,6 +760,79 @@ extern "C" int cg_sgd_momentum_dev(const void *host_table, int ntensors, long lo
 }
 
 
+// Adam (lib/graph_model.py:293 tf.train.AdamOptimizer; here with torch.optim.Adam's arithmetic, which the host model used
+// before): every variable in ONE launch.  table[t] = {param, grad, exp_avg, exp_avg_sq, element count}.  The step count
+// lives on the device (state[0]; a replayed CUDA graph bakes kernel arguments): every block reads it when it starts, the
+// block that finishes last (ticket in state[1]) advances it -- no block can still be waiting to read by then.
+struct CgAdamEntry {
+    float *p;
+    const float *g;
+    float *m, *v;
+    long long n;
+};
+constexpr int CG_ADAM_MAX = 48;
+struct CgAdamTable {
+    CgAdamEntry e[CG_ADAM_MAX];
+};
+
+__global__ void __launch_bounds__(256) k_adam(const __grid_constant__ CgAdamTable table, float lr, float beta1, float beta2, float eps,
+                                               int *__restrict__ state, int bump) {
+    __shared__ float coef[2];
+    if (threadIdx.x == 0) {
+        const int t = *reinterpret_cast<volatile int *>(state) + 1;
+        coef[0] = (float)((double)lr / (1.0 - pow((double)beta1, (double)t)));      // step size
+        coef[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));         // 1 / sqrt(bias correction 2)
+    }
+    __syncthreads();
+    const float step_size = coef[0], inv_bc2 = coef[1];
+    const CgAdamEntry e = table.e[blockIdx.y];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += stride) {
+        const float g = e.g[i];
+        float m = e.m[i], v = e.v[i];
+        m = fmaf(1.f - beta1, g - m, m);                        // exp_avg.lerp_(grad, 1 - beta1)
+        v = fmaf(1.f - beta2, g * g, beta2 * v);                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        e.m[i] = m;
+        e.v[i] = v;
+        e.p[i] -= step_size * (m / (sqrtf(v) * inv_bc2 + eps));
+    }
+    if (bump) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned total = gridDim.x * gridDim.y;
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(state + 1), 1u);
+            if (ticket == total - 1) {
+                state[0] = state[0] + 1;
+                state[1] = 0;
+            }
+        }
+    }
+}
+
+extern "C" int cg_adam(const void *host_table, int ntensors, long long max_numel, float lr, float beta1, float beta2, float eps,
+                       int *dev_state, void *stream) {
+    CG_REQUIRE(host_table != nullptr && ntensors > 0 && dev_state != nullptr, "cg_adam: bad table (%d tensors) or NULL state", ntensors);
+    long long blocks = cg_ceil_div(max_numel, 1024);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;
+    const CgAdamEntry *src = reinterpret_cast<const CgAdamEntry *>(host_table);
+    for (int t0 = 0; t0 < ntensors; t0 += CG_ADAM_MAX) {
+        const int n = ntensors - t0 < CG_ADAM_MAX ? ntensors - t0 : CG_ADAM_MAX;
+        CgAdamTable tab;
+        memset(&tab, 0, sizeof(tab));
+        for (int i = 0; i < n; ++i) {
+            tab.e[i] = src[t0 + i];
+            CG_REQUIRE(tab.e[i].p && tab.e[i].g && tab.e[i].m && tab.e[i].v && tab.e[i].n >= 0, "cg_adam: NULL tensor in record %d", t0 + i);
+        }
+        CgProfScope prof("adam", (cudaStream_t)stream);
+        k_adam<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(tab, lr, beta1, beta2, eps, dev_state,
+                                                                                      t0 + n >= ntensors ? 1 : 0);
+        CG_LAUNCH_CHECK();
+    }
+    return CG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sparse input batches (lib/graph_model.py:150-151 densifies scipy batches on the host and feeds
 // the dense array): the CSR batch travels to the device as it is (indptr, indices, values: ~1 % of the dense bytes

@@ -52,7 +52,11 @@ class GraphModel(object):
 
     def _make_optimizer(self):
         # lib/graph_model.py:293 -- the fork trains with Adam at the (decayed) learning rate
-        return torch.optim.Adam(self.store.parameters(), lr=self.learning_rate, capturable=torch.cuda.is_available())
+        params = list(self.store.parameters())
+        if params and all(q.is_cuda and q.dtype == torch.float32 for q in params):
+            from .. import ops                                   # the whole Adam step in one native launch
+            return ops.NativeAdam(params, lr=self.learning_rate)
+        return torch.optim.Adam(params, lr=self.learning_rate, capturable=torch.cuda.is_available())
 
     def _current_lr(self):
         # tf.train.exponential_decay(..., staircase=True), lib/graph_model.py:282-284

@@ -797,6 +797,44 @@ class NativeMomentumSGD(torch.optim.Optimizer):
         return None
 
 
+class NativeAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (no weight decay, no amsgrad) with the whole step in ONE native launch (cg_adam).
+    The step count lives on the device next to the first variable's moments, so a captured CUDA graph keeps counting
+    when it is replayed (what torch needs ``capturable=True`` and ~25 small launches per step for)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.grad is not None]
+            if not ps:
+                continue
+            rec = []
+            for p in ps:
+                if not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError('NativeAdam: fp32 contiguous variables and gradients only')
+                st = self.state[p]
+                if 'exp_avg' not in st:
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                rec += [p.data_ptr(), p.grad.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), p.numel()]
+            # {steps done, scratch}: kept in the state of the group's first variable, so whatever snapshots / restores the
+            # optimiser state (GraphModel._capture_step) carries the step count along
+            head = self.state[group['params'][0]]
+            if 'step_state' not in head:
+                head['step_state'] = torch.zeros(2, dtype=torch.int32, device=ps[0].device)
+            table = np.array(rec, dtype=np.int64)
+            b1, b2 = group['betas']
+            check(_native.lib().cg_adam(table.ctypes.data, len(ps), max(p.numel() for p in ps), ctypes.c_float(group['lr']),
+                                        ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(group['eps']),
+                                        ptr(head['step_state']), _stream()), 'cg_adam')
+        return None
+
+
 # ---------------------------------------------------------------------------------------
 # sparse input batches
 # ---------------------------------------------------------------------------------------

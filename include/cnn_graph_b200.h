@@ -310,6 +310,14 @@ int cg_sgd_momentum(const void *host_table, int ntensors, long long max_numel, f
 int cg_sgd_momentum_dev(const void *host_table, int ntensors, long long max_numel, float lr, const float *dev_lr, float momentum,
                         void *stream);
 
+/* Adam step of every variable in one launch (lib/graph_model.py:293: the fork trains the gconv-LSTM models with
+ * tf.train.AdamOptimizer; arithmetic of torch.optim.Adam: m += (1-b1)(g-m), v = b2 v + (1-b2) g^2,
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).  host_table: ntensors records of five 64-bit words
+ * {param, grad, exp_avg, exp_avg_sq (device pointers), element count}; dev_state: two int32 on the device, zero before
+ * the first step: [0] = steps done (advanced by the kernel, so a replayed CUDA graph keeps counting), [1] = scratch.  */
+int cg_adam(const void *host_table, int ntensors, long long max_numel, float lr, float beta1, float beta2, float eps,
+            int *dev_state, void *stream);
+
 /* Debug aids of the fused recurrence kernels.  cg_debug_fused_trace: device buffer [K][10] of int64 that receives
  * clock64 stamps of CTA 0's second group (NULL switches it off).  cg_debug_fused_plan_info: the plan of the most
  * recent fused forward ([0..3]) and Clenshaw ([4..7]) launch: {row-block gather used, samples per group, items per

@@ -13,10 +13,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 echo "launch list exit $?"
 # the native kernels of ONE step (the 5th of the process: after the eager count, warm-up and capture-free steps)
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:k_(cheb_fused|cheb_clenshaw|dw_planes|dw_umma|dw_thin|contract_umma|basis_onchip|gemm_pipe|gemm_umma|bias_act_pool|softmax_xent|sgd_momentum)' -s 60 -c 20 \
+    -k 'regex:k_(cheb_fused|cheb_clenshaw|dw_planes|dw_umma|dw_thin|contract_umma|basis_onchip|gemm_pipe|gemm_stream|pack_b|gemm_umma|bias_act_pool|softmax_xent|sgd_momentum)' -s 66 -c 22 \
     -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_f_$TAG.log 2>&1
 echo "full capture exit $?"; tail -1 $OUT/ncu_f_$TAG.log
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_spmm' -s 40 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_(spmm|gemm_stream)' -s 40 -c 4 \
     -o $OUT/prof_c5_$TAG -f python bench.py --config c5 --no-cpu-baseline --steps 1 --warmup 1 > $OUT/ncu_c5_$TAG.log 2>&1
 echo "c5 capture exit $?"
 ls -la $OUT/*.ncu-rep

@@ -17,7 +17,7 @@ COLS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__shared_mem_per_block_dynamic']
 # profile-scope names of bench.py (cg_profile_*) for the kernels whose DRAM traffic the roofline line quotes
 SCOPE = {'k_cheb_fused': 'fused_fwd', 'k_cheb_clenshaw': 'clenshaw_dx', 'k_dw_planes': 'dw_planes', 'k_dw_umma': 'dw_umma', 'k_dw_thin': 'dw_thin',
-         'k_contract_umma': 'contract_umma', 'k_gemm_pipe': 'gemm_pipe', 'k_gemm_umma': 'gemm_umma', 'k_basis_onchip': 'basis_onchip',
+         'k_contract_umma': 'contract_umma', 'k_gemm_pipe': 'gemm_pipe', 'k_gemm_stream': 'gemm_pipe', 'k_pack_b': 'gemm_pack_b', 'k_thin_contract': 'thin_contract', 'k_thin_dw': 'thin_dw', 'k_gemm_umma': 'gemm_umma', 'k_basis_onchip': 'basis_onchip',
          'k_spmm_tile_p': 'spmm_step', 'k_spmm_step': 'spmm_step'}
 
 

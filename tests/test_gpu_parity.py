@@ -776,6 +776,25 @@ def test_streaming_gemm_bit_equal_to_pipelined(ops, M, N, K, transA, transB):
     close(got, torch.relu(ref + bias.double()).cpu().numpy())
 
 
+def test_native_adam_matches_torch(ops):
+    """ops.NativeAdam (cg_adam: every variable in one launch, step count on the device) against torch.optim.Adam over
+    several steps and tensor sizes (one not a multiple of 4, one larger than a block's stride)."""
+    torch.manual_seed(5)
+    shapes = [(7,), (33, 5), (128, 64), (1, 1), (700, 1001)]
+    ps = [torch.randn(s, device='cuda').requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    mine, ref = ops.NativeAdam(ps, lr=3e-3), torch.optim.Adam(qs, lr=3e-3)
+    for it in range(7):
+        gs = [torch.randn(s, device='cuda') * (0.1 + it) for s in shapes]
+        for p, q, g in zip(ps, qs, gs):
+            p.grad, q.grad = g.clone(), g.clone()
+        mine.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-5, atol=2e-6)
+    assert int(mine.state[ps[0]]['step_state'][0]) == 7 and int(mine.state[ps[0]]['step_state'][1]) == 0
+
+
 def test_linear_layer_gradients(ops):
     torch.manual_seed(3)
     x = torch.randn(64, 200, device='cuda', requires_grad=True)
