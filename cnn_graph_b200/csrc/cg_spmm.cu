@@ -600,84 +600,93 @@ k_basis_onchip(const float2 *__restrict__ ell_g, const int *__restrict__ rowptr,
     const int tid = threadIdx.x;
     const int lane = tid % LPR;
     const int row0 = tid / LPR;
-    const int64_t cbase = (int64_t)blockIdx.x * CW + lane * 4;
-    const bool cvalid = cbase < C;              // C % 4 == 0 -> the whole float4 is in range
     const int64_t slab = (int64_t)M * C;
 
-    // global element offsets of the thread's four columns at m = 0, and the stride between vertices
-    int64_t o[4];
-    int64_t rs;
-    bool vec;                                   // the four columns are contiguous and 16-byte aligned
-    if (SM) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t c = cbase + i, n = c / F, f = c - n * F;
-            o[i] = n * (int64_t)M * F + f;
-        }
-        rs = F;
-        vec = (F % 4) == 0;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = cbase + i;
-        rs = C;
-        vec = true;
-    }
-    auto gload = [&](const float *base, int m) {
-        if (vec) return *reinterpret_cast<const float4 *>(base + o[0] + (int64_t)m * rs);
-        return make_float4(base[o[0] + (int64_t)m * rs], base[o[1] + (int64_t)m * rs], base[o[2] + (int64_t)m * rs],
-                           base[o[3] + (int64_t)m * rs]);
-    };
-    auto gstore = [&](float *base, int m, const float4 v) {
-        if (vec) {
-            *reinterpret_cast<float4 *>(base + o[0] + (int64_t)m * rs) = v;
-        } else {
-            base[o[0] + (int64_t)m * rs] = v.x;
-            base[o[1] + (int64_t)m * rs] = v.y;
-            base[o[2] + (int64_t)m * rs] = v.z;
-            base[o[3] + (int64_t)m * rs] = v.w;
-        }
-    };
-
+    // the operator is staged once per CTA; the CTA then walks its column groups (persistent when there are more groups
+    // than SMs: the gate filters of the gconv-LSTM have N * H / CW = 800 groups, and 800 CTAs each staging the 78 KB
+    // operator for a 32 KB tile spent most of their time on it -- 70 us per launch)
     for (int i = tid; i < width * m_pad; i += kOnchipThreads) ell[i] = ell_g[i];
     for (int m = tid; m < m_pad; m += kOnchipThreads) len[m] = m < M ? rowptr[m + 1] - rowptr[m] : 0;
-    for (int m = row0; m < M; m += RPP) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cvalid) v = gload(in, m);
-        *reinterpret_cast<float4 *>(S0 + m * CW + lane * 4) = v;
-        if (write_slab0 && cvalid) gstore(stack, m, v);
-    }
-    __syncthreads();
 
-    float *prev = S0, *cur = S1;                // cur holds X_{k-2} and receives X_k
-    for (int k = 1; k < K; ++k) {
-        float *dst = stack + (int64_t)k * slab;
+    const int64_t ngroups = (C + CW - 1) / CW;
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t cbase = grp * CW + lane * 4;
+        const bool cvalid = cbase < C;              // C % 4 == 0 -> the whole float4 is in range
+
+        // global element offsets of the thread's four columns at m = 0, and the stride between vertices
+        int64_t o[4];
+        int64_t rs;
+        bool vec;                                   // the four columns are contiguous and 16-byte aligned
+        if (SM) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t c = cbase + i, n = c / F, f = c - n * F;
+                o[i] = n * (int64_t)M * F + f;
+            }
+            rs = F;
+            vec = (F % 4) == 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = cbase + i;
+            rs = C;
+            vec = true;
+        }
+        auto gload = [&](const float *base, int m) {
+            if (vec) return *reinterpret_cast<const float4 *>(base + o[0] + (int64_t)m * rs);
+            return make_float4(base[o[0] + (int64_t)m * rs], base[o[1] + (int64_t)m * rs], base[o[2] + (int64_t)m * rs],
+                               base[o[3] + (int64_t)m * rs]);
+        };
+        auto gstore = [&](float *base, int m, const float4 v) {
+            if (vec) {
+                *reinterpret_cast<float4 *>(base + o[0] + (int64_t)m * rs) = v;
+            } else {
+                base[o[0] + (int64_t)m * rs] = v.x;
+                base[o[1] + (int64_t)m * rs] = v.y;
+                base[o[2] + (int64_t)m * rs] = v.z;
+                base[o[3] + (int64_t)m * rs] = v.w;
+            }
+        };
+
+        // (the previous group's last step ended with a barrier: nobody reads S0 / S1 any more)
         for (int m = row0; m < M; m += RPP) {
-            const int n = len[m];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int j = 0;
-            for (; j + 1 < n; j += 2) {
-                const float2 e0 = ell[j * m_pad + m];
-                const float2 e1 = ell[(j + 1) * m_pad + m];
-                const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
-                const float4 x1 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e1.y) * CW + lane * 4);
-                fma_acc(acc, e0.x, x0);
-                fma_acc(acc, e1.x, x1);
-            }
-            if (j < n) {
-                const float2 e0 = ell[j * m_pad + m];
-                const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
-                fma_acc(acc, e0.x, x0);
-            }
-            float4 *slot = reinterpret_cast<float4 *>(cur + m * CW + lane * 4);
-            float4 r = acc;
-            if (k > 1) r = axmb(2.0f, acc, *slot);
-            *slot = r;
-            if (cvalid) gstore(dst, m, r);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cvalid) v = gload(in, m);
+            *reinterpret_cast<float4 *>(S0 + m * CW + lane * 4) = v;
+            if (write_slab0 && cvalid) gstore(stack, m, v);
         }
         __syncthreads();
-        float *t = prev;
-        prev = cur;
-        cur = t;
+
+        float *prev = S0, *cur = S1;                // cur holds X_{k-2} and receives X_k
+        for (int k = 1; k < K; ++k) {
+            float *dst = stack + (int64_t)k * slab;
+            for (int m = row0; m < M; m += RPP) {
+                const int n = len[m];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int j = 0;
+                for (; j + 1 < n; j += 2) {
+                    const float2 e0 = ell[j * m_pad + m];
+                    const float2 e1 = ell[(j + 1) * m_pad + m];
+                    const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e1.y) * CW + lane * 4);
+                    fma_acc(acc, e0.x, x0);
+                    fma_acc(acc, e1.x, x1);
+                }
+                if (j < n) {
+                    const float2 e0 = ell[j * m_pad + m];
+                    const float4 x0 = *reinterpret_cast<const float4 *>(prev + __float_as_int(e0.y) * CW + lane * 4);
+                    fma_acc(acc, e0.x, x0);
+                }
+                float4 *slot = reinterpret_cast<float4 *>(cur + m * CW + lane * 4);
+                float4 r = acc;
+                if (k > 1) r = axmb(2.0f, acc, *slot);
+                *slot = r;
+                if (cvalid) gstore(dst, m, r);
+            }
+            __syncthreads();
+            float *t = prev;
+            prev = cur;
+            cur = t;
+        }
     }
 }
 
@@ -703,7 +712,7 @@ static int launch_onchip(const cg_graph *g, const CgCsr &L, const float *in, flo
     const size_t smem = (size_t)L.width * L.m_pad * sizeof(float2) + (size_t)L.m_pad * sizeof(int) +
                         2 * (size_t)g->M * CW * sizeof(float);
     CG_CHECK_CUDA(cudaFuncSetAttribute(k_basis_onchip<CW, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)cg_ceil_div(C, CW);
+    const unsigned grid = (unsigned)std::min<int64_t>(cg_ceil_div(C, CW), g->sm_count);       // persistent over the column groups
     CgProfScope prof("basis_onchip", s);
     k_basis_onchip<CW, SM><<<grid, kOnchipThreads, smem, s>>>(L.ell, L.rowptr, L.width, L.m_pad, g->M, in, stack, C, K,
                                                               write_slab0, F);
