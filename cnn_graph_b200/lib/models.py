@@ -279,7 +279,7 @@ class cgcnn(GraphConvOps, GraphModel):
                 fused_layer = self._fused_first_layer(x, i)          # declares the same variables in the same scopes
                 if fused_layer is not None:
                     x = fused_layer
-                    self.nets['conv{}/pooling'.format(i + 1)] = x
+                    self.nets['conv{}/pooling'.format(i + 1)] = x.detach()
                     continue
                 # upstream wraps the three blocks in tf.name_scope('filter' / 'bias_relu' / 'pooling'), which does not
                 # prefix variables: they are conv{i}/weights and conv{i}/bias
@@ -287,9 +287,11 @@ class cgcnn(GraphConvOps, GraphModel):
                 fused = self._fused_brelu_pool(x, self.p[i])
                 if fused is None:
                     x = self.brelu(x)
-                    self.nets['conv{}/bias_relu'.format(i + 1)] = x     # like self.nets[x.name] = x in the fork
+                    self.nets['conv{}/bias_relu'.format(i + 1)] = x.detach()    # like self.nets[x.name] = x in the fork: values only --
+                    # a tensor with its autograd graph would keep the previous step's AccumulateGrad nodes (and the stream they
+                    # were created on) alive into the next step, which breaks CUDA-graph capture of the step now and then
                 x = fused if fused is not None else self.pool(x, self.p[i])
-                self.nets['conv{}/pooling'.format(i + 1)] = x
+                self.nets['conv{}/pooling'.format(i + 1)] = x.detach()
         N, Mv, Fv = (int(d) for d in x.shape)
         x = x.reshape(N, Mv * Fv)
         hook = getattr(self, 'grad_hook', None)
@@ -298,7 +300,7 @@ class cgcnn(GraphConvOps, GraphModel):
         for i, width in enumerate(self.M[:-1]):
             with self.variable_scope('fc{}'.format(i + 1)):
                 x = self.fc(x, width)
-                self.nets['fc{}'.format(i + 1)] = x
+                self.nets['fc{}'.format(i + 1)] = x.detach()
                 if self.is_train and 0 < dropout < 1 and not x.is_meta:
                     x = torch.nn.functional.dropout(x, p=1 - dropout, training=True)
         with self.variable_scope('logits'):
