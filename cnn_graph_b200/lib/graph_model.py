@@ -132,7 +132,9 @@ class GraphModel(object):
             hook.set_lr(self.optimizer.param_groups[0]['lr'])
         self.global_step += 1
         self.is_train = False
-        return loss
+        # the value only: a loss that still heads its autograd graph keeps the step's AccumulateGrad nodes (and the stream
+        # they were created on) alive for as long as the caller holds it -- into the capture of a later step
+        return loss.detach()
 
     # ------------------------------------------------------------------ captured step / pipelined feeding
     def train_step_graphed(self, batch_data, batch_labels):

@@ -2,7 +2,7 @@
 # C5 row partition at N GPUs (gpurun --gpus N): peer-memory halo exchange vs the all-to-all collective
 N=${1:-2}; TAG=${2:-r2}
 i=0
-for ex in peer collective; do i=$((i+1))
+for ex in ${3:-peer collective}; do i=$((i+1))
   CG_C5_EXCHANGE=$ex timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$i \
      bench.py --gpus $N --config c5 --no-cpu-baseline --steps 10 > gpurun_out/bench_c5_g${N}_${ex}_$TAG.json 2> gpurun_out/bench_c5_g${N}_${ex}_$TAG.err
   python - $ex gpurun_out/bench_c5_g${N}_${ex}_$TAG <<'PY'
