@@ -127,6 +127,10 @@ def step_work(config, L, N):
         work['dw_thin'] = {'bound': 'hbm', 'bytes': 4.0 * N * l['M'] * l['K'] + gy_b, 'flops': g1}
         if not wide:
             work['spmm_step'] = {'bound': 'hbm', 'bytes': common.b_step(l['M'], l['nnz'], N), 'flops': 0}
+        # short-reduction kernels (cg_thin.cu, K * Fin <= 16): the basis slabs and the [N M, Fout] tensor, once
+        tb = 4.0 * N * l['M'] * (l['K'] + l['Fout'])
+        work['thin_contract'] = {'bound': 'hbm', 'bytes': tb, 'flops': g1}
+        work['thin_dw'] = {'bound': 'hbm', 'bytes': tb, 'flops': g1}
     # dense head: fc layers forward + both gradients, fp32-equivalent flops against the dense bf16 peak
     widths = [layers[-1]['M'] // layers[-1]['p'] * layers[-1]['Fout']] + list(cfg['M'])
     fc = [2.0 * N * a * b for a, b in zip(widths[:-1], widths[1:])]
