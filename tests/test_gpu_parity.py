@@ -146,6 +146,33 @@ def test_filter_forward_backward_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout,
     close(Wt.grad, dW)
 
 
+# short reductions (cg_thin.cu, K * Fin <= 16): every width of the register tile (Q = 2, 3, 4, 7 -> 8, 9 -> 12, 13 -> 16, 16),
+# scalar and 4-column lanes, ragged column groups, K = 1 (one "sample" of N * M rows), both stack layouts
+THIN_SHAPES = [(3, 9, 2, 40, 1), (3, 5, 3, 128, 1), (4, 12, 4, 20, 1), (3, 6, 1, 64, 7), (3, 4, 3, 132, 3), (4, 7, 13, 24, 1),
+               (3, 3, 4, 256, 4), (2, 70, 1, 32, 16), (1, 11, 2, 36, 5)]
+
+
+@pytest.mark.parametrize('flags', [0, 1])        # sample-major stack of the on-chip basis / vertex-major stack of the streaming steps
+@pytest.mark.parametrize('level,N,Fin,Fout,K', THIN_SHAPES)
+def test_short_reduction_filter_vs_oracle(ops, tf_ref, c2, level, N, Fin, Fout, K, flags):
+    L = csr_from(c2, 'L%d' % level)
+    M = L.shape[0]
+    rng = np.random.RandomState(7 * level + K + Fin)
+    x = rng.standard_normal((N, M, Fin)).astype(np.float32)
+    W = (0.1 * rng.standard_normal((Fin * K, Fout))).astype(np.float32)
+    gy = rng.standard_normal((N, M, Fout)).astype(np.float32)
+    for grad_x in (True, False):                 # without dx the weight gradient comes from the X stack (first layers)
+        xt = dev(x).requires_grad_(grad_x)
+        Wt = dev(W).requires_grad_(True)
+        y = ops.cheb_filter(xt, Wt, L, K, lmax=2, flags=flags, grad_x=grad_x)
+        close(y, tf_ref.chebyshev5(x, L, W, K))
+        y.backward(dev(gy))
+        dx, dW = tf_ref.chebyshev5_backward(x, L, W, K, gy)
+        close(Wt.grad, dW)
+        if grad_x:
+            close(xt.grad, dx)
+
+
 # shapes the fused recurrence+contraction (tcgen05) kernel must accept: (level, N, Fin, Fout, K)
 FUSED_SHAPES = [
     (2, 5, 32, 64, 25),      # C2 layer 2
