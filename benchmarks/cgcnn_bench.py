@@ -14,7 +14,7 @@ from .common import METRIC
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's numpy/scipy path restated in oracle/ (never touches cnn_graph_b200)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_training_steps(config, batch, steps, warmup, seed=0, keep_stack=True):
+def cpu_training_steps(config, batch, steps, warmup, seed=0, keep_stack=True, budget_s=None):
     from oracle import model_ref
     cfg = workloads.CGCNN[config]
     lib = workloads.host_lib('oracle')
@@ -29,6 +29,7 @@ def cpu_training_steps(config, batch, steps, warmup, seed=0, keep_stack=True):
     H = workloads.HYPER
     times = []
     loss = float('nan')
+    t_begin = time.perf_counter()
     for it in range(warmup + steps):
         masks = [(rng.uniform(size=(batch, m)) < H['dropout']).astype(np.float32) / H['dropout'] for m in cfg['M'][:-1]]
         t0 = time.perf_counter()
@@ -38,6 +39,8 @@ def cpu_training_steps(config, batch, steps, warmup, seed=0, keep_stack=True):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_begin > budget_s:
+            break               # bounded sample: the steps that fit the wall-clock budget (at least one timed step)
     return times, float(loss)
 
 
@@ -62,7 +65,8 @@ def run_reference(args, config):
         return
     cfg = workloads.CGCNN[config]
     batch = args.batch or cfg['batch']
-    times, _ = cpu_training_steps(config, batch, args.steps, args.warmup)
+    # a CPU step of the C2 batch takes seconds: at most two warm-up steps, and the timed steps that fit ~2.5 minutes
+    times, _ = cpu_training_steps(config, batch, args.steps, min(args.warmup, 2), budget_s=150.0)
     total = float(np.sum(times))
     value = batch * len(times) / total
     line = {
@@ -75,7 +79,8 @@ def run_reference(args, config):
                            'the reference\'s sources, is timed; graphs are built with oracle/ too (no product library is '
                            'loaded); the backward reuses the forward\'s Chebyshev stack as TF autodiff does'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
-                         'sample': '%d steps of batch %d (full train step: fwd+loss+bwd+update)' % (len(times), batch)},
+                         'sample': '%d timed steps of batch %d (full train step: fwd+loss+bwd+update; of %d requested, bounded to '
+                                   '150 s of wall clock)' % (len(times), batch, args.steps)},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
